@@ -1,0 +1,770 @@
+// C ABI of libccvm_b200.so (see include/ccvm_b200.h) and the small kernels around the
+// persistent SDE kernel: schedule builder, fused epilogue (change of variables, projected
+// GD / Adam post-processing, BoxQP energy), solution statistics, scaling factor, FP32 probe.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/ccvm_b200.h"
+#include "sde_kernel.cuh"
+
+using namespace ccvm;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return fail(CCVM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char* ccvm_last_error(void) { return g_err; }
+extern "C" int ccvm_abi_version(void) { return CCVM_ABI_VERSION; }
+
+struct DeviceInfo {
+  int device = -1, sms = 0, max_smem = 0;
+};
+static int device_info(DeviceInfo& di) {
+  static thread_local DeviceInfo cache;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (cache.device != dev) {
+    int sms = 0, smem = 0, major = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10)
+      return fail(CCVM_E_CUDA, "ccvm_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+    cache.device = dev;
+    cache.sms = sms;
+    cache.max_smem = smem;
+  }
+  di = cache;
+  return CCVM_OK;
+}
+
+// ------------------------------------------------------------------- schedule builder
+// The reference evaluates its per-iteration schedules (pump ramp, noise-ratio decay,
+// measurement-strength decay, Adam bias corrections) as fp64 host scalars
+// (dl_solver.py:523-527,704,715; mf_solver.py:550-559; pumped_langevin_solver.py:278-283).
+// They are evaluated here once, in fp64, on the device, and rounded to fp32 per use.
+struct SchedArgs {
+  int solver, adam, iterations, flag;
+  double pump, dt, noise_ratio, j, fs, g, beta1, beta2;
+};
+
+__global__ void build_schedule_kernel(SchedArgs a, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.iterations) return;
+  const double t = (double)(i + 1), T = (double)a.iterations;
+  const double rate = a.flag ? t / T : 1.0;
+  const double decay = exp(-t / T * 3.0);
+  float r[SCHED_W] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.solver == SOLVER_DL) {
+    const double ratio = (a.noise_ratio - 1.0) * decay + 1.0;
+    const double p = a.pump * rate;  // == pump*(i+1)/T when the flag is set, else pump
+    r[SC_A] = (float)(a.adam ? a.dt : a.dt * a.fs * (0.5 + rate));
+    r[SC_P1] = (float)(a.dt * (-1.0 + p));
+    r[SC_P2] = (float)(a.dt * (-1.0 - p));
+    r[SC_N1] = (float)(2.0 * a.g * sqrt(a.dt) * ratio);
+    r[SC_N2] = (float)(2.0 * a.g * sqrt(a.dt) / ratio);
+  } else if (a.solver == SOLVER_MF) {
+    const double ji = a.j * decay;
+    r[SC_A] = (float)(sqrt(1.0 / (4.0 * ji)) / sqrt(a.dt));
+    r[SC_P1] = (float)(a.pump * rate);
+    r[SC_P2] = (float)ji;
+    r[SC_N1] = (float)(sqrt(ji) / sqrt(a.dt));
+    r[SC_N2] = (float)(1.0 + ji);
+  } else if (a.solver == SOLVER_PLV) {
+    r[SC_P1] = (float)(a.dt * (a.pump * rate - 1.0));
+  }
+  if (a.adam) {
+    r[SC_IB1] = (float)(1.0 / (1.0 - pow(a.beta1, t)));
+    r[SC_IB2] = a.beta2 == 1.0 ? 0.f : (float)(1.0 / (1.0 - pow(a.beta2, t)));
+  }
+  float4* o = reinterpret_cast<float4*>(out + (size_t)i * SCHED_W);
+  o[0] = make_float4(r[0], r[1], r[2], r[3]);
+  o[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+
+// ------------------------------------------------------------------------ launch plan
+struct LaunchPlan {
+  int tb, rg, cg, xs, threads, ctas, use_tma;
+  size_t smem;
+};
+
+static size_t sde_smem_bytes(int np, int xs) {
+  return ((size_t)np * np * 2 + (size_t)2 * np * xs + 2 * (size_t)np) * sizeof(float) + 16;
+}
+
+static int plan_launch(const ccvm_solve_desc& d, const DeviceInfo& di, LaunchPlan& L) {
+  const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1;
+  const int cg = (d.n + 3) / 4, np = 4 * cg;
+  if (cg > 256) return fail(CCVM_E_TOO_LARGE, "n=%d exceeds the SIMT path (n <= 1024)", d.n);
+  const int share = (d.batch + di.sms - 1) / di.sms;
+  int tb = 4;
+  if (d.solver != CCVM_SOLVER_DL && share >= 64) tb = 8;
+  if (((share + tb - 1) / tb) * cg < 64) tb = 2;
+  if (const char* e = getenv("CCVM_TB")) {
+    const int v = atoi(e);
+    if (v == 2 || v == 4 || (v == 8 && d.solver != CCVM_SOLVER_DL)) tb = v;
+  }
+  int rg = (share + tb - 1) / tb;
+  if (const char* e = getenv("CCVM_RG")) {
+    const int v = atoi(e);
+    if (v > 0) rg = v;
+  }
+  if (rg < 1) rg = 1;
+  if (rg > 256 / cg) rg = 256 / cg;
+  auto xs_of = [&](int r) { return ((K * r * tb + 7) / 8) * 8 + 32; };
+  while (rg > 1 && sde_smem_bytes(np, xs_of(rg)) > (size_t)di.max_smem) --rg;
+  const size_t smem = sde_smem_bytes(np, xs_of(rg));
+  if (smem > (size_t)di.max_smem)
+    return fail(CCVM_E_TOO_LARGE, "n=%d needs %zu B of shared memory (> %d): use the large-n path", d.n, smem,
+                di.max_smem);
+  L.tb = tb;
+  L.rg = rg;
+  L.cg = cg;
+  L.xs = xs_of(rg);
+  L.threads = ((rg * cg + 31) / 32) * 32;
+  L.ctas = (d.batch + rg * tb - 1) / (rg * tb);
+  L.smem = smem;
+  const size_t qbytes = (size_t)d.n * d.n * 4;
+  L.use_tma = (qbytes % 16 == 0) && (((uintptr_t)d.q) % 16 == 0) && (qbytes <= (size_t)2 * np * L.xs * 4);
+  if (getenv("CCVM_NO_TMA")) L.use_tma = 0;
+  return CCVM_OK;
+}
+
+template <int SOLVER, bool ADAM, int TB>
+static int launch_one(const SdeParams& p, const LaunchPlan& L, cudaStream_t st) {
+  auto kern = sde_kernel<SOLVER, ADAM, TB>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
+  kern<<<L.ctas, L.threads, L.smem, st>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+template <int SOLVER, bool ADAM>
+static int launch_tb(const SdeParams& p, const LaunchPlan& L, cudaStream_t st) {
+  switch (L.tb) {
+    case 2: return launch_one<SOLVER, ADAM, 2>(p, L, st);
+    case 4: return launch_one<SOLVER, ADAM, 4>(p, L, st);
+    case 8:
+      if constexpr (SOLVER != SOLVER_DL) return launch_one<SOLVER, ADAM, 8>(p, L, st);
+  }
+  return fail(CCVM_E_INVALID, "unsupported trajectory tile %d", L.tb);
+}
+
+template <int SOLVER, bool ADAM, int TB>
+static int regs_one() {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, sde_kernel<SOLVER, ADAM, TB>) != cudaSuccess) return -1;
+  return fa.numRegs;
+}
+
+static int validate_solve(const ccvm_solve_desc* d) {
+  if (!d) return fail(CCVM_E_INVALID, "null descriptor");
+  if (d->solver < 0 || d->solver > 3) return fail(CCVM_E_INVALID, "unknown solver id %d", d->solver);
+  if (d->algorithm != CCVM_ALG_ORIGINAL && d->algorithm != CCVM_ALG_ADAM)
+    return fail(CCVM_E_INVALID, "unknown algorithm id %d", d->algorithm);
+  if (d->n < 1 || d->batch < 1 || d->iterations < 1)
+    return fail(CCVM_E_INVALID, "n, batch and iterations must be >= 1 (got %d, %d, %d)", d->n, d->batch, d->iterations);
+  if (!d->q || !d->v || !d->out0) return fail(CCVM_E_INVALID, "q, v and out0 are required");
+  if (d->solver == CCVM_SOLVER_DL && !d->out1) return fail(CCVM_E_INVALID, "DL needs out1 (s)");
+  if (d->solver == CCVM_SOLVER_MF && (!d->out1 || !d->out2)) return fail(CCVM_E_INVALID, "MF needs out1 and out2");
+  if (!(d->upper > d->lower)) return fail(CCVM_E_INVALID, "solution bounds must satisfy lower < upper");
+  if (d->rng_mode == CCVM_RNG_REPLAY) {
+    if (!d->noise) return fail(CCVM_E_INVALID, "replay mode needs a noise tensor");
+    if (d->noise_batch < d->traj_base + d->batch) return fail(CCVM_E_INVALID, "noise tensor is too small for the batch");
+  } else if (d->rng_mode != CCVM_RNG_PHILOX) {
+    return fail(CCVM_E_INVALID, "unknown rng mode %d", d->rng_mode);
+  }
+  if (d->evolution_step > 0 && (!d->samples || d->num_samples < 1))
+    return fail(CCVM_E_INVALID, "evolution sampling needs a samples buffer");
+  return CCVM_OK;
+}
+
+// Resolve which S the drift and the clamp see:
+//   DL  _solve      drift S = sqrt(pump-1) if pump>1 else 1 ; final clamp = the S handed in
+//   DL  _solve_adam S := sqrt(pump-1) if pump>1 (drift AND clamp) else the S handed in
+//   MF / Langevin / PumpedLangevin: the S handed in everywhere
+static void resolve_saturation(const ccvm_solve_desc& d, SdeParams& p) {
+  p.drift_s_vec = d.s_vec;
+  p.clamp_s_vec = d.s_vec;
+  p.drift_s = (float)d.s;
+  p.clamp_s = (float)d.s;
+  if (d.solver == CCVM_SOLVER_DL) {
+    const bool pumped = d.pump > 1.0;
+    const double sp = pumped ? sqrt(d.pump - 1.0) : 1.0;
+    if (d.algorithm == CCVM_ALG_ORIGINAL) {
+      p.drift_s_vec = nullptr;
+      p.drift_s = (float)sp;
+    } else if (pumped) {
+      p.drift_s_vec = p.clamp_s_vec = nullptr;
+      p.drift_s = p.clamp_s = (float)sp;
+    }
+  }
+}
+
+extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
+  int rc = validate_solve(d);
+  if (rc) return rc;
+  DeviceInfo di;
+  if ((rc = device_info(di))) return rc;
+  LaunchPlan L;
+  if ((rc = plan_launch(*d, di, L))) return rc;
+  info5[0] = L.threads;
+  info5[1] = L.ctas;
+  info5[2] = L.rg * L.tb;
+  info5[3] = (int)L.smem;
+  int regs = -1;
+  const bool ad = d->algorithm == CCVM_ALG_ADAM;
+#define REGS_CASE(S)                                                                             \
+  if (d->solver == S) {                                                                          \
+    if (L.tb == 2) regs = ad ? regs_one<S, true, 2>() : regs_one<S, false, 2>();                 \
+    if (L.tb == 4) regs = ad ? regs_one<S, true, 4>() : regs_one<S, false, 4>();                 \
+  }
+  REGS_CASE(SOLVER_DL) REGS_CASE(SOLVER_MF) REGS_CASE(SOLVER_LV) REGS_CASE(SOLVER_PLV)
+#undef REGS_CASE
+  if (L.tb == 8) {
+    if (d->solver == SOLVER_MF) regs = ad ? regs_one<SOLVER_MF, true, 8>() : regs_one<SOLVER_MF, false, 8>();
+    if (d->solver == SOLVER_LV) regs = ad ? regs_one<SOLVER_LV, true, 8>() : regs_one<SOLVER_LV, false, 8>();
+    if (d->solver == SOLVER_PLV) regs = ad ? regs_one<SOLVER_PLV, true, 8>() : regs_one<SOLVER_PLV, false, 8>();
+  }
+  info5[4] = regs;
+  return CCVM_OK;
+}
+
+extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
+  int rc = validate_solve(d);
+  if (rc) return rc;
+  DeviceInfo di;
+  if ((rc = device_info(di))) return rc;
+  LaunchPlan L;
+  if ((rc = plan_launch(*d, di, L))) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool adam = d->algorithm == CCVM_ALG_ADAM;
+
+  float* sched = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&sched, (size_t)d->iterations * SCHED_W * sizeof(float), st));
+  SchedArgs sa;
+  sa.solver = d->solver;
+  sa.adam = adam;
+  sa.iterations = d->iterations;
+  sa.flag = d->solver == CCVM_SOLVER_LANGEVIN ? 0 : (d->pump_rate_flag != 0);
+  sa.pump = d->pump;
+  sa.dt = d->dt;
+  sa.noise_ratio = d->noise_ratio;
+  sa.j = d->j;
+  sa.fs = d->feedback_scale;
+  sa.g = d->g;
+  sa.beta1 = d->beta1;
+  sa.beta2 = d->beta2;
+  build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(sa, sched);
+  CUDA_TRY(cudaGetLastError());
+
+  SdeParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = d->q;
+  p.v = d->v;
+  resolve_saturation(*d, p);
+  p.sched = sched;
+  p.noise = d->rng_mode == CCVM_RNG_REPLAY ? d->noise : nullptr;
+  p.noise_batch = d->noise_batch;
+  p.traj_base = d->traj_base;
+  p.out0 = d->out0;
+  p.out1 = d->out1;
+  p.out2 = d->out2;
+  p.samples = d->evolution_step > 0 ? d->samples : nullptr;
+  p.evolution_step = d->evolution_step > 0 ? d->evolution_step : 0;
+  p.num_samples = d->num_samples;
+  p.n = d->n;
+  p.batch = d->batch;
+  p.iterations = d->iterations;
+  p.rg = L.rg;
+  p.cg = L.cg;
+  p.xs = L.xs;
+  p.use_tma = L.use_tma;
+  p.a_half = (float)((d->upper - d->lower) * 0.5);
+  p.b_half = (float)((d->upper + d->lower) * 0.5);
+  p.dt = (float)d->dt;
+  p.fs = (float)d->feedback_scale;
+  p.g2 = (float)(d->g * d->g);
+  p.sig = (float)(d->sigma * sqrt(d->dt));
+  p.dtfs = (float)(d->dt * d->feedback_scale);
+  p.beta1 = (float)d->beta1;
+  p.beta2 = (float)d->beta2;
+  p.omb1 = (float)(1.0 - d->beta1);
+  p.omb2 = (float)(1.0 - d->beta2);
+  p.adam_alpha = (float)d->alpha;
+  p.add_assign = d->add_assign != 0;
+  p.beta2_is_one = d->beta2 == 1.0;
+  p.seed_lo = (uint32_t)d->seed;
+  p.seed_hi = (uint32_t)(d->seed >> 32);
+  p.off_lo = (uint32_t)d->offset;
+  p.off_hi = (uint32_t)(d->offset >> 32);
+
+  switch (d->solver * 2 + (adam ? 1 : 0)) {
+    case 0: rc = launch_tb<SOLVER_DL, false>(p, L, st); break;
+    case 1: rc = launch_tb<SOLVER_DL, true>(p, L, st); break;
+    case 2: rc = launch_tb<SOLVER_MF, false>(p, L, st); break;
+    case 3: rc = launch_tb<SOLVER_MF, true>(p, L, st); break;
+    case 4: rc = launch_tb<SOLVER_LV, false>(p, L, st); break;
+    case 5: rc = launch_tb<SOLVER_LV, true>(p, L, st); break;
+    case 6: rc = launch_tb<SOLVER_PLV, false>(p, L, st); break;
+    default: rc = launch_tb<SOLVER_PLV, true>(p, L, st); break;
+  }
+  cudaError_t fe = cudaFreeAsync(sched, st);
+  if (rc) return rc;
+  if (fe != cudaSuccess) return fail(CCVM_E_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(fe));
+  return CCVM_OK;
+}
+
+// ------------------------------------------------------------------------- epilogue
+// One warp walks one trajectory at a time; lanes own variables j = lane, lane+32, ...
+// The working vector x lives in a per-warp shared buffer; Q is staged in shared memory with an
+// odd leading dimension (row and column sweeps are both conflict-free) when it fits, else read
+// through L2.  The objective is reduced with warp shuffles.
+struct EpiParams {
+  const float* q;
+  const float* v;
+  const float* state;
+  const float* m1vec;
+  const float* m2vec;
+  float* pv;
+  float* energy;
+  int n, batch, ld, q_in_smem;
+  int map1, map2, pp, pp_iters;
+  float m1s, m1o, m2s, m2o, step, lo, hi, scaled_by;
+};
+
+constexpr int EPI_WARPS = 8;
+
+__global__ void __launch_bounds__(EPI_WARPS * 32) epilogue_kernel(const EpiParams p) {
+  extern __shared__ __align__(16) float esm[];
+  const int N = p.n, LD = p.ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* qs = esm;
+  float* xbuf = esm + (p.q_in_smem ? (size_t)N * LD : 0) + (size_t)warp * 2 * N;
+  const float* Q = p.q;
+  int ld = N;
+  if (p.q_in_smem) {
+    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+      const int i = idx / N, j = idx - i * N;
+      qs[i * LD + j] = p.q[idx];
+    }
+    Q = qs;
+    ld = LD;
+  }
+  __syncthreads();
+
+  for (int b = blockIdx.x * EPI_WARPS + warp; b < p.batch; b += gridDim.x * EPI_WARPS) {
+    float* x = xbuf;
+    float* y = xbuf + N;
+    for (int j = lane; j < N; j += 32) {
+      float val = p.state[(size_t)b * N + j];
+      if (p.map1) val = val * (p.m1vec ? p.m1vec[j] : p.m1s) + p.m1o;
+      x[j] = val;
+    }
+    __syncwarp();
+    if (p.pp == CCVM_PP_GRAD_DESCENT) {
+      // x <- clamp(x - step (xQ + V), lo, hi), all variables from the OLD x (grad_descent.py:61-64)
+      for (int it = 0; it < p.pp_iters; ++it) {
+        for (int j = lane; j < N; j += 32) {
+          float acc = 0.f;
+          for (int i = 0; i < N; ++i) acc = fmaf(x[i], Q[i * ld + j], acc);
+          const float g = acc + p.v[j];
+          y[j] = fminf(fmaxf(x[j] + (-p.step) * g, p.lo), p.hi);
+        }
+        __syncwarp();
+        float* tmp = x;
+        x = y;
+        y = tmp;
+      }
+    } else if (p.pp == CCVM_PP_ADAM) {
+      // one torch.optim.Adam step on 1/2 xQx + Vx then clamp (adam.py:58-66):
+      // g = 1/2 (xQ + x Q^T) + V ; x <- clamp(x - lr * (m/(1-b1)) / (sqrt(v/(1-b2)) + eps))
+      for (int j = lane; j < N; j += 32) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = 0; i < N; ++i) {
+          a1 = fmaf(x[i], Q[i * ld + j], a1);
+          a2 = fmaf(x[i], Q[j * ld + i], a2);
+        }
+        const float g = 0.5f * (a1 + a2) + p.v[j];
+        const float m = (1.f - 0.9f) * g, vv = (1.f - 0.99f) * g * g;
+        const float den = sqrtf(vv) / sqrtf(1.f - 0.99f) + 1e-8f;
+        y[j] = fminf(fmaxf(x[j] - (p.step / (1.f - 0.9f)) * (m / den), p.lo), p.hi);
+      }
+      __syncwarp();
+      float* tmp = x;
+      x = y;
+      y = tmp;
+    }
+    if (p.pv)
+      for (int j = lane; j < N; j += 32) p.pv[(size_t)b * N + j] = x[j];
+    if (p.energy) {
+      if (p.map2) {
+        for (int j = lane; j < N; j += 32) y[j] = x[j] * (p.m2vec ? p.m2vec[j] : p.m2s) + p.m2o;
+        __syncwarp();
+        x = y;
+      }
+      // E = (1/2 x Q x + V x) * scaled_by   (problem_instance.py:226-241)
+      float e1 = 0.f, e2 = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        float acc = 0.f;
+        for (int i = 0; i < N; ++i) acc = fmaf(x[i], Q[i * ld + j], acc);
+        e1 = fmaf(acc, x[j], e1);
+        e2 = fmaf(p.v[j], x[j], e2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+        e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+      }
+      if (lane == 0) p.energy[b] = 0.5f * (e1 * p.scaled_by) + e2 * p.scaled_by;
+    }
+    __syncwarp();
+  }
+}
+
+static int run_epilogue(const EpiParams& p0, cudaStream_t st) {
+  EpiParams p = p0;
+  DeviceInfo di;
+  int rc = device_info(di);
+  if (rc) return rc;
+  p.ld = p.n | 1;
+  size_t xb = (size_t)EPI_WARPS * 2 * p.n * sizeof(float);
+  size_t qb = (size_t)p.n * p.ld * sizeof(float);
+  p.q_in_smem = (qb + xb) <= (size_t)di.max_smem;
+  const size_t smem = xb + (p.q_in_smem ? qb : 0);
+  if (smem > (size_t)di.max_smem) return fail(CCVM_E_TOO_LARGE, "n=%d too large for the epilogue kernel", p.n);
+  CUDA_TRY(cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = (p.batch + EPI_WARPS - 1) / EPI_WARPS;
+  if (grid > 2 * di.sms) grid = 2 * di.sms;
+  epilogue_kernel<<<grid, EPI_WARPS * 32, smem, st>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+extern "C" int ccvm_epilogue(const ccvm_epilogue_desc* d, void* stream) {
+  if (!d) return fail(CCVM_E_INVALID, "null descriptor");
+  if (d->n < 1 || d->batch < 1) return fail(CCVM_E_INVALID, "n and batch must be >= 1");
+  if (!d->q || !d->v || !d->state) return fail(CCVM_E_INVALID, "q, v and state are required");
+  if (d->post_processor < CCVM_PP_NONE || d->post_processor > CCVM_PP_ADAM)
+    return fail(CCVM_E_INVALID, "unknown post-processor id %d", d->post_processor);
+  EpiParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = d->q;
+  p.v = d->v;
+  p.state = d->state;
+  p.m1vec = d->map1_scale_vec;
+  p.m2vec = d->map2_scale_vec;
+  p.pv = d->problem_variables;
+  p.energy = d->energy;
+  p.n = d->n;
+  p.batch = d->batch;
+  p.map1 = d->apply_map1 != 0;
+  p.map2 = d->apply_map2 != 0;
+  p.pp = d->post_processor;
+  p.pp_iters = d->pp_iterations;
+  p.m1s = (float)d->map1_scale;
+  p.m1o = (float)d->map1_shift;
+  p.m2s = (float)d->map2_scale;
+  p.m2o = (float)d->map2_shift;
+  p.step = (float)d->pp_step;
+  p.lo = (float)d->pp_lower;
+  p.hi = (float)d->pp_upper;
+  p.scaled_by = (float)d->scaled_by;
+  return run_epilogue(p, (cudaStream_t)stream);
+}
+
+extern "C" int ccvm_compute_energy(const float* x, const float* q, const float* v, double scaled_by,
+                                   int32_t batch, int32_t n, float* energy, void* stream) {
+  if (!x || !q || !v || !energy || batch < 1 || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_compute_energy");
+  EpiParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q;
+  p.v = v;
+  p.state = x;
+  p.energy = energy;
+  p.n = n;
+  p.batch = batch;
+  p.scaled_by = (float)scaled_by;
+  return run_epilogue(p, (cudaStream_t)stream);
+}
+
+extern "C" int ccvm_postprocess_grad_descent(float* x, const float* q, const float* v, int32_t batch,
+                                             int32_t n, int32_t iterations, double step_size, double lower,
+                                             double upper, void* stream) {
+  if (!x || !q || !v || batch < 1 || n < 1 || iterations < 0)
+    return fail(CCVM_E_INVALID, "bad argument to ccvm_postprocess_grad_descent");
+  EpiParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q;
+  p.v = v;
+  p.state = x;
+  p.pv = x;
+  p.n = n;
+  p.batch = batch;
+  p.pp = CCVM_PP_GRAD_DESCENT;
+  p.pp_iters = iterations;
+  p.step = (float)step_size;
+  p.lo = (float)lower;
+  p.hi = (float)upper;
+  return run_epilogue(p, (cudaStream_t)stream);
+}
+
+extern "C" int ccvm_postprocess_adam(float* x, const float* q, const float* v, int32_t batch, int32_t n,
+                                     double lr, double lower, double upper, void* stream) {
+  if (!x || !q || !v || batch < 1 || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_postprocess_adam");
+  EpiParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = q;
+  p.v = v;
+  p.state = x;
+  p.pv = x;
+  p.n = n;
+  p.batch = batch;
+  p.pp = CCVM_PP_ADAM;
+  p.pp_iters = 1;
+  p.step = (float)lr;
+  p.lo = (float)lower;
+  p.hi = (float)upper;
+  return run_epilogue(p, (cudaStream_t)stream);
+}
+
+// -------------------------------------------------------------------- solution stats
+struct StatsOut {
+  float best;
+  int arg_best;
+  int counts[7];
+};
+
+__global__ void __launch_bounds__(1024) stats_kernel(const float* __restrict__ energy, int batch, float optimal,
+                                                     StatsOut* out) {
+  __shared__ float s_best[32];
+  __shared__ int s_arg[32];
+  __shared__ int s_cnt[7];
+  __shared__ int s_nan;
+  const float thr[7] = {0.1f, 1.f, 2.f, 3.f, 4.f, 5.f, 10.f};
+  if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_nan = 0;
+  __syncthreads();
+  float best = -INFINITY;
+  int arg = 0x7fffffff, cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+  bool saw_nan = false;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    const float val = -energy[b];
+    if (val != val) saw_nan = true;
+    if (val > best) {
+      best = val;
+      arg = b;
+    }
+    // gap = (optimal - val) * 100 / |val|   (solution.py:125-129), fp32 like the reference
+    const float gap = __fdiv_rn(__fmul_rn(__fsub_rn(optimal, val), 100.f), fabsf(val));
+#pragma unroll
+    for (int k = 0; k < 7; ++k) cnt[k] += (gap <= thr[k]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) {
+      best = ob;
+      arg = oa;
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
+  }
+  if (saw_nan) atomicOr(&s_nan, 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_best[warp] = best;
+    s_arg[warp] = arg;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) atomicAdd(&s_cnt[k], cnt[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float bb = s_best[0];
+    int ba = s_arg[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (s_best[w] > bb || (s_best[w] == bb && s_arg[w] < ba)) {
+        bb = s_best[w];
+        ba = s_arg[w];
+      }
+    out->best = s_nan ? NAN : bb;  // torch.max propagates NaN
+    out->arg_best = ba == 0x7fffffff ? 0 : ba;
+    for (int k = 0; k < 7; ++k) out->counts[k] = s_cnt[k];
+  }
+}
+
+extern "C" int ccvm_solution_stats(const float* energy, int32_t batch, double optimal_value, void* result,
+                                   void* stream) {
+  if (!energy || !result || batch < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_solution_stats");
+  stats_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(energy, batch, (float)optimal_value, (StatsOut*)result);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+// -------------------------------------------------------------------- scaling factor
+__global__ void __launch_bounds__(1024) scaling_factor_kernel(const float* __restrict__ q, int nn, float mult,
+                                                              float* out) {
+  __shared__ double part[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) acc += (double)fabsf(q[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+    *out = __fmul_rn(sqrtf((float)tot), mult);  // sqrt(sum|Q|) * multiplier, fp32 (ccvm_solver.py:146-149)
+  }
+}
+
+extern "C" int ccvm_scaling_factor(const float* q, int32_t n, double multiplier, float* out, void* stream) {
+  if (!q || !out || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_scaling_factor");
+  scaling_factor_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(q, n * n, (float)multiplier, out);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer entry
+extern "C" int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue_desc* epi, const float* h_q,
+                               const float* h_v, double optimal_value, float* h_energy, void* h_stats,
+                               void* stream) {
+  if (!solve || !epi || !h_q || !h_v || !h_energy || !h_stats) return fail(CCVM_E_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = solve->n, b = solve->batch;
+  if (solve->n < 1 || solve->batch < 1) return fail(CCVM_E_INVALID, "n and batch must be >= 1");
+  const size_t words = n * n + n + 3 * b * n + b * n + b + 16;
+  float* buf = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&buf, words * sizeof(float), st));
+  float* d_q = buf;
+  float* d_v = d_q + n * n;
+  float* d_o0 = d_v + n;
+  float* d_o1 = d_o0 + b * n;
+  float* d_o2 = d_o1 + b * n;
+  float* d_pv = d_o2 + b * n;
+  float* d_e = d_pv + b * n;
+  float* d_stats = d_e + b;
+  d_stats = (float*)(((uintptr_t)d_stats + 15) & ~(uintptr_t)15);
+  int rc = CCVM_OK;
+  cudaError_t ce;
+  if ((ce = cudaMemcpyAsync(d_q, h_q, n * n * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess ||
+      (ce = cudaMemcpyAsync(d_v, h_v, n * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) {
+    rc = fail(CCVM_E_CUDA, "H2D copy failed: %s", cudaGetErrorString(ce));
+  }
+  ccvm_solve_desc sd = *solve;
+  sd.q = d_q;
+  sd.v = d_v;
+  sd.out0 = d_o0;
+  sd.out1 = d_o1;
+  sd.out2 = d_o2;
+  sd.evolution_step = 0;
+  sd.samples = nullptr;
+  if (!rc) rc = ccvm_solve(&sd, stream);
+  ccvm_epilogue_desc ed = *epi;
+  ed.n = solve->n;
+  ed.batch = solve->batch;
+  ed.q = d_q;
+  ed.v = d_v;
+  ed.state = solve->solver == CCVM_SOLVER_MF ? d_o1 : d_o0;
+  ed.problem_variables = d_pv;
+  ed.energy = d_e;
+  if (!rc) rc = ccvm_epilogue(&ed, stream);
+  if (!rc) rc = ccvm_solution_stats(d_e, solve->batch, optimal_value, d_stats, stream);
+  if (!rc) {
+    if ((ce = cudaMemcpyAsync(h_energy, d_e, b * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+        (ce = cudaMemcpyAsync(h_stats, d_stats, sizeof(StatsOut), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      rc = fail(CCVM_E_CUDA, "D2H copy failed: %s", cudaGetErrorString(ce));
+  }
+  cudaFreeAsync(buf, st);
+  ce = cudaStreamSynchronize(st);
+  if (!rc && ce != cudaSuccess) rc = fail(CCVM_E_CUDA, "stream sync failed: %s", cudaGetErrorString(ce));
+  return rc;
+}
+
+// ---------------------------------------------------------------------- FP32 probe
+template <int MODE>
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* out, int iters, float seed) {
+  if constexpr (MODE == 0) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + i * 0.001f + threadIdx.x * 1e-6f;
+    const float x = 0.999f + seed * 1e-3f, y = 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) out[0] = s;
+  } else {
+    pf2 a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = pk(seed + i * 0.001f, seed + threadIdx.x * 1e-6f);
+    const pf2 x = dup(0.999f + seed * 1e-3f), y = dup(1e-3f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fma2(a[i], x, y);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i].x + a[i].y;
+    if (s == 123.456f) out[0] = s;
+  }
+}
+
+extern "C" int ccvm_microbench_fp32(int32_t mode, double* tflops, void* stream) {
+  if (!tflops || (mode != 0 && mode != 1)) return fail(CCVM_E_INVALID, "bad argument to ccvm_microbench_fp32");
+  DeviceInfo di;
+  int rc = device_info(di);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* d = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d, 64, st));
+  const int iters = 4096, grid = di.sms * 8, block = 256;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    if (mode == 0) fp32_probe_kernel<0><<<grid, block, 0, st>>>(d, iters, 0.5f);
+    else fp32_probe_kernel<1><<<grid, block, 0, st>>>(d, iters, 0.5f);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * (mode == 0 ? 1.0 : 2.0) * 16.0 * 8.0 * iters * (double)grid * block;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFreeAsync(d, st);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *tflops = best;
+  return CCVM_OK;
+}

@@ -1,0 +1,214 @@
+"""Thin tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers and
+the current CUDA stream to ``libccvm_b200.so``.  No arithmetic happens here."""
+import ctypes as C
+
+import torch
+
+from . import _native as nat
+
+GAP_NAMES = ("optimal", "one_percent", "two_percent", "three_percent", "four_percent",
+             "five_percent", "ten_percent")
+
+
+def _device_of(t):
+    if not t.is_cuda:
+        raise nat.NativeError("ccvm_b200 engine tensors must live on a CUDA device; there is no CPU path.")
+    return t.device
+
+
+def next_philox_stream(device, increment):
+    """(seed, offset) taken from -- and advanced on -- torch's CUDA generator of ``device`` so that
+    ``torch.manual_seed`` keeps governing reproducibility (the reference has no seed argument and
+    draws from the global generator, dl_solver.py:512-519)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    gen = torch.cuda.default_generators[idx]
+    seed = gen.initial_seed()
+    offset = gen.get_offset()
+    gen.set_offset(offset + 4 * ((int(increment) + 3) // 4))
+    return seed & 0xFFFFFFFFFFFFFFFF, offset
+
+
+def solve(solver, algorithm, q, v, batch, iterations, *, lower=0.0, upper=1.0, s=1.0, s_vec=None,
+          pump=0.0, dt=0.0, noise_ratio=1.0, j=1.0, sigma=0.0, feedback_scale=1.0, g=0.0,
+          pump_rate_flag=True, hyperparameters=None, noise=None, seed=None, offset=None,
+          traj_base=0, evolution_step=None, num_samples=0):
+    """Run one ``_solve`` / ``_solve_adam`` loop on the GPU.  Returns (outputs, samples):
+    outputs is the tuple of (B, N) state tensors documented in ccvm_b200.h."""
+    nat.require_cuda()
+    lib = nat.load()
+    dev = _device_of(q)
+    n = int(q.shape[0])
+    qc, vc = nat.as_f32(q, dev), nat.as_f32(v, dev)
+    d = nat.SolveDesc()
+    d.solver, d.algorithm = solver, algorithm
+    d.n, d.batch, d.iterations = n, int(batch), int(iterations)
+    d.pump_rate_flag = 1 if pump_rate_flag else 0
+    d.q, d.v = nat.ptr(qc), nat.ptr(vc)
+    d.lower, d.upper = float(lower), float(upper)
+    svc = None
+    if s_vec is not None:
+        svc = nat.as_f32(s_vec, dev)
+        if svc.numel() != n:
+            raise ValueError("Tensor S size should be equal to problem size.")
+        d.s_vec = nat.ptr(svc)
+        d.s = 0.0
+    else:
+        d.s = float(s)
+    d.pump, d.dt, d.noise_ratio, d.j = float(pump), float(dt), float(noise_ratio), float(j)
+    d.sigma, d.feedback_scale, d.g = float(sigma), float(feedback_scale), float(g)
+    if algorithm == nat.ALG_ADAM:
+        d.alpha, d.beta1, d.beta2 = (float(hyperparameters[k]) for k in ("alpha", "beta1", "beta2"))
+        d.add_assign = 1 if hyperparameters["add_assign"] else 0
+    k_draws = 2 if solver == nat.SOLVER_DL else 1
+    nz = None
+    if noise is not None:
+        nz = nat.as_f32(noise, dev)
+        if nz.dim() != 4 or nz.shape[0] < iterations or nz.shape[1] != k_draws or nz.shape[2] != n:
+            raise ValueError(f"replay noise must be [iterations][{k_draws}][n][batch], got {tuple(nz.shape)}")
+        d.rng_mode, d.noise, d.noise_batch = nat.RNG_REPLAY, nat.ptr(nz), int(nz.shape[3])
+    else:
+        if seed is None:
+            seed, offset = next_philox_stream(dev, 1)
+        d.rng_mode, d.seed, d.offset = nat.RNG_PHILOX, int(seed), int(offset or 0)
+    d.traj_base = int(traj_base)
+    n_out = {nat.SOLVER_DL: 2, nat.SOLVER_MF: 3}.get(solver, 1)
+    outs = [torch.empty((batch, n), dtype=torch.float32, device=dev) for _ in range(n_out)]
+    d.out0 = nat.ptr(outs[0])
+    d.out1 = nat.ptr(outs[1]) if n_out > 1 else None
+    d.out2 = nat.ptr(outs[2]) if n_out > 2 else None
+    samples = None
+    if evolution_step:
+        n_state = 1 if solver in (nat.SOLVER_LANGEVIN, nat.SOLVER_PUMPED_LANGEVIN) else 2
+        samples = torch.zeros((n_state, num_samples, batch, n), dtype=torch.float32, device=dev)
+        d.evolution_step, d.num_samples, d.samples = int(evolution_step), int(num_samples), nat.ptr(samples)
+    with torch.cuda.device(dev):
+        nat.check(lib.ccvm_solve(C.byref(d), nat.current_stream_ptr(dev)))
+    del qc, vc, svc, nz  # kept alive until the launch was enqueued on the current stream
+    return tuple(outs), samples
+
+
+def query_launch(desc):
+    info = (C.c_int32 * 5)()
+    nat.check(nat.load().ccvm_query_launch(C.byref(desc), info))
+    return dict(threads=info[0], ctas=info[1], traj_per_cta=info[2], smem=info[3], regs=info[4])
+
+
+def _vec_or_scalar(val, n, dev):
+    """(scalar, tensor-or-None) for an affine-map coefficient that may be per-variable."""
+    if torch.is_tensor(val) and val.numel() > 1:
+        if val.dim() == 2:  # (B, N) outer(ones, S): rows are identical by construction
+            val = val[0]
+        if val.numel() != n:
+            raise ValueError("Tensor S size should be equal to problem size.")
+        return 0.0, nat.as_f32(val, dev)
+    return float(val), None
+
+
+def epilogue(state, q, v, *, map1=None, post_processor=None, pp_iterations=10, pp_step=None,
+             pp_lower=0.0, pp_upper=1.0, map2=None, scaled_by=1.0, want_energy=True, want_pv=True):
+    """Fused tail of ``Solver.__call__``: x = state*m1s + m1o -> post-processor -> pv ;
+    energy((pv*m2s + m2o)).  ``map1`` / ``map2`` are (scale, shift) or None."""
+    nat.require_cuda()
+    lib = nat.load()
+    dev = _device_of(state)
+    st = nat.as_f32(state, dev)
+    b, n = st.shape
+    qc, vc = nat.as_f32(q, dev), nat.as_f32(v, dev)
+    d = nat.EpilogueDesc()
+    d.n, d.batch = n, b
+    d.q, d.v, d.state = nat.ptr(qc), nat.ptr(vc), nat.ptr(st)
+    keep = []
+    if map1 is not None:
+        sc, vec = _vec_or_scalar(map1[0], n, dev)
+        keep.append(vec)
+        d.apply_map1, d.map1_scale, d.map1_shift, d.map1_scale_vec = 1, sc, float(map1[1]), nat.ptr(vec)
+    if map2 is not None:
+        sc, vec = _vec_or_scalar(map2[0], n, dev)
+        keep.append(vec)
+        d.apply_map2, d.map2_scale, d.map2_shift, d.map2_scale_vec = 1, sc, float(map2[1]), nat.ptr(vec)
+    if post_processor not in nat.PP_IDS:
+        raise AssertionError(f"Method type is not valid. Provided: {post_processor}")
+    d.post_processor = nat.PP_IDS[post_processor]
+    d.pp_iterations = int(pp_iterations)
+    if pp_step is None:
+        pp_step = 0.1 if post_processor == "grad-descent" else 0.01
+    d.pp_step, d.pp_lower, d.pp_upper = float(pp_step), float(pp_lower), float(pp_upper)
+    d.scaled_by = float(scaled_by)
+    pv = torch.empty((b, n), dtype=torch.float32, device=dev) if want_pv else None
+    en = torch.empty((b,), dtype=torch.float32, device=dev) if want_energy else None
+    d.problem_variables, d.energy = nat.ptr(pv), nat.ptr(en)
+    with torch.cuda.device(dev):
+        nat.check(lib.ccvm_epilogue(C.byref(d), nat.current_stream_ptr(dev)))
+    del keep, qc, vc, st
+    return pv, en
+
+
+def compute_energy(x, q, v, scaled_by=1.0):
+    nat.require_cuda()
+    dev = _device_of(x)
+    xc, qc, vc = nat.as_f32(x, dev), nat.as_f32(q, dev), nat.as_f32(v, dev)
+    b, n = xc.shape
+    en = torch.empty((b,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_compute_energy(nat.ptr(xc), nat.ptr(qc), nat.ptr(vc), float(scaled_by), b, n,
+                                                 nat.ptr(en), nat.current_stream_ptr(dev)))
+    return en
+
+
+def postprocess_grad_descent(x, q, v, iterations, step_size, lower, upper):
+    """In place on ``x`` (must be a contiguous fp32 CUDA tensor)."""
+    nat.require_cuda()
+    dev = _device_of(x)
+    qc, vc = nat.as_f32(q, dev), nat.as_f32(v, dev)
+    b, n = x.shape
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_postprocess_grad_descent(nat.ptr(x), nat.ptr(qc), nat.ptr(vc), b, n,
+                                                           int(iterations), float(step_size), float(lower),
+                                                           float(upper), nat.current_stream_ptr(dev)))
+    return x
+
+
+def postprocess_adam(x, q, v, lr, lower, upper):
+    nat.require_cuda()
+    dev = _device_of(x)
+    qc, vc = nat.as_f32(q, dev), nat.as_f32(v, dev)
+    b, n = x.shape
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_postprocess_adam(nat.ptr(x), nat.ptr(qc), nat.ptr(vc), b, n, float(lr),
+                                                   float(lower), float(upper), nat.current_stream_ptr(dev)))
+    return x
+
+
+def solution_stats(energy, optimal_value):
+    """(best_objective_value, arg_best, counts[7]) with ONE device->host read of 36 bytes
+    (the reference does eight .item() syncs, solution.py:82,113-136)."""
+    nat.require_cuda()
+    dev = _device_of(energy)
+    en = nat.as_f32(energy, dev)
+    res = torch.empty(9, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_solution_stats(nat.ptr(en), en.numel(), float(optimal_value), nat.ptr(res),
+                                                 nat.current_stream_ptr(dev)))
+    host = res.cpu()
+    best = host[:1].view(torch.float32).item()
+    return best, int(host[1]), [int(c) for c in host[2:9]]
+
+
+def scaling_factor(q, multiplier):
+    """Device 0-d fp32 tensor sqrt(sum|Q|) * multiplier (ccvm_solver.py:134-150)."""
+    nat.require_cuda()
+    dev = _device_of(q)
+    qc = nat.as_f32(q, dev)
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_scaling_factor(nat.ptr(qc), int(qc.shape[0]), float(multiplier), nat.ptr(out),
+                                                 nat.current_stream_ptr(dev)))
+    return out
+
+
+def microbench_fp32(mode=1):
+    """Measured register-only FP32 FMA throughput in TFLOP/s (0 = FFMA, 1 = packed FFMA2)."""
+    nat.require_cuda()
+    val = C.c_double(0.0)
+    nat.check(nat.load().ccvm_microbench_fp32(int(mode), C.byref(val), nat.current_stream_ptr()))
+    return val.value

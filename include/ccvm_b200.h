@@ -1,0 +1,204 @@
+/*
+ * ccvm_b200.h -- C ABI of the B200-native CCVM dynamics engine (libccvm_b200.so).
+ *
+ * The reference (1QB-Information-Technologies/ccvm) is pure Python on torch; it has no FFI.
+ * Every entry point below replaces ONE Python-level operator of the reference's hot path and is
+ * what a ctypes binding inside the reference's solver classes would call (INTEGRATION.md shows
+ * the stub).  Paths are relative to the reference's `ccvm_simulators/` package.
+ *
+ * Conventions
+ *  - All matrices are fp32, row-major, resident in DEVICE memory unless the name says `_host`.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).  All work is
+ *    enqueued on it; nothing synchronises unless documented.
+ *  - Return value: 0 on success, a negative CCVM_E_* code otherwise; `ccvm_last_error()` returns
+ *    a thread-local message.  No CPU fallback exists: without a CUDA device every compute call
+ *    fails with CCVM_E_CUDA.
+ *  - y·Q means the ROW vector times the matrix, (yQ)_j = sum_i y_i Q_ij, as in the reference's
+ *    einsum("bi,ij->bj") (solvers/dl_solver.py:145-149).
+ */
+#ifndef CCVM_B200_H
+#define CCVM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCVM_ABI_VERSION 1
+
+/* error codes */
+#define CCVM_OK 0
+#define CCVM_E_INVALID (-1)  /* bad argument / unsupported combination            */
+#define CCVM_E_CUDA (-2)     /* CUDA runtime error (message has the CUDA string)   */
+#define CCVM_E_TOO_LARGE (-3) /* problem does not fit the on-chip layout of any path */
+
+/* solver ids: which reference class the loop belongs to */
+#define CCVM_SOLVER_DL 0               /* solvers/dl_solver.py              DLSolver             */
+#define CCVM_SOLVER_MF 1               /* solvers/mf_solver.py              MFSolver             */
+#define CCVM_SOLVER_LANGEVIN 2         /* solvers/langevin_solver.py        LangevinSolver       */
+#define CCVM_SOLVER_PUMPED_LANGEVIN 3  /* solvers/pumped_langevin_solver.py PumpedLangevinSolver */
+
+/* algorithm ids */
+#define CCVM_ALG_ORIGINAL 0 /* Solver._solve      */
+#define CCVM_ALG_ADAM 1     /* Solver._solve_adam */
+
+/* noise source */
+#define CCVM_RNG_PHILOX 0 /* in-kernel Philox4x32-10 + Box-Muller, keyed by (seed, offset, trajectory, step, variable) */
+#define CCVM_RNG_REPLAY 1 /* validation: consume a recorded noise tensor [T][K][N][B]                 */
+
+/* post-processor ids (post_processor/factory.py:12-35; only the two batched ones are on the hot path) */
+#define CCVM_PP_NONE 0
+#define CCVM_PP_GRAD_DESCENT 1 /* post_processor/grad_descent.py:58-64 */
+#define CCVM_PP_ADAM 2         /* post_processor/adam.py:58-66 (effective 1-step behaviour) */
+
+/*
+ * One call of Solver._solve / Solver._solve_adam.
+ *
+ * Replaces: DLSolver._solve (dl_solver.py:468-569), DLSolver._solve_adam (571-769),
+ *           MFSolver._solve (mf_solver.py:493-593), MFSolver._solve_adam (595-764),
+ *           LangevinSolver._solve (langevin_solver.py:368-435), ._solve_adam (437-561),
+ *           PumpedLangevinSolver._solve (pumped_langevin_solver.py:232-309), ._solve_adam (311-449),
+ *           including the hooks they call (calculate_drift / calculate_grads / fit_to_constraints).
+ *
+ * The whole iteration loop runs as ONE persistent kernel launch.
+ */
+typedef struct ccvm_solve_desc {
+  int32_t solver;     /* CCVM_SOLVER_*                                                        */
+  int32_t algorithm;  /* CCVM_ALG_*                                                           */
+  int32_t n;          /* problem_size                                                         */
+  int32_t batch;      /* batch_size: trajectories solved by THIS call                         */
+  int32_t iterations; /* parameter_key[n]["iterations"]                                       */
+  int32_t pump_rate_flag; /* __call__(pump_rate_flag=...) ; ignored by Langevin               */
+  const float* q;     /* device [n*n]  self.q_matrix (already scaled & negated by the loader) */
+  const float* v;     /* device [n]    self.v_vector                                          */
+  double lower;       /* instance.solution_bounds[0]                                          */
+  double upper;       /* instance.solution_bounds[1]                                          */
+  /* Saturation value S exactly as the reference hands it to _solve/_solve_adam: DL = the
+   * constructor's S, others = parameter_key[n]["S"].  If `s_vec` is non-NULL it is a device
+   * [n] per-variable S (the reference's 1-D tensor S broadcast over the batch,
+   * dl_solver.py:843-848) and `s` is ignored wherever the reference would use the tensor. */
+  double s;
+  const float* s_vec;
+  /* parameter_key / __call__ scalars; unused ones are ignored per solver */
+  double pump, dt, noise_ratio, j, sigma, feedback_scale, g;
+  /* AdamParameters.to_dict() (solvers/algorithms.py:38-45); used when algorithm == ADAM */
+  double alpha, beta1, beta2;
+  int32_t add_assign;
+  /* noise */
+  int32_t rng_mode;    /* CCVM_RNG_*                                                          */
+  const float* noise;  /* REPLAY: device [iterations][K][n][noise_batch], K = 2 for DL else 1  */
+  int64_t noise_batch; /* REPLAY: trajectory extent of `noise` (>= traj_base + batch)          */
+  uint64_t seed;       /* PHILOX key                                                          */
+  uint64_t offset;     /* PHILOX stream offset (advance by >= 1 between calls)                */
+  int64_t traj_base;   /* global index of this call's trajectory 0 (batch sharding across GPUs:
+                          noise depends on the GLOBAL trajectory index, so results do not
+                          depend on how the batch was split)                                 */
+  /* outputs, device [batch*n] each, row-major (B,N):
+   *   DL:  out0 = c (clamped), out1 = s
+   *   MF:  out0 = mu, out1 = mu_tilde (clamped last measurement), out2 = sigma
+   *   Langevin / PumpedLangevin: out0 = c                                                   */
+  float* out0;
+  float* out1;
+  float* out2;
+  /* optional evolution sampling (dl_solver.py:557-564): when evolution_step > 0, state is
+   * stored whenever i % evolution_step == 0 or i + 1 >= iterations into
+   * samples[k][sample][b][n], k over (c,s) / (mu,sigma) / (c). */
+  int32_t evolution_step;
+  int32_t num_samples;
+  float* samples;
+} ccvm_solve_desc;
+
+int ccvm_solve(const ccvm_solve_desc* desc, void* stream);
+
+/*
+ * The tail of Solver.__call__: optional affine change of variables, optional batched
+ * post-processor, optional second change of variables (the DL double map), BoxQP energy.
+ *
+ * Replaces: CCVMSolver.change_variables (dl_solver.py:219-235 and siblings; Langevin's
+ *           (c+S)/(2S), langevin_solver.py:717-722), PostProcessorGradDescent.postprocess
+ *           (post_processor/grad_descent.py:13-68), PostProcessorAdam.postprocess
+ *           (post_processor/adam.py:15-69), ProblemInstance.compute_energy
+ *           (problem_classes/boxqp/problem_instance.py:226-241).
+ *
+ *   x  = state * map1_scale_j + map1_shift          (map1_scale_vec overrides the scalar)
+ *   pv = post_process(x)                            (or x)
+ *   cf = pv * map2_scale_j + map2_shift             (skipped when apply_map2 == 0: cf = pv)
+ *   energy_b = (0.5 * cf_b Q cf_b + V . cf_b) * scaled_by
+ */
+typedef struct ccvm_epilogue_desc {
+  int32_t n;
+  int32_t batch;
+  const float* q;
+  const float* v;
+  const float* state; /* device [batch*n]                                              */
+  int32_t apply_map1;
+  double map1_scale, map1_shift;
+  const float* map1_scale_vec; /* optional device [n]                                  */
+  int32_t post_processor;      /* CCVM_PP_*                                            */
+  int32_t pp_iterations;       /* grad-descent: num_iter_pp (reference default 10)     */
+  double pp_step;              /* grad-descent step_size (0.1); adam lr (0.01)         */
+  double pp_lower, pp_upper;   /* clamp bounds (0, 1)                                  */
+  int32_t apply_map2;
+  double map2_scale, map2_shift;
+  const float* map2_scale_vec;
+  double scaled_by;            /* instance.scaled_by                                   */
+  float* problem_variables;    /* out, device [batch*n] (pv); may be NULL              */
+  float* energy;               /* out, device [batch]; may be NULL                     */
+} ccvm_epilogue_desc;
+
+int ccvm_epilogue(const ccvm_epilogue_desc* desc, void* stream);
+
+/* Replaces ProblemInstance.compute_energy (problem_instance.py:226-241). */
+int ccvm_compute_energy(const float* x, const float* q, const float* v, double scaled_by,
+                        int32_t batch, int32_t n, float* energy, void* stream);
+
+/* Replaces PostProcessorGradDescent.postprocess (grad_descent.py:58-64); x is updated in place. */
+int ccvm_postprocess_grad_descent(float* x, const float* q, const float* v, int32_t batch,
+                                  int32_t n, int32_t iterations, double step_size, double lower,
+                                  double upper, void* stream);
+
+/* Replaces PostProcessorAdam.postprocess (adam.py:58-66, one Adam step + clamp); in place. */
+int ccvm_postprocess_adam(float* x, const float* q, const float* v, int32_t batch, int32_t n,
+                          double lr, double lower, double upper, void* stream);
+
+/*
+ * Replaces Solution.__post_init__ / get_solution_stats (solution.py:65-146):
+ *   best = max_b(-energy_b), arg_best = its index, counts[k] = #{b : gap_b <= thr_k},
+ *   gap_b = (optimal - (-energy_b)) * 100 / |energy_b|, thr = {0.1, 1, 2, 3, 4, 5, 10}.
+ * `result` is a device buffer of 9 x 4 bytes: {float best, int32 arg_best, int32 counts[7]}.
+ */
+int ccvm_solution_stats(const float* energy, int32_t batch, double optimal_value, void* result,
+                        void* stream);
+
+/* Replaces CCVMSolver.get_scaling_factor (solvers/ccvm_solver.py:134-150):
+ *   *out (device float) = sqrt(sum |Q_ij|) * multiplier. */
+int ccvm_scaling_factor(const float* q, int32_t n, double multiplier, float* out, void* stream);
+
+/*
+ * Host-buffer convenience used for end-to-end timing: copies Q and V from HOST memory,
+ * runs ccvm_solve + ccvm_epilogue + ccvm_solution_stats on `stream`, copies energy[batch] and the
+ * 9-word stats block back to HOST memory and synchronises the stream.  `solve` and `epi` carry
+ * the scalar parameters; their device pointers (q, v, state, outputs) are ignored and replaced
+ * by internal buffers.  `h_*` pointers are host memory (pinned recommended).
+ */
+int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue_desc* epi,
+                    const float* h_q, const float* h_v, double optimal_value, float* h_energy,
+                    void* h_stats, void* stream);
+
+/* Register-only FP32 FMA throughput probe (roofline denominator for the SIMT path).
+ * mode 0 = scalar FFMA, mode 1 = packed FFMA2 (fma.rn.f32x2).  Runs on `stream`, synchronises,
+ * writes achieved TFLOP/s. */
+int ccvm_microbench_fp32(int32_t mode, double* tflops, void* stream);
+
+/* Query the launch geometry ccvm_solve would use: fills threads per CTA, CTAs, trajectories per
+ * CTA, dynamic shared memory bytes, registers per thread.  For reports and tests. */
+int ccvm_query_launch(const ccvm_solve_desc* desc, int32_t* info5);
+
+int ccvm_abi_version(void);
+const char* ccvm_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCVM_B200_H */

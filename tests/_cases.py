@@ -87,3 +87,39 @@ def run_oracle(name, z, dtype=torch.float32):
                                                   _f(z, "sigma"), _f(z, "feedback_scale"), noise,
                                                   hyper_of(z), flag, bounds, dtype)}
     raise ValueError(name)
+
+
+def run_engine(name, z, device="cuda"):
+    """Run the CUDA engine (through the C ABI) on fixture ``z`` in noise-replay mode."""
+    from ccvm_b200 import engine as E
+    from ccvm_b200 import _native as nat
+    k = kind_of(name)
+    q = torch.from_numpy(z["q"]).to(device)
+    v = torch.from_numpy(z["v"]).to(device)
+    b, t = int(z["batch"]), int(z["iterations"])
+    bounds = tuple(float(x) for x in z["bounds"]) if "bounds" in z else (0.0, 1.0)
+    flag = bool(z["flag"]) if "flag" in z else True
+    noise = torch.from_numpy(z["noise"]).to(device)
+    adam = k.endswith("adam")
+    kw = dict(lower=bounds[0], upper=bounds[1], pump_rate_flag=flag, noise=noise,
+              hyperparameters=hyper_of(z) if adam else None)
+    alg = nat.ALG_ADAM if adam else nat.ALG_ORIGINAL
+    if k in ("dl", "dladam"):
+        outs, _ = E.solve(nat.SOLVER_DL, alg, q, v, b, t, s=_f(z, "s_ctor"), pump=_f(z, "pump"), dt=_f(z, "dt"),
+                          noise_ratio=_f(z, "noise_ratio"), feedback_scale=_f(z, "feedback_scale"), g=_f(z, "g"),
+                          **kw)
+        return {"c": outs[0].cpu(), "s": outs[1].cpu()}
+    if k in ("mf", "mfadam"):
+        s_vec = torch.from_numpy(z["s_vec"]) if "s_vec" in z else None
+        outs, _ = E.solve(nat.SOLVER_MF, alg, q, v, b, t, s=_f(z, "S", 0.0), s_vec=s_vec, pump=_f(z, "pump"),
+                          dt=_f(z, "dt"), j=_f(z, "j"), feedback_scale=_f(z, "feedback_scale"), g=_f(z, "g"), **kw)
+        return {"mu": outs[0].cpu(), "mu_tilde": outs[1].cpu(), "sigma": outs[2].cpu()}
+    if k in ("lv", "lvadam"):
+        outs, _ = E.solve(nat.SOLVER_LANGEVIN, alg, q, v, b, t, s=_f(z, "S"), dt=_f(z, "dt"),
+                          sigma=_f(z, "sigma"), feedback_scale=_f(z, "feedback_scale"), **kw)
+        return {"c": outs[0].cpu()}
+    if k in ("plv", "plvadam"):
+        outs, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, alg, q, v, b, t, s=_f(z, "S"), pump=_f(z, "pump"),
+                          dt=_f(z, "dt"), sigma=_f(z, "sigma"), feedback_scale=_f(z, "feedback_scale"), **kw)
+        return {"c": outs[0].cpu()}
+    raise ValueError(name)
