@@ -22,6 +22,7 @@ EXPORTS = (
     "ccvm_solve", "ccvm_epilogue", "ccvm_compute_energy", "ccvm_postprocess_grad_descent",
     "ccvm_postprocess_adam", "ccvm_solution_stats", "ccvm_scaling_factor", "ccvm_solve_host",
     "ccvm_microbench_fp32", "ccvm_query_launch", "ccvm_abi_version", "ccvm_last_error",
+    "ccvm_eval_hook", "ccvm_change_variables", "ccvm_fit_to_constraints", "ccvm_scale_coefs",
 )
 
 _fp = C.c_void_p  # device / host pointers travel as plain addresses
@@ -59,6 +60,16 @@ class EpilogueDesc(C.Structure):
     ]
 
 
+class HookDesc(C.Structure):
+    _fields_ = [
+        ("solver", C.c_int32), ("kind", C.c_int32), ("n", C.c_int32), ("batch", C.c_int32),
+        ("q", _fp), ("v", _fp), ("in0", _fp), ("in1", _fp), ("in2", _fp),
+        ("lower", C.c_double), ("upper", C.c_double), ("s", C.c_double), ("s_vec", _fp),
+        ("pump", C.c_double), ("rate", C.c_double), ("feedback_scale", C.c_double), ("j", C.c_double),
+        ("g", C.c_double), ("out0", _fp), ("out1", _fp),
+    ]
+
+
 _lib = None
 
 
@@ -91,6 +102,12 @@ def load():
                                     _fp, _fp, _fp]
     lib.ccvm_microbench_fp32.argtypes = [C.c_int32, C.POINTER(C.c_double), _fp]
     lib.ccvm_query_launch.argtypes = [C.POINTER(SolveDesc), C.POINTER(C.c_int32)]
+    lib.ccvm_eval_hook.argtypes = [C.POINTER(HookDesc), _fp]
+    lib.ccvm_change_variables.argtypes = [_fp, _fp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
+                                          _fp, _fp]
+    lib.ccvm_fit_to_constraints.argtypes = [_fp, _fp, C.c_int32, C.c_int32, C.c_double, C.c_double, _fp, _fp,
+                                            C.c_int64, _fp]
+    lib.ccvm_scale_coefs.argtypes = [_fp, _fp, C.c_int32, _fp, C.c_int64, _fp, _fp, _fp]
     for name in EXPORTS:
         if name not in ("ccvm_last_error",):
             getattr(lib, name).restype = C.c_int if name != "ccvm_last_error" else C.c_char_p

@@ -10,6 +10,7 @@
 
 #include "../../include/ccvm_b200.h"
 #include "sde_kernel.cuh"
+#include "sde_kernel_tmem.cuh"
 
 using namespace ccvm;
 
@@ -48,6 +49,13 @@ static int device_info(DeviceInfo& di) {
     CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10)
       return fail(CCVM_E_CUDA, "ccvm_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+    // keep stream-ordered allocations cached across synchronisations (the default pool hands
+    // memory back to the driver at every sync, which cost ~50 ms per host-buffer solve)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     cache.device = dev;
     cache.sms = sms;
     cache.max_smem = smem;
@@ -175,6 +183,73 @@ static int regs_one() {
   return fa.numRegs;
 }
 
+
+// ---- TMEM path (n <= 128): see sde_kernel_tmem.cuh
+struct TmemPlan {
+  TmemLaunch L;
+  int cg, threads, ctas;
+  size_t smem;
+};
+
+static bool tmem_path_applies(const ccvm_solve_desc& d) {
+  return d.n <= 128 && getenv("CCVM_NO_TMEM") == nullptr;
+}
+
+static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, TmemPlan& P) {
+  const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1, RW = 2 * K;
+  const int cg = (d.n + 3) / 4, np = 4 * cg;
+  const int rg_max = 128 / cg;
+  const int share = (d.batch + di.sms - 1) / di.sms;
+  const int pairs = (share + 1) / 2;
+  int ng = pairs <= rg_max ? 1 : 2;
+  int rg = (pairs + ng - 1) / ng;
+  if (const char* e = getenv("CCVM_NG")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2) ng = v;
+  }
+  if (const char* e = getenv("CCVM_RG")) {
+    const int v = atoi(e);
+    if (v > 0) rg = v;
+  }
+  if (rg > rg_max) rg = rg_max;
+  if (rg < 1) rg = 1;
+  int xs = ((RW * rg + 32 + 3) / 4) * 4;
+  auto smem_of = [&](int xs_) { return ((size_t)2 * np + (size_t)ng * 2 * np * xs_) * sizeof(float); };
+  while (smem_of(xs) > (size_t)di.max_smem && rg > 1) {
+    --rg;
+    xs = ((RW * rg + 32 + 3) / 4) * 4;
+  }
+  if (smem_of(xs) > (size_t)di.max_smem) return fail(CCVM_E_TOO_LARGE, "TMEM path: panel does not fit shared memory");
+  int tcols = 32;
+  while (tcols < 4 * np) tcols *= 2;
+  P.L.rg = rg;
+  P.L.ng = ng;
+  P.L.gt = ng > 1 ? 128 : ((rg * cg + 31) / 32) * 32;
+  P.L.xs = xs;
+  P.L.tcols = tcols;
+  P.cg = cg;
+  P.threads = ng * P.L.gt;
+  P.ctas = (d.batch + ng * 2 * rg - 1) / (ng * 2 * rg);
+  P.smem = smem_of(xs);
+  return CCVM_OK;
+}
+
+template <int SOLVER, bool ADAM>
+static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
+  auto kern = sde_tmem_kernel<SOLVER, ADAM>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+  kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+template <int SOLVER, bool ADAM>
+static int regs_tmem() {
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM>) != cudaSuccess) return -1;
+  return fa.numRegs;
+}
+
 static int validate_solve(const ccvm_solve_desc* d) {
   if (!d) return fail(CCVM_E_INVALID, "null descriptor");
   if (d->solver < 0 || d->solver > 3) return fail(CCVM_E_INVALID, "unknown solver id %d", d->solver);
@@ -224,6 +299,22 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
   if (rc) return rc;
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
+  if (tmem_path_applies(*d)) {
+    TmemPlan P;
+    if ((rc = plan_tmem(*d, di, P))) return rc;
+    info5[0] = P.threads;
+    info5[1] = P.ctas;
+    info5[2] = P.L.ng * 2 * P.L.rg;
+    info5[3] = (int)P.smem;
+    const bool a = d->algorithm == CCVM_ALG_ADAM;
+    int r = -1;
+    if (d->solver == SOLVER_DL) r = a ? regs_tmem<SOLVER_DL, true>() : regs_tmem<SOLVER_DL, false>();
+    if (d->solver == SOLVER_MF) r = a ? regs_tmem<SOLVER_MF, true>() : regs_tmem<SOLVER_MF, false>();
+    if (d->solver == SOLVER_LV) r = a ? regs_tmem<SOLVER_LV, true>() : regs_tmem<SOLVER_LV, false>();
+    if (d->solver == SOLVER_PLV) r = a ? regs_tmem<SOLVER_PLV, true>() : regs_tmem<SOLVER_PLV, false>();
+    info5[4] = r;
+    return CCVM_OK;
+  }
   LaunchPlan L;
   if ((rc = plan_launch(*d, di, L))) return rc;
   info5[0] = L.threads;
@@ -253,8 +344,16 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   if (rc) return rc;
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
+  const bool use_tmem = tmem_path_applies(*d);
   LaunchPlan L;
-  if ((rc = plan_launch(*d, di, L))) return rc;
+  TmemPlan TP;
+  memset(&L, 0, sizeof(L));
+  if (use_tmem) {
+    if ((rc = plan_tmem(*d, di, TP))) return rc;
+    L.cg = TP.cg;
+  } else if ((rc = plan_launch(*d, di, L))) {
+    return rc;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const bool adam = d->algorithm == CCVM_ALG_ADAM;
 
@@ -317,6 +416,18 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   p.off_lo = (uint32_t)d->offset;
   p.off_hi = (uint32_t)(d->offset >> 32);
 
+  if (use_tmem) {
+    switch (d->solver * 2 + (adam ? 1 : 0)) {
+      case 0: rc = launch_tmem<SOLVER_DL, false>(p, TP, st); break;
+      case 1: rc = launch_tmem<SOLVER_DL, true>(p, TP, st); break;
+      case 2: rc = launch_tmem<SOLVER_MF, false>(p, TP, st); break;
+      case 3: rc = launch_tmem<SOLVER_MF, true>(p, TP, st); break;
+      case 4: rc = launch_tmem<SOLVER_LV, false>(p, TP, st); break;
+      case 5: rc = launch_tmem<SOLVER_LV, true>(p, TP, st); break;
+      case 6: rc = launch_tmem<SOLVER_PLV, false>(p, TP, st); break;
+      default: rc = launch_tmem<SOLVER_PLV, true>(p, TP, st); break;
+    }
+  } else
   switch (d->solver * 2 + (adam ? 1 : 0)) {
     case 0: rc = launch_tb<SOLVER_DL, false>(p, L, st); break;
     case 1: rc = launch_tb<SOLVER_DL, true>(p, L, st); break;
@@ -387,7 +498,7 @@ __global__ void __launch_bounds__(EPI_WARPS * 32) epilogue_kernel(const EpiParam
           float acc = 0.f;
           for (int i = 0; i < N; ++i) acc = fmaf(x[i], Q[i * ld + j], acc);
           const float g = acc + p.v[j];
-          y[j] = fminf(fmaxf(x[j] + (-p.step) * g, p.lo), p.hi);
+          y[j] = clampf(x[j] + (-p.step) * g, p.lo, p.hi);
         }
         __syncwarp();
         float* tmp = x;
@@ -406,7 +517,7 @@ __global__ void __launch_bounds__(EPI_WARPS * 32) epilogue_kernel(const EpiParam
         const float g = 0.5f * (a1 + a2) + p.v[j];
         const float m = (1.f - 0.9f) * g, vv = (1.f - 0.99f) * g * g;
         const float den = sqrtf(vv) / sqrtf(1.f - 0.99f) + 1e-8f;
-        y[j] = fminf(fmaxf(x[j] - (p.step / (1.f - 0.9f)) * (m / den), p.lo), p.hi);
+        y[j] = clampf(x[j] - (p.step / (1.f - 0.9f)) * (m / den), p.lo, p.hi);
       }
       __syncwarp();
       float* tmp = x;
@@ -766,5 +877,208 @@ extern "C" int ccvm_microbench_fp32(int32_t mode, double* tflops, void* stream) 
   cudaFreeAsync(d, st);
   CUDA_TRY(cudaStreamSynchronize(st));
   *tflops = best;
+  return CCVM_OK;
+}
+
+// ------------------------------------------------------------------ operator hooks
+// One thread per output element, arithmetic in the reference's fp32 operation order
+// (host scalars are folded in fp64 first, exactly as Python does before they meet a tensor).
+struct HookParams {
+  const float* q;
+  const float* v;
+  const float* in0;
+  const float* in1;
+  const float* in2;
+  const float* svec;
+  float* out0;
+  float* out1;
+  int solver, kind, n, batch;
+  float s, a, b, half_b, two_s;
+  float c_lin, c_lin2;   // DL: -1 + pump*rate and -1 - pump*rate ; MF: -(1+j) + pump ; PLV: -1 + p
+  float fsd;             // DL: -(fs*(0.5+rate)) ; MF / PLV: fs
+  float g2, g2x2, g2x3, m2j, opj;
+};
+
+__device__ __forceinline__ float hook_contract(const HookParams& p, const float* in, int b, int j, bool half) {
+  // sum_i (in_i * a / S_i + b) Q_ij     (half: in_i * a / (2 S_i) + b/2)
+  const int N = p.n;
+  float acc = 0.f;
+  for (int i = 0; i < N; ++i) {
+    const float si = p.svec ? p.svec[i] : p.s;
+    const float den = half ? __fmul_rn(2.f, si) : si;
+    const float x = __fadd_rn(__fdiv_rn(__fmul_rn(in[(size_t)b * N + i], p.a), den), half ? p.half_b : p.b);
+    acc = fmaf(x, p.q[(size_t)i * N + j], acc);
+  }
+  return acc;
+}
+
+__global__ void hook_kernel(const HookParams p) {
+  const int N = p.n;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)p.batch * N) return;
+  const int b = (int)(idx / N), j = (int)(idx - (size_t)b * N);
+  const float sj = p.svec ? p.svec[j] : p.s;
+  const float two_sj = __fmul_rn(2.f, sj);
+  if (p.solver == SOLVER_DL) {
+    const float c = p.in0[idx], s = p.in1[idx];
+    const float ec = hook_contract(p, p.in0, b, j, false), es = hook_contract(p, p.in1, b, j, false);
+    const float g1c = __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, ec), p.a), sj);
+    const float g1s = __fdiv_rn(__fmul_rn(__fmul_rn(0.25f, es), p.a), sj);
+    const float g3 = __fdiv_rn(__fmul_rn(p.v[j], p.a), two_sj);
+    if (p.kind == 0) {
+      p.out0[idx] = __fsub_rn(-g1c, g3);
+      p.out1[idx] = __fsub_rn(-g1s, g3);
+    } else {
+      const float c2 = __fmul_rn(c, c), s2 = __fmul_rn(s, s);
+      const float g2c = __fmul_rn(__fsub_rn(__fsub_rn(p.c_lin, c2), s2), c);
+      const float g2s = __fmul_rn(__fsub_rn(__fsub_rn(p.c_lin2, c2), s2), s);
+      p.out0[idx] = __fadd_rn(__fmul_rn(p.fsd, __fadd_rn(g1c, g3)), g2c);
+      p.out1[idx] = __fadd_rn(__fmul_rn(p.fsd, __fadd_rn(g1s, g3)), g2s);
+    }
+  } else if (p.solver == SOLVER_MF) {
+    const float* mt = p.kind == 0 ? p.in0 : p.in1;
+    const float e = hook_contract(p, mt, b, j, false);
+    const float t21 = __fdiv_rn(__fmul_rn(__fmul_rn(-0.25f, e), p.a), sj);
+    const float t22 = __fdiv_rn(__fmul_rn(-p.v[j], p.a), two_sj);
+    const float fb = __fmul_rn(p.fsd, __fadd_rn(t21, t22));
+    if (p.kind == 0) {
+      p.out0[idx] = fb;
+    } else {
+      const float mu = p.in0[idx], sg = p.in2[idx];
+      const float mu2 = __fmul_rn(mu, mu);
+      const float term1 = __fmul_rn(__fsub_rn(p.c_lin, __fmul_rn(p.g2, mu2)), mu);
+      p.out0[idx] = __fadd_rn(term1, fb);
+      const float s1 = __fmul_rn(__fmul_rn(2.f, __fsub_rn(p.c_lin, __fmul_rn(p.g2x3, mu2))), sg);
+      const float sh = __fsub_rn(sg, 0.5f);
+      const float s2 = __fmul_rn(p.m2j, __fmul_rn(sh, sh));
+      const float s3 = __fadd_rn(p.opj, __fmul_rn(p.g2x2, mu2));
+      p.out1[idx] = __fadd_rn(__fadd_rn(s1, s2), s3);
+    }
+  } else if (p.solver == SOLVER_LV) {
+    const float e = hook_contract(p, p.in0, b, j, true);
+    p.out0[idx] = __fdiv_rn(__fmul_rn(-__fadd_rn(e, p.v[j]), p.a), two_sj);
+  } else {
+    const float e = hook_contract(p, p.in0, b, j, true);
+    const float g1 = __fdiv_rn(__fmul_rn(e, p.a), two_sj);
+    const float g2 = __fdiv_rn(__fmul_rn(p.v[j], p.a), two_sj);
+    const float grads = __fsub_rn(-g1, g2);
+    if (p.kind == 0) {
+      p.out0[idx] = grads;
+    } else {
+      const float c = p.in0[idx];
+      const float d0 = __fmul_rn(__fsub_rn(p.c_lin, __fmul_rn(c, c)), c);
+      p.out0[idx] = __fadd_rn(d0, __fmul_rn(p.fsd, grads));
+    }
+  }
+}
+
+extern "C" int ccvm_eval_hook(const ccvm_hook_desc* d, void* stream) {
+  if (!d) return fail(CCVM_E_INVALID, "null descriptor");
+  if (d->solver < 0 || d->solver > 3 || (d->kind != 0 && d->kind != 1)) return fail(CCVM_E_INVALID, "bad solver/kind");
+  if (d->n < 1 || d->batch < 1 || !d->q || !d->v || !d->in0 || !d->out0) return fail(CCVM_E_INVALID, "bad hook arguments");
+  if (d->solver == CCVM_SOLVER_DL && (!d->in1 || !d->out1)) return fail(CCVM_E_INVALID, "DL hooks need c, s and two outputs");
+  if (d->solver == CCVM_SOLVER_MF && d->kind == 1 && (!d->in1 || !d->in2 || !d->out1))
+    return fail(CCVM_E_INVALID, "MF drift needs mu, mu_tilde, sigma and two outputs");
+  HookParams p;
+  memset(&p, 0, sizeof(p));
+  p.q = d->q; p.v = d->v; p.in0 = d->in0; p.in1 = d->in1; p.in2 = d->in2;
+  p.out0 = d->out0; p.out1 = d->out1;
+  p.solver = d->solver; p.kind = d->kind; p.n = d->n; p.batch = d->batch;
+  double s = d->s;
+  p.svec = d->s_vec;
+  if (d->solver == CCVM_SOLVER_DL && d->kind == 1 && d->pump > 1.0) {  // dl_solver.py:140-141
+    s = sqrt(d->pump - 1.0);
+    p.svec = nullptr;
+  }
+  p.s = (float)s;
+  p.two_s = (float)(2.0 * s);
+  p.a = (float)(d->upper - d->lower);
+  p.b = (float)(d->upper + d->lower);
+  p.half_b = (float)((d->upper + d->lower) / 2.0);
+  if (d->solver == CCVM_SOLVER_DL) {
+    p.c_lin = (float)(-1.0 + d->pump * d->rate);
+    p.c_lin2 = (float)(-1.0 - d->pump * d->rate);
+    p.fsd = (float)(-(d->feedback_scale * (0.5 + d->rate)));
+  } else if (d->solver == CCVM_SOLVER_MF) {
+    p.c_lin = (float)(-(1.0 + d->j) + d->pump);
+    p.fsd = (float)d->feedback_scale;
+    p.g2 = (float)(d->g * d->g);
+    p.g2x2 = (float)(2.0 * d->g * d->g);
+    p.g2x3 = (float)(3.0 * d->g * d->g);
+    p.m2j = (float)(-2.0 * d->j);
+    p.opj = (float)(1.0 + d->j);
+  } else {
+    p.c_lin = (float)(-1.0 + d->pump);
+    p.fsd = (float)d->feedback_scale;
+  }
+  const size_t total = (size_t)d->batch * d->n;
+  hook_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+__global__ void change_variables_kernel(const float* __restrict__ x, float* __restrict__ out, size_t total, int n,
+                                        float a, float half_b, float s, const float* __restrict__ svec) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const float sj = svec ? svec[idx % n] : s;
+  // 0.5 * y / S * (u - l) + 0.5 * (u + l), left to right
+  out[idx] = __fadd_rn(__fmul_rn(__fdiv_rn(__fmul_rn(0.5f, x[idx]), sj), a), half_b);
+}
+
+extern "C" int ccvm_change_variables(const float* x, float* out, int32_t batch, int32_t n, double lower,
+                                     double upper, double s, const float* s_vec, void* stream) {
+  if (!x || !out || batch < 1 || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_change_variables");
+  const size_t total = (size_t)batch * n;
+  change_variables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, out, total, n, (float)(upper - lower), (float)(0.5 * (upper + lower)), (float)s, s_vec);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+__global__ void clamp_kernel(const float* __restrict__ x, float* __restrict__ out, size_t total, int n, float lo,
+                             float hi, const float* __restrict__ lo_t, const float* __restrict__ hi_t,
+                             long long bound_len) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const size_t bi = bound_len == (long long)total ? idx : idx % n;
+  const float l = lo_t ? lo_t[bi] : lo, h = hi_t ? hi_t[bi] : hi;
+  out[idx] = clampf(x[idx], l, h);
+}
+
+extern "C" int ccvm_fit_to_constraints(const float* x, float* out, int32_t batch, int32_t n, double lo, double hi,
+                                       const float* lo_t, const float* hi_t, int64_t bound_len, void* stream) {
+  if (!x || !out || batch < 1 || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_fit_to_constraints");
+  const size_t total = (size_t)batch * n;
+  if ((lo_t || hi_t) && bound_len != n && bound_len != (int64_t)total)
+    return fail(CCVM_E_INVALID, "tensor bounds must have n or batch*n elements");
+  clamp_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, total, n, (float)lo,
+                                                                                    (float)hi, lo_t, hi_t, bound_len);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+__global__ void scale_coefs_kernel(const float* __restrict__ q, const float* __restrict__ v, int n,
+                                   const float* __restrict__ f, long long flen, float* __restrict__ qo,
+                                   float* __restrict__ vo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nn = n * n;
+  if (idx >= nn) return;
+  const float fi = flen == 1 ? f[0] : f[idx];
+  qo[idx] = __fdiv_rn(q[idx], fi);
+  if (flen == 1) {
+    if (idx < n) vo[idx] = __fdiv_rn(v[idx], fi);
+  } else {
+    vo[idx] = __fdiv_rn(v[idx % n], fi);
+  }
+}
+
+extern "C" int ccvm_scale_coefs(const float* q, const float* v, int32_t n, const float* factor, int64_t factor_len,
+                                float* q_out, float* v_out, void* stream) {
+  if (!q || !v || !factor || !q_out || !v_out || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_scale_coefs");
+  if (factor_len != 1 && factor_len != (int64_t)n * n)
+    return fail(CCVM_E_INVALID, "scaling factor must have 1 or n*n elements");
+  scale_coefs_kernel<<<(n * n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(q, v, n, factor, factor_len, q_out, v_out);
+  CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
 }

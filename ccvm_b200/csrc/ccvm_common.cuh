@@ -42,8 +42,16 @@ __device__ __forceinline__ pf2 add2(const pf2& a, const pf2& b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(as_u64(d)) : "l"(as_u64(a)), "l"(as_u64(b)));
   return d;
 }
+// torch.clamp propagates NaN (a diverged trajectory must stay NaN); fminf/fmaxf
+// would silently replace it by a bound, so use the NaN-propagating FMNMX forms.
+__device__ __forceinline__ float clampf(float x, float lo, float hi) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(lo));
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(hi));
+  return r;
+}
 __device__ __forceinline__ pf2 clamp2(const pf2& a, float lo, float hi) {
-  return pk(fminf(fmaxf(a.x, lo), hi), fminf(fmaxf(a.y, lo), hi));
+  return pk(clampf(a.x, lo, hi), clampf(a.y, lo, hi));
 }
 __device__ __forceinline__ float fast_sqrt(float x) {
   float r;

@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256, 1) sde_kernel(const SdeParams p) {
         const pf2 a0 = st[0][i / 2][jj], a1 = st[1][i / 2][jj], mm = meas[i / 2][jj];
         const float v0 = (i & 1) ? a0.y : a0.x, v1 = (i & 1) ? a1.y : a1.x, vm = (i & 1) ? mm.y : mm.x;
         if constexpr (SOLVER == SOLVER_DL) {
-          p.out0[o] = fminf(fmaxf(v0, -sclamp[jj]), sclamp[jj]);
+          p.out0[o] = clampf(v0, -sclamp[jj], sclamp[jj]);
           p.out1[o] = v1;
         } else if constexpr (SOLVER == SOLVER_MF) {
           p.out0[o] = v0;

@@ -1,0 +1,404 @@
+// Persistent Euler-Maruyama kernel, TMEM variant (n <= 128): the production path at the
+// benchmark sizes.  Same contract as sde_kernel.cuh; what changes is where the operands live.
+//
+// Why (ncu, profiles/r1_ncu_sde_dl_adam_v1.txt): with the scaled matrix Qs in shared memory the
+// loop was bound by shared-memory wavefronts (every LDS.128 costs 4 wavefronts no matter how much
+// of it is a broadcast; 64 wavefronts per k per SM against 32 FMA-pipe cycles).  Qs is constant
+// for the whole run and each thread only ever needs the 4 columns of its own tile, so:
+//
+//   * every thread keeps ITS slice Qs[0..NP)[4 cols] in its own TMEM lane (4*NP <= 512 columns,
+//     written once with tcgen05.st) and streams it back with one tcgen05.ld.x16 per 4 k --
+//     TMEM delivers > 800 B/clk/SM (tools/ubench_drift.cu) and does not touch the LSU;
+//   * FFMA2 takes a scalar broadcast operand (SASS `Rq.F32`), so the natural (non-duplicated)
+//     Qs feeds the packed FMA directly:  acc(b0,b1 ; j) += x(b0,b1 ; k) * Qs[k][j];
+//   * only the contraction input X goes through shared memory: one LDS.128 (DL: c0,c1,s0,s1) or
+//     LDS.64 per thread per k, from a double-buffered panel X[buf][k][row-group][2K];
+//   * a thread owns 2 trajectories x K quadratures x 4 variables of every state array;
+//   * a CTA runs NG independent trajectory groups (<= 128 threads each, one warp per SM
+//     sub-partition and group), each with its own named barrier: the groups drift out of phase, so
+//     one group's FMA/LSU-bound contraction overlaps the other's ALU/MUFU-bound noise + update.
+//     Threads t and t+128 share a TMEM lane and therefore the same column group.
+#pragma once
+#include "ccvm_common.cuh"
+#include "sde_kernel.cuh"
+
+namespace ccvm {
+
+struct TmemLaunch {
+  int rg;      // trajectory pairs per group
+  int ng;      // groups per CTA
+  int gt;      // threads per group (128 when ng > 1)
+  int xs;      // floats per k-row of a group's X panel
+  int tcols;   // TMEM columns to allocate (power of two >= 4*NP, >= 32)
+};
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t base, int cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(__float_as_uint(a)),
+               "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&r)[16]) {
+  uint32_t u[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(addr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Adam transform on a 4-variable tile of trajectory pairs (dl_solver.py:699-727 and siblings).
+__device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4], const SdeParams& p, float ib1,
+                                           float ib2) {
+  const pf2 b1 = dup(p.beta1), b2 = dup(p.beta2), o1 = dup(p.omb1), o2 = dup(p.omb2);
+  const pf2 i1 = dup(ib1), i2 = dup(ib2), al = dup(p.adam_alpha), eps = dup(1e-8f);
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const pf2 gr = g[jj];
+    m[jj] = fma2(m[jj], b1, mul2(gr, o1));
+    const pf2 mh = mul2(m[jj], i1);
+    pf2 upd;
+    if (!p.beta2_is_one) {
+      v[jj] = fma2(v[jj], b2, mul2(mul2(gr, gr), o2));
+      const pf2 den = add2(sqrt2(mul2(v[jj], i2)), eps);
+      upd = mul2(al, div2(mh, den));
+    } else {
+      upd = mul2(al, mh);
+    }
+    g[jj] = p.add_assign ? add2(gr, upd) : upd;
+  }
+}
+
+template <int SOLVER, bool ADAM>
+__global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
+  constexpr int K = SolverTraits<SOLVER>::K;
+  constexpr int RW = 2 * K;  // floats per (k, trajectory pair): (b0,b1) or (c0,c1,s0,s1)
+
+  extern __shared__ __align__(16) float smem[];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x;
+  const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = L.xs, T = p.iterations;
+  const int grp = tid / L.gt, l = tid - grp * L.gt;  // group and lane-in-group (== TMEM lane)
+  const int warp = tid >> 5;
+
+  float* hv = smem;                                   // [NP]
+  float* av = hv + NP;                                // [NP]
+  float* X = av + NP + (size_t)grp * 2 * NP * XS;     // this group's [2][NP][XS] panel
+
+  // ------------------------------------------------------------------ prologue
+  if (warp == 0) tmem_alloc(&tmem_slot, L.tcols);
+  for (int j = tid; j < NP; j += blockDim.x) {
+    float a = 0.f;
+    if (j < N) a = p.a_half / (p.drift_s_vec ? p.drift_s_vec[j] : p.drift_s);
+    av[j] = a;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  for (int j = tid; j < NP; j += blockDim.x) {
+    float h = 0.f;
+    if (j < N) {
+      float cs = 0.f;
+      for (int i = 0; i < N; ++i) cs += p.q[i * N + j];
+      h = -av[j] * (p.b_half * cs + p.v[j]);
+    }
+    hv[j] = h;
+  }
+  for (int i = l; i < 2 * NP * XS; i += L.gt) X[i] = 0.f;
+
+  const int rg = l % RG, cg = l / RG;
+  const bool active = cg < CG;
+  const int cgc = active ? cg : 0;
+  const int j0 = 4 * cgc;
+  const uint32_t tlane = tbase + ((uint32_t)((l >> 5) * 32) << 16);  // this warp's TMEM lane quadrant
+  if (grp == 0) {
+    // every lane stores its own copy of the 4 columns it contracts against
+    for (int k = 0; k < NP; ++k) {
+      float qv[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj;
+        qv[jj] = (k < N && j < N) ? -av[k] * av[j] * p.q[k * N + j] : 0.f;
+      }
+      tmem_st4(tlane + 4 * k, qv[0], qv[1], qv[2], qv[3]);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // ------------------------------------------------------------------ thread tile
+  const long long gb0 = ((long long)blockIdx.x * L.ng + grp) * (2 * RG) + 2 * rg;  // first of 2 trajectories
+  float hreg[4], sclamp[4];
+  bool colok[4];
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    colok[jj] = active && (j0 + jj < N);
+    hreg[jj] = hv[j0 + jj];
+    sclamp[jj] = colok[jj] ? (p.clamp_s_vec ? p.clamp_s_vec[j0 + jj] : p.clamp_s) : 0.f;
+  }
+
+  pf2 st[2][4];             // st[0] = c | mu, st[1] = s | sigma  (x: trajectory gb0, y: gb0+1)
+  pf2 am[K][4], avv[K][4];  // Adam moments of the tracked arrays
+  pf2 W[K][4];              // noise of the current iteration
+  pf2 meas[4];              // MF: clamped measurement
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    st[0][jj] = dup(0.f);
+    st[1][jj] = dup(SOLVER == SOLVER_MF ? 0.5f : 0.f);
+    meas[jj] = dup(0.f);
+#pragma unroll
+    for (int q = 0; q < K; ++q) {
+      am[q][jj] = dup(0.f);
+      avv[q][jj] = dup(0.f);
+      W[q][jj] = dup(0.f);
+    }
+  }
+
+  const uint2 key = make_uint2(p.seed_lo, p.seed_hi ^ p.off_hi);
+
+  auto draw = [&](int t) {
+    if (p.noise == nullptr) {
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const unsigned long long gb = (unsigned long long)(p.traj_base + gb0 + i);
+          const uint4 r = philox4x32_10(
+              make_uint4((uint32_t)gb, (uint32_t)t,
+                         (uint32_t)cgc | ((uint32_t)q << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
+              key);
+          float n0, n1, n2, n3;
+          box_muller(r.x, r.y, n0, n1);
+          box_muller(r.z, r.w, n2, n3);
+          const float nn[4] = {n0, n1, n2, n3};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float w = colok[jj] ? nn[jj] : 0.f;
+            if (i) W[q][jj].y = w; else W[q][jj].x = w;
+          }
+        }
+    } else {
+#pragma unroll
+      for (int q = 0; q < K; ++q)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            float w = 0.f;
+            const long long b = gb0 + i;
+            if (colok[jj] && b < p.batch)
+              w = p.noise[(((size_t)t * K + q) * N + (j0 + jj)) * (size_t)p.noise_batch + (size_t)(p.traj_base + b)];
+            if (i) W[q][jj].y = w; else W[q][jj].x = w;
+          }
+    }
+  };
+
+  // stores the tile's contraction input for the next iteration: X[buf][k = j0+jj][rg][2K]
+  const int xoff = (cgc * RW * RG) & 31 & ~(RW - 1);
+  auto stage = [&](int buf, const pf2 (&a)[4], const pf2 (&b)[4]) {
+    if (!active) return;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      float* dst = X + ((size_t)buf * NP + (j0 + jj)) * XS + xoff + RW * rg;
+      if constexpr (K == 2) *reinterpret_cast<float4*>(dst) = make_float4(a[jj].x, a[jj].y, b[jj].x, b[jj].y);
+      else *reinterpret_cast<float2*>(dst) = make_float2(a[jj].x, a[jj].y);
+    }
+  };
+
+  const int bar_id = 1 + grp, bar_n = L.gt;
+  const float4* sched4 = reinterpret_cast<const float4*>(p.sched);
+  float4 sa = __ldg(sched4), sb = __ldg(sched4 + 1);
+
+  if constexpr (SOLVER == SOLVER_MF) {
+    draw(0);  // measurement of iteration 0 (mf_solver.py:551-554): mu = 0
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      meas[jj] = clamp2(fma2(dup(sa.x), W[0][jj], st[0][jj]), -sclamp[jj], sclamp[jj]);
+    group_barrier(bar_id, bar_n);  // zero fill of the panel done
+    stage(0, meas, meas);
+  }
+  group_barrier(bar_id, bar_n);
+
+  // ------------------------------------------------------------------ main loop
+  for (int t = 0; t < T; ++t) {
+    const int buf = t & 1;
+    const float4 ca = sa, cb = sb;
+    if (t + 1 < T) {
+      sa = __ldg(sched4 + 2 * (t + 1));
+      sb = __ldg(sched4 + 2 * (t + 1) + 1);
+    }
+
+    // ---- drift contraction: acc = h + X . Qs   (Qs from TMEM, X from shared memory)
+    pf2 acc[K][4];
+#pragma unroll
+    for (int q = 0; q < K; ++q)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[q][jj] = dup(hreg[jj]);
+    {
+      const float* xp = X + (size_t)buf * NP * XS + RW * rg;
+      float qn[16], qnx[16];
+      tmem_ld16(tlane, qnx);
+      for (int kc = 0; kc < CG; ++kc) {
+        const float* xrow = xp + ((kc * RW * RG) & 31 & ~(RW - 1));
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) qn[i] = qnx[i];
+        if (kc + 1 < CG) tmem_ld16(tlane + 16 * (kc + 1), qnx);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          pf2 xv[K];
+          if constexpr (K == 2) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xrow);
+            xv[0] = pk(x4.x, x4.y);
+            xv[1] = pk(x4.z, x4.w);
+          } else {
+            const float2 x2 = *reinterpret_cast<const float2*>(xrow);
+            xv[0] = pk(x2.x, x2.y);
+          }
+#pragma unroll
+          for (int q = 0; q < K; ++q)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qn[4 * kk + jj]), acc[q][jj]);
+          xrow += XS;
+        }
+        xp += 4 * XS;
+      }
+    }
+
+    // ---- elementwise SDE step (same arithmetic as sde_kernel.cuh)
+    if constexpr (SOLVER == SOLVER_DL) {
+      draw(t);
+      if constexpr (ADAM) {
+        adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
+        adam_tile4(acc[1], am[1], avv[1], p, cb.y, cb.z);
+      }
+      const pf2 gain = dup(ca.x), d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
+      const pf2 mdt = dup(-p.dt), half = dup(0.5f);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const pf2 c = st[0][jj], s = st[1][jj];
+        const pf2 r2 = fma2(c, c, mul2(s, s));
+        const pf2 rt = sqrt2(add2(r2, half));
+        const pf2 uc = fma2(r2, mdt, d1), us = fma2(r2, mdt, d2);
+        const pf2 nc = mul2(mul2(rt, n1), W[0][jj]);
+        const pf2 ns = mul2(mul2(rt, n2), W[1][jj]);
+        st[0][jj] = add2(c, fma2(c, uc, fma2(gain, acc[0][jj], nc)));
+        st[1][jj] = add2(s, fma2(s, us, fma2(gain, acc[1][jj], ns)));
+      }
+      stage(buf ^ 1, st[0], st[1]);
+    } else if constexpr (SOLVER == SOLVER_MF) {
+      const pf2 fs = dup(p.fs);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[0][jj] = mul2(fs, acc[0][jj]);
+      if constexpr (ADAM) adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
+      const pf2 pr = dup(ca.y), sj = dup(ca.w), opj = dup(cb.x), m2j = dup(-2.f * ca.z);
+      const pf2 g2 = dup(p.g2), dtp = dup(p.dt), mhalf = dup(-0.5f);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const pf2 mu = st[0][jj], sg = st[1][jj];
+        const pf2 g2m2 = mul2(mul2(mu, mu), g2);
+        const pf2 a1 = fma2(g2m2, dup(-1.f), pr);
+        const pf2 sh = add2(sg, mhalf);
+        const pf2 dmu = fma2(a1, mu, acc[0][jj]);
+        const pf2 diff = mul2(mul2(sh, sj), W[0][jj]);
+        st[0][jj] = fma2(dtp, add2(dmu, diff), mu);
+        const pf2 a3 = fma2(g2m2, dup(-3.f), pr);
+        const pf2 t1 = mul2(mul2(a3, sg), dup(2.f));
+        const pf2 t2 = mul2(mul2(sh, sh), m2j);
+        const pf2 t3 = fma2(g2m2, dup(2.f), opj);
+        st[1][jj] = fma2(dtp, add2(add2(t1, t2), t3), sg);
+      }
+      if (t + 1 < T) {
+        draw(t + 1);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          meas[jj] = clamp2(fma2(dup(sa.x), W[0][jj], st[0][jj]), -sclamp[jj], sclamp[jj]);
+        stage(buf ^ 1, meas, meas);
+      }
+    } else {
+      draw(t);
+      if constexpr (ADAM) adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
+      const pf2 dtfs = dup(p.dtfs), sig = dup(p.sig), mdt = dup(-p.dt), d1 = dup(ca.y);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const pf2 c = st[0][jj];
+        pf2 inc = fma2(dtfs, acc[0][jj], mul2(sig, W[0][jj]));
+        if constexpr (SOLVER == SOLVER_PLV) inc = fma2(c, fma2(mul2(c, c), mdt, d1), inc);
+        st[0][jj] = clamp2(add2(c, inc), -sclamp[jj], sclamp[jj]);
+      }
+      stage(buf ^ 1, st[0], st[0]);
+    }
+
+    // ---- optional evolution snapshot (dl_solver.py:557-564)
+    if (p.evolution_step > 0) {
+      int sidx = -1;
+      if (t % p.evolution_step == 0) sidx = t / p.evolution_step;
+      else if (t + 1 >= T) sidx = (T - 1) / p.evolution_step + 1;
+      if (sidx >= 0 && sidx < p.num_samples && active) {
+        constexpr int NS = SolverTraits<SOLVER>::NSTATE;
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const long long b = gb0 + i;
+              if (b < p.batch && colok[jj])
+                p.samples[(((size_t)a * p.num_samples + sidx) * p.batch + b) * N + j0 + jj] =
+                    i ? st[a][jj].y : st[a][jj].x;
+            }
+      }
+    }
+    group_barrier(bar_id, bar_n);
+  }
+
+  // ------------------------------------------------------------------ results
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long b = gb0 + i;
+      if (b >= p.batch) continue;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        if (!colok[jj]) continue;
+        const size_t o = (size_t)b * N + j0 + jj;
+        const float v0 = i ? st[0][jj].y : st[0][jj].x, v1 = i ? st[1][jj].y : st[1][jj].x;
+        const float vm = i ? meas[jj].y : meas[jj].x;
+        if constexpr (SOLVER == SOLVER_DL) {
+          p.out0[o] = clampf(v0, -sclamp[jj], sclamp[jj]);
+          p.out1[o] = v1;
+        } else if constexpr (SOLVER == SOLVER_MF) {
+          p.out0[o] = v0;
+          p.out1[o] = vm;
+          p.out2[o] = v1;
+        } else {
+          p.out0[o] = v0;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_free(tbase, L.tcols);
+}
+
+}  // namespace ccvm

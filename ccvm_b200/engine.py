@@ -144,15 +144,17 @@ def epilogue(state, q, v, *, map1=None, post_processor=None, pp_iterations=10, p
 
 
 def compute_energy(x, q, v, scaled_by=1.0):
-    nat.require_cuda()
-    dev = _device_of(x)
-    xc, qc, vc = nat.as_f32(x, dev), nat.as_f32(q, dev), nat.as_f32(v, dev)
+    """E_b = (1/2 x_b Q x_b + V x_b) * scaled_by on the device; result returned where x lives."""
+    home = x.device
+    xg = to_engine_device(x)
+    dev = xg.device
+    xc, qc, vc = nat.as_f32(xg, dev), nat.as_f32(q, dev), nat.as_f32(v, dev)
     b, n = xc.shape
     en = torch.empty((b,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nat.check(nat.load().ccvm_compute_energy(nat.ptr(xc), nat.ptr(qc), nat.ptr(vc), float(scaled_by), b, n,
                                                  nat.ptr(en), nat.current_stream_ptr(dev)))
-    return en
+    return en.to(home)
 
 
 def postprocess_grad_descent(x, q, v, iterations, step_size, lower, upper):
@@ -195,15 +197,17 @@ def solution_stats(energy, optimal_value):
 
 
 def scaling_factor(q, multiplier):
-    """Device 0-d fp32 tensor sqrt(sum|Q|) * multiplier (ccvm_solver.py:134-150)."""
-    nat.require_cuda()
-    dev = _device_of(q)
-    qc = nat.as_f32(q, dev)
+    """0-d fp32 tensor sqrt(sum|Q|) * multiplier (ccvm_solver.py:134-150), reduced on the device and
+    returned where q lives."""
+    home = q.device
+    qg = to_engine_device(q)
+    dev = qg.device
+    qc = nat.as_f32(qg, dev)
     out = torch.empty((), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nat.check(nat.load().ccvm_scaling_factor(nat.ptr(qc), int(qc.shape[0]), float(multiplier), nat.ptr(out),
                                                  nat.current_stream_ptr(dev)))
-    return out
+    return out.to(home)
 
 
 def microbench_fp32(mode=1):
@@ -212,3 +216,108 @@ def microbench_fp32(mode=1):
     val = C.c_double(0.0)
     nat.check(nat.load().ccvm_microbench_fp32(int(mode), C.byref(val), nat.current_stream_ptr()))
     return val.value
+
+
+def to_engine_device(t):
+    """Tensors handed to a kernel must be on a CUDA device; CPU tensors are copied to the current
+    one (plumbing).  Without a GPU this raises -- there is no CPU implementation to fall back to."""
+    nat.require_cuda()
+    return t if t.is_cuda else t.to("cuda")
+
+
+def _s_args(S, n, dev):
+    """(scalar, device-vector-or-None) for a saturation value that may be a 1-D / (B, N) tensor."""
+    if torch.is_tensor(S) and S.numel() > 1:
+        vec = S if S.dim() == 1 else S[0]
+        if vec.numel() != n:
+            raise ValueError("Tensor S size should be equal to problem size.")
+        return 0.0, nat.as_f32(vec, dev)
+    return (float(S.item()) if torch.is_tensor(S) else float(S)), None
+
+
+def eval_hook(solver, kind, q, v, inputs, lower, upper, S, pump=0.0, rate=0.0, feedback_scale=0.0, j=0.0,
+              g=0.0):
+    """calculate_drift / calculate_grads of ``solver`` on explicit inputs; returns a tuple of
+    tensors on the inputs' device."""
+    src = inputs[0]
+    home = src.device
+    ins = [nat.as_f32(to_engine_device(t), to_engine_device(t).device) for t in inputs]
+    dev = ins[0].device
+    b, n = ins[0].shape
+    qc, vc = nat.as_f32(q, dev), nat.as_f32(v, dev)
+    d = nat.HookDesc()
+    d.solver, d.kind, d.n, d.batch = solver, 1 if kind == "drift" else 0, n, b
+    d.q, d.v = nat.ptr(qc), nat.ptr(vc)
+    d.in0 = nat.ptr(ins[0])
+    d.in1 = nat.ptr(ins[1]) if len(ins) > 1 else None
+    d.in2 = nat.ptr(ins[2]) if len(ins) > 2 else None
+    d.lower, d.upper = float(lower), float(upper)
+    s_val, s_vec = _s_args(S, n, dev)
+    d.s, d.s_vec = s_val, nat.ptr(s_vec)
+    d.pump, d.rate, d.feedback_scale, d.j, d.g = float(pump), float(rate), float(feedback_scale), float(j), float(g)
+    two = solver == nat.SOLVER_DL or (solver == nat.SOLVER_MF and kind == "drift")
+    o0 = torch.empty((b, n), dtype=torch.float32, device=dev)
+    o1 = torch.empty((b, n), dtype=torch.float32, device=dev) if two else None
+    d.out0, d.out1 = nat.ptr(o0), nat.ptr(o1)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_eval_hook(C.byref(d), nat.current_stream_ptr(dev)))
+    outs = (o0, o1) if two else (o0,)
+    return tuple(o.to(home) for o in outs)
+
+
+def change_variables(x, lower, upper, S):
+    home = x.device
+    xc = nat.as_f32(to_engine_device(x), to_engine_device(x).device)
+    dev = xc.device
+    b, n = xc.shape
+    s_val, s_vec = _s_args(S, n, dev)
+    out = torch.empty_like(xc)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_change_variables(nat.ptr(xc), nat.ptr(out), b, n, float(lower), float(upper),
+                                                   s_val, nat.ptr(s_vec), nat.current_stream_ptr(dev)))
+    return out.to(home)
+
+
+def clamp(x, lo, hi):
+    """torch.clamp(x, lo, hi) with scalar or tensor bounds ((N,) or x-shaped), on the device."""
+    home = x.device
+    xc = nat.as_f32(to_engine_device(x), to_engine_device(x).device)
+    dev = xc.device
+    b, n = xc.shape
+    lo_t = nat.as_f32(lo, dev) if torch.is_tensor(lo) and lo.numel() > 1 else None
+    hi_t = nat.as_f32(hi, dev) if torch.is_tensor(hi) and hi.numel() > 1 else None
+    blen = 0
+    for t in (lo_t, hi_t):
+        if t is not None:
+            if blen and t.numel() != blen:
+                raise ValueError("clamp bounds must have matching shapes")
+            blen = t.numel()
+    lo_s = 0.0 if lo_t is not None else float(lo)
+    hi_s = 0.0 if hi_t is not None else float(hi)
+    if (lo_t is None) != (hi_t is None):  # mixed scalar/tensor bounds: materialise the scalar one
+        fill = torch.full((blen,), lo_s if lo_t is None else hi_s, dtype=torch.float32, device=dev)
+        lo_t, hi_t = (fill, hi_t) if lo_t is None else (lo_t, fill)
+    out = torch.empty_like(xc)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_fit_to_constraints(nat.ptr(xc), nat.ptr(out), b, n, lo_s, hi_s, nat.ptr(lo_t),
+                                                     nat.ptr(hi_t), blen, nat.current_stream_ptr(dev)))
+    return out.to(home)
+
+
+def scale_coefs(q, v, factor):
+    """(q / factor, v / factor) computed on the device; results live where q lived."""
+    home = q.device
+    qc = nat.as_f32(to_engine_device(q), to_engine_device(q).device)
+    dev = qc.device
+    vc = nat.as_f32(v, dev)
+    n = qc.shape[0]
+    f = factor if torch.is_tensor(factor) else torch.tensor(float(factor))
+    f = nat.as_f32(f, dev).reshape(-1)
+    if f.numel() not in (1, n * n):
+        raise ValueError("scaling_factor must be a scalar or an (n, n) tensor")
+    q_out = torch.empty_like(qc)
+    v_out = torch.empty((n,) if f.numel() == 1 else (n, n), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_scale_coefs(nat.ptr(qc), nat.ptr(vc), n, nat.ptr(f), f.numel(), nat.ptr(q_out),
+                                              nat.ptr(v_out), nat.current_stream_ptr(dev)))
+    return q_out.to(home), v_out.to(home)

@@ -1,0 +1,60 @@
+"""Multi-GPU layer: one process per GPU, trajectories (or instances) sharded across ranks with NO
+data-path collective; a single collective round at the end merges the per-rank results.
+
+The reference has no multi-device code; the contract here is "same result as one
+GPU over the union of the shards": noise is keyed by the GLOBAL trajectory index
+(``traj_base``), the best objective is the min over ranks, the winner's solution vector comes
+from its owner, and success counters add up.
+
+Collective: one ``all_gather`` of a packed [best_energy, owner_local_index, counts(7), x(N)]
+record per rank (N+9 floats; latency-bound, NVLink bandwidth irrelevant), after which every rank
+selects the winner locally -- no second round, no host synchronisation.
+"""
+import torch
+import torch.distributed as dist
+
+N_COUNTS = 7
+
+
+def shard_bounds(total, world_size, rank):
+    """Contiguous split of ``total`` items: (start, count) of ``rank``; remainders go to the
+    lowest ranks, so shard sizes differ by at most one."""
+    base, rem = divmod(int(total), int(world_size))
+    count = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    return start, count
+
+
+def instance_owner(index, world_size):
+    """Round-robin owner of instance ``index`` in a sweep."""
+    return index % world_size
+
+
+def pack_local_result(energy, problem_variables, counts, traj_base):
+    """Per-rank record from the local objective values (B_local,), the local solution matrix
+    (B_local, N) and the 7 local success counters.  Everything stays on the device."""
+    e_min, idx = torch.min(energy, dim=0)
+    rec = torch.empty(2 + N_COUNTS + problem_variables.shape[1], dtype=torch.float32, device=energy.device)
+    rec[0] = e_min
+    rec[1] = (idx + traj_base).to(torch.float32)
+    rec[2:2 + N_COUNTS] = torch.as_tensor(counts, dtype=torch.float32, device=energy.device)
+    rec[2 + N_COUNTS:] = problem_variables[idx]
+    return rec
+
+
+def merge_results(record, group=None):
+    """All-gather the per-rank records and reduce them identically on every rank.
+
+    Returns (best_objective_value tensor = max(-E) over all ranks, global trajectory index of
+    the winner, summed counts (7,), winner's solution vector (N,)).  Ties go to the lowest rank."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        gathered = record.unsqueeze(0)
+    else:
+        world = dist.get_world_size(group)
+        flat = torch.empty(world * record.numel(), dtype=record.dtype, device=record.device)
+        dist.all_gather_into_tensor(flat, record.contiguous(), group=group)
+        gathered = flat.view(world, record.numel())
+    owner = torch.argmin(gathered[:, 0])
+    best = -gathered[owner, 0]
+    counts = gathered[:, 2:2 + N_COUNTS].sum(dim=0)
+    return best, gathered[owner, 1], counts, gathered[owner, 2 + N_COUNTS:]

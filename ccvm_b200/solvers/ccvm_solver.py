@@ -116,13 +116,8 @@ class CCVMSolver(ABC):
 
     # -------------------------------------------------------------- shared operators
     def _change_variables_boxqp(self, problem_variables, lower_limit=0, upper_limit=1, S=1):
-        """x = 0.5 * y / S * (u - l) + 0.5 * (u + l)  (reference dl_solver.py:219-235).
-        Evaluated by the engine's fused epilogue kernel in map-only mode."""
-        dev = problem_variables.device
-        scale = _half_range_over_s(S, lower_limit, upper_limit, dev)
-        pv, _ = engine.epilogue(problem_variables, *_dummy_qv(problem_variables), want_energy=False,
-                                map1=(scale, 0.5 * (upper_limit + lower_limit)))
-        return pv
+        """x = 0.5 * y / S * (u - l) + 0.5 * (u + l)  (reference dl_solver.py:219-235), on the device."""
+        return engine.change_variables(problem_variables, lower_limit, upper_limit, S)
 
     def _fit_to_constraints_boxqp(self, c, lower_clamp, upper_clamp):
         """Box clamp (reference dl_solver.py:237-250).  Bounds may be scalars or tensors."""
@@ -208,7 +203,8 @@ class CCVMSolver(ABC):
             num_samples += 1
         return num_samples, evolution_file
 
-    def _engine_solve(self, solver_id, algorithm, batch_size, iterations, S, hyperparameters=None, **scalars):
+    def _engine_solve(self, solver_id, algorithm, batch_size, iterations, S, evolution_step_size,
+                      hyperparameters=None, **scalars):
         """Common body of every ``_solve`` / ``_solve_adam``: one engine call, evolution samples
         stored on ``self`` the way the reference does."""
         if self.device != "cuda":
@@ -217,12 +213,12 @@ class CCVMSolver(ABC):
         self._require_stock_hooks()
         s_vec, s_val = (S if S.ndim == 1 else S[0], 0.0) if torch.is_tensor(S) and S.numel() > 1 else (None, float(S))
         lower, upper = self.solution_bounds
-        plan = getattr(self, "_evolution", None)
+        num_samples, _ = self._evolution_plan(None, iterations, evolution_step_size, "unused")
         outs, samples = engine.solve(
             solver_id, algorithm, self.q_matrix, self.v_vector, batch_size, iterations,
             lower=lower, upper=upper, s=s_val, s_vec=s_vec, hyperparameters=hyperparameters,
-            noise=self.noise_source, evolution_step=plan[0] if plan else None,
-            num_samples=plan[1] if plan else 0, **scalars)
+            noise=self.noise_source, evolution_step=evolution_step_size or None,
+            num_samples=num_samples or 0, **scalars)
         self._samples = samples
         return outs
 
@@ -234,7 +230,6 @@ class CCVMSolver(ABC):
         batch_size = self.batch_size
         num_samples, evolution_file = self._evolution_plan(instance, iterations, evolution_step_size,
                                                            evolution_file)
-        self._evolution = (evolution_step_size, num_samples) if evolution_step_size else None
         self._samples = None
         if self.device == "cuda":
             torch.cuda.synchronize()
@@ -393,19 +388,3 @@ class CCVMSolver(ABC):
 # ------------------------------------------------------------------------ helpers
 def _as_float(x):
     return float(x.item()) if torch.is_tensor(x) else float(x)
-
-
-def _half_range_over_s(S, lower, upper, device):
-    """0.5 * (u - l) / S as a scalar or a per-variable tensor."""
-    half = 0.5 * (upper - lower)
-    if torch.is_tensor(S) and S.numel() > 1:
-        vec = S if S.ndim == 1 else S[0]
-        return engine.reciprocal_scale(vec.to(device), half)
-    return half / _as_float(S)
-
-
-def _dummy_qv(x):
-    """Map-only epilogue calls still need valid (unused) Q/V pointers."""
-    n = x.shape[-1]
-    z = torch.zeros((n * n + n,), dtype=torch.float32, device=x.device)
-    return z[: n * n].view(n, n), z[n * n:]

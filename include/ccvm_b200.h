@@ -176,6 +176,58 @@ int ccvm_solution_stats(const float* energy, int32_t batch, double optimal_value
 int ccvm_scaling_factor(const float* q, int32_t n, double multiplier, float* out, void* stream);
 
 /*
+ * The reference's per-solver operator hooks evaluated on arbitrary inputs (the "de-facto
+ * operator API" its tests exercise, tests/unit/solvers/test_mf_solver.py:63-204).
+ *
+ * Replaces: _calculate_drift_boxqp / _calculate_grads_boxqp of DLSolver (dl_solver.py:117-217),
+ *           MFSolver (mf_solver.py:141-233), LangevinSolver (langevin_solver.py:117-166),
+ *           PumpedLangevinSolver (pumped_langevin_solver.py:95-147).
+ * kind 0 = calculate_grads, 1 = calculate_drift.  Inputs/outputs are device (batch, n) tensors:
+ *   DL   in0 = c, in1 = s                -> out0, out1 (c and s parts)
+ *   MF   drift: in0 = mu, in1 = mu_tilde, in2 = sigma -> out0 = drift_mu, out1 = drift_sigma
+ *        grads: in0 = mu_tilde                       -> out0
+ *   Langevin / PumpedLangevin: in0 = c   -> out0
+ * `pump` is the hook's pump argument (MF: instantaneous pump; PumpedLangevin: p), `rate` the DL
+ * pump-rate multiplier.
+ */
+typedef struct ccvm_hook_desc {
+  int32_t solver;
+  int32_t kind;
+  int32_t n;
+  int32_t batch;
+  const float* q;
+  const float* v;
+  const float* in0;
+  const float* in1;
+  const float* in2;
+  double lower, upper;
+  double s;
+  const float* s_vec; /* optional device [n] */
+  double pump, rate, feedback_scale, j, g;
+  float* out0;
+  float* out1;
+} ccvm_hook_desc;
+
+int ccvm_eval_hook(const ccvm_hook_desc* desc, void* stream);
+
+/* Replaces CCVMSolver.change_variables (dl_solver.py:219-235): out = 0.5*x/S*(u-l) + 0.5*(u+l),
+ * evaluated in the reference's operation order.  s_vec optional device [n]. */
+int ccvm_change_variables(const float* x, float* out, int32_t batch, int32_t n, double lower,
+                          double upper, double s, const float* s_vec, void* stream);
+
+/* Replaces CCVMSolver.fit_to_constraints (dl_solver.py:237-250): out = clamp(x, lo, hi).
+ * Bounds are scalars, or device tensors of `bound_len` = n (per variable) or batch*n elements. */
+int ccvm_fit_to_constraints(const float* x, float* out, int32_t batch, int32_t n, double lo,
+                            double hi, const float* lo_t, const float* hi_t, int64_t bound_len,
+                            void* stream);
+
+/* Replaces ProblemInstance.scale_coefs (problem_instance.py:243-255): q_out = q / f, v_out = v / f.
+ * `factor` is a device tensor of factor_len = 1 (scalar) or n*n elements; in the latter case v is
+ * broadcast against it like torch does and v_out has n*n elements. */
+int ccvm_scale_coefs(const float* q, const float* v, int32_t n, const float* factor,
+                     int64_t factor_len, float* q_out, float* v_out, void* stream);
+
+/*
  * Host-buffer convenience used for end-to-end timing: copies Q and V from HOST memory,
  * runs ccvm_solve + ccvm_epilogue + ccvm_solution_stats on `stream`, copies energy[batch] and the
  * 9-word stats block back to HOST memory and synchronises the stream.  `solve` and `epi` carry

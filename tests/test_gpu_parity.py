@@ -1,0 +1,186 @@
+"""Parity proper: the CUDA loops (through the C ABI) against the CPU oracle on the same seeded
+inputs and the same replayed noise, at sizes the oracle finishes in seconds; plus the Philox
+production mode (reproducibility, shard invariance, noise statistics, statistical equivalence).
+
+Tolerance for replay mode (north_star): per-trajectory final objective within 1e-3 relative of
+the reference arithmetic (2e-3 for DL-adam, whose interior solutions are more sensitive,
+SURVEY.md 8c "Sensitivity")."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ccvm_oracle as O
+from ccvm_b200 import engine as E, _native as nat
+
+pytestmark = pytest.mark.gpu
+
+HP = dict(alpha=0.001, beta1=0.9, beta2=0.999, add_assign=False)
+
+
+def instance(n, seed, mult):
+    q, v = O.synthetic_boxqp(n, seed)
+    f = O.scaling_factor(q, mult)
+    return q / f, v / f, float(f)
+
+
+def rel_obj_err(x_gpu, x_ref, q, v, sb):
+    e_gpu, e_ref = O.energy(x_gpu.cpu(), q, v, sb), O.energy(x_ref, q, v, sb)
+    return ((e_gpu - e_ref).abs() / e_ref.abs().clamp_min(1e-6)).max().item()
+
+
+CASES = [
+    # (solver, adam, n, batch, iterations, tolerance on the objective)
+    ("dl", False, 70, 300, 400, 1e-3), ("dl", True, 70, 300, 400, 2e-3),
+    ("mf", False, 70, 300, 400, 1e-3), ("mf", True, 70, 300, 400, 1e-3),
+    ("lv", False, 70, 300, 400, 1e-3), ("lv", True, 70, 300, 400, 1e-3),
+    ("plv", False, 70, 300, 400, 1e-3), ("plv", True, 70, 300, 400, 1e-3),
+    ("dl", False, 20, 1000, 1500, 1e-3), ("mf", False, 33, 129, 300, 1e-3),   # ragged: n % 4 != 0, odd batch
+    ("lv", False, 128, 64, 100, 1e-3), ("dl", False, 1, 3, 50, 1e-3), ("plv", True, 5, 1, 50, 1e-3),
+]
+
+
+@pytest.mark.parametrize("solver,adam,n,b,t,tol", CASES)
+def test_replay_parity_vs_oracle(solver, adam, n, b, t, tol):
+    mult = 0.2 if solver == "dl" else 0.05
+    q, v, sb = instance(n, n + 7, mult)
+    k = 2 if solver == "dl" else 1
+    noise = O.make_replay_noise(3, t, k, n, b)
+    src = O.NoiseSource(n, b, replay=noise)
+    qg, vg, ng = q.cuda(), v.cuda(), noise.cuda()
+    alg = nat.ALG_ADAM if adam else nat.ALG_ORIGINAL
+    if solver == "dl":
+        if adam:
+            c_ref, _ = O.dl_solve_adam(q, v, b, t, 8.0, 0.001, 10.0, src, HP)
+            outs, _ = E.solve(nat.SOLVER_DL, alg, qg, vg, b, t, s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0, g=0.05,
+                              hyperparameters=HP, noise=ng)
+            s_map = np.sqrt(7.0)
+        else:
+            c_ref, _ = O.dl_solve(q, v, b, t, 8.0, 0.001, 10.0, 100.0, src)
+            outs, _ = E.solve(nat.SOLVER_DL, alg, qg, vg, b, t, s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0,
+                              feedback_scale=100.0, g=0.05, noise=ng)
+            s_map = 1.0
+        x_ref, x_gpu = O.change_variables(c_ref, 0, 1, s_map), O.change_variables(outs[0].cpu(), 0, 1, s_map)
+    elif solver == "mf":
+        fn = O.mf_solve_adam if adam else O.mf_solve
+        args = (q, v, b, t, 20.0, 0.0, 0.0025, 5.0, 4000.0, src) + ((HP,) if adam else ())
+        _, mt_ref, _ = fn(*args)
+        outs, _ = E.solve(nat.SOLVER_MF, alg, qg, vg, b, t, s=20.0, pump=0.0, dt=0.0025, j=5.0, feedback_scale=4000.0,
+                          g=0.01, hyperparameters=HP if adam else None, noise=ng)
+        x_ref, x_gpu = O.change_variables(mt_ref, 0, 1, 20.0), O.change_variables(outs[1].cpu(), 0, 1, 20.0)
+    elif solver == "lv":
+        fn = O.langevin_solve_adam if adam else O.langevin_solve
+        args = (q, v, b, t, 0.5, 0.002, 0.5, 1.0, src) + ((HP,) if adam else ())
+        c_ref = fn(*args)
+        outs, _ = E.solve(nat.SOLVER_LANGEVIN, alg, qg, vg, b, t, s=0.5, dt=0.002, sigma=0.5, feedback_scale=1.0,
+                          hyperparameters=HP if adam else None, noise=ng)
+        x_ref, x_gpu = (c_ref + 0.5), (outs[0].cpu() + 0.5)
+    else:
+        fn = O.pumped_langevin_solve_adam if adam else O.pumped_langevin_solve
+        args = (q, v, b, t, 0.5, 2.0, 0.002, 0.5, 1.0, src) + ((HP,) if adam else ())
+        c_ref = fn(*args)
+        outs, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, alg, qg, vg, b, t, s=0.5, pump=2.0, dt=0.002, sigma=0.5,
+                          feedback_scale=1.0, hyperparameters=HP if adam else None, noise=ng)
+        x_ref, x_gpu = (c_ref + 0.5), (outs[0].cpu() + 0.5)
+    assert torch.isfinite(x_gpu).all()
+    err = rel_obj_err(x_gpu, x_ref, q, v, sb)
+    assert err <= tol, f"{solver} adam={adam} n={n}: objective rel err {err:.3e}"
+
+
+def test_nan_for_nan():
+    """README quick-start with feedback_scale=100 diverges to NaN in the reference;
+    the kernel must diverge too rather than mask it."""
+    q, v, _ = instance(20, 1, 0.2)
+    b, t = 16, 600
+    noise = O.make_replay_noise(0, t, 2, 20, b)
+    c_ref, _ = O.dl_solve(q, v, b, t, 2.0, 0.005, 10.0, 100.0, O.NoiseSource(20, b, replay=noise))
+    outs, _ = E.solve(nat.SOLVER_DL, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, s=1.0, pump=2.0, dt=0.005,
+                      noise_ratio=10.0, feedback_scale=100.0, g=0.05, noise=noise.cuda())
+    assert torch.isnan(c_ref).all() and torch.isnan(outs[0]).all()
+
+
+def test_philox_reproducible_and_shard_invariant():
+    q, v, _ = instance(30, 2, 0.05)
+    kw = dict(s=0.5, pump=2.0, dt=0.002, sigma=0.5, feedback_scale=1.0)
+    full, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), 96, 200, seed=11, offset=4, **kw)
+    again, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), 96, 200, seed=11, offset=4, **kw)
+    assert torch.equal(full[0], again[0])
+    other, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), 96, 200, seed=12, offset=4, **kw)
+    assert not torch.equal(full[0], other[0])
+    # a batch split 40 + 56 with global trajectory offsets gives the same trajectories
+    a, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), 40, 200, seed=11, offset=4,
+                   traj_base=0, **kw)
+    bb, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), 56, 200, seed=11, offset=4,
+                    traj_base=40, **kw)
+    assert torch.equal(torch.cat([a[0], bb[0]]), full[0])
+
+
+def test_philox_noise_is_standard_normal():
+    """With Q = V = 0 and a huge S, Langevin's c_T is sigma*sqrt(dt) * sum of T normals."""
+    n, b, t = 64, 2048, 64
+    q, v = torch.zeros(n, n), torch.zeros(n)
+    outs, _ = E.solve(nat.SOLVER_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, s=1e6, dt=1.0 / t, sigma=1.0,
+                      feedback_scale=1.0, seed=5, offset=0)
+    x = outs[0].double().cpu().flatten()
+    m = x.numel()
+    assert abs(x.mean().item()) < 5 / np.sqrt(m)
+    assert abs(x.var().item() - 1.0) < 5 * np.sqrt(2.0 / m)
+    assert abs(((x - x.mean()) ** 4).mean().item() / x.var().item() ** 2 - 3.0) < 0.1
+    # independent across variables and trajectories
+    c = np.corrcoef(outs[0].cpu().numpy()[:, :8].T)
+    assert np.abs(c - np.eye(8)).max() < 5 / np.sqrt(b)
+    one, _ = E.solve(nat.SOLVER_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, 1, s=1e6, dt=1.0, sigma=1.0,
+                     feedback_scale=1.0, seed=5, offset=0)
+    y = one[0].double().cpu().flatten()
+    assert abs(y.mean().item()) < 5 / np.sqrt(m) and abs(y.var().item() - 1) < 5 * np.sqrt(2 / m)
+    assert y.abs().max().item() > 3.5  # tails exist
+
+
+@pytest.mark.parametrize("solver", ["mf", "lv", "plv", "dl"])
+def test_philox_statistical_equivalence(solver):
+    """Production mode vs the oracle drawing from torch's generator: success fractions at every
+    gap threshold of solution.py:130-136 must agree within binomial 95% intervals (with a
+    Bonferroni allowance over the 7 thresholds)."""
+    z = np.load(__import__("os").path.join(__import__("os").path.dirname(__file__), "golden", "call_lv_gd.npz"))
+    q0, v0 = torch.from_numpy(z["q"]), torch.from_numpy(z["v"])   # LV-scaled (0.05) n=20 bundled instance
+    sb0, opt = float(z["scaled_by"]), float(z["optimal"])
+    b, t = 1000, 1500
+    if solver == "dl":      # DL scaling multiplier is 0.2: rescale the coefficients
+        q, v, sb = q0 / 4.0, v0 / 4.0, sb0 * 4.0
+    else:
+        q, v, sb = q0, v0, sb0
+    gen = torch.Generator().manual_seed(0)
+    src = O.NoiseSource(20, b, generator=gen)
+    qg, vg = q.cuda(), v.cuda()
+    if solver == "mf":
+        _, st_ref, _ = O.mf_solve(q, v, b, t, 20.0, 0.0, 0.0025, 5.0, 4000.0, src)
+        outs, _ = E.solve(nat.SOLVER_MF, nat.ALG_ORIGINAL, qg, vg, b, t, s=20.0, pump=0.0, dt=0.0025, j=5.0,
+                          feedback_scale=4000.0, g=0.01, seed=0, offset=0)
+        name, st_gpu, s_val = "mf", outs[1].cpu(), 20.0
+    elif solver == "lv":
+        st_ref = O.langevin_solve(q, v, b, t, 0.5, 0.002, 0.5, 1.0, src)
+        outs, _ = E.solve(nat.SOLVER_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, b, t, s=0.5, dt=0.002, sigma=0.5,
+                          feedback_scale=1.0, seed=0, offset=0)
+        name, st_gpu, s_val = "langevin", outs[0].cpu(), 0.5
+    elif solver == "plv":
+        st_ref = O.pumped_langevin_solve(q, v, b, t, 0.5, 2.0, 0.002, 0.5, 1.0, src)
+        outs, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, b, t, s=0.5, pump=2.0, dt=0.002,
+                          sigma=0.5, feedback_scale=1.0, seed=0, offset=0)
+        name, st_gpu, s_val = "pumped_langevin", outs[0].cpu(), 0.5
+    else:
+        st_ref, _ = O.dl_solve(q, v, b, t, 8.0, 0.001, 10.0, 100.0, src)
+        outs, _ = E.solve(nat.SOLVER_DL, nat.ALG_ORIGINAL, qg, vg, b, t, s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0,
+                          feedback_scale=100.0, g=0.05, seed=0, offset=0)
+        name, st_gpu, s_val = "dl", outs[0].cpu(), 1.0
+    pp = None if solver == "dl" else "grad-descent"
+    _, e_ref = O.epilogue(name, st_ref, q, v, sb, s_val, post_processor=pp)
+    _, e_gpu = O.epilogue(name, st_gpu, q, v, sb, s_val, post_processor=pp)
+    _, p_ref = O.solution_stats(e_ref, opt)
+    _, p_gpu = O.solution_stats(e_gpu, opt)
+    for key in p_ref:
+        pr, pg = p_ref[key], p_gpu[key]
+        pooled = (pr + pg) / 2
+        sigma = np.sqrt(max(pooled * (1 - pooled), 1e-4) * 2 / b)
+        assert abs(pr - pg) <= 2.7 * sigma + 2.0 / b, f"{solver} {key}: ref {pr} vs gpu {pg}"
+    both_opt = p_ref["optimal"] > 0 and p_gpu["optimal"] > 0
+    if both_opt:
+        assert abs((-e_ref).max().item() - (-e_gpu).max().item()) <= 1e-3 * abs(opt)
