@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
   };
 
   // stores the tile's contraction input for the next iteration: X[buf][k = j0+jj][rg][2K]
-  const int xoff = (cgc * RW * RG) & 31 & ~(RW - 1);
+  const int xoff = (cgc * RW * RG) & 31;
   auto stage = [&](int buf, const pf2 (&a)[4], const pf2 (&b)[4]) {
     if (!active) return;
 #pragma unroll
@@ -254,33 +254,47 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) acc[q][jj] = dup(hreg[jj]);
     {
-      const float* xp = X + (size_t)buf * NP * XS + RW * rg;
-      float qn[16], qnx[16];
-      tmem_ld16(tlane, qnx);
-      for (int kc = 0; kc < CG; ++kc) {
-        const float* xrow = xp + ((kc * RW * RG) & 31 & ~(RW - 1));
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) qn[i] = qnx[i];
-        if (kc + 1 < CG) tmem_ld16(tlane + 16 * (kc + 1), qnx);
+      // four k's against one 16-column TMEM chunk; two chunk buffers ping-pong so that the next
+      // tcgen05.ld is in flight while the current chunk is consumed (no register copies)
+      const float* xrow = X + (size_t)buf * NP * XS + RW * rg;
+      int off = 0;
+      auto contract4 = [&](const float (&qq)[16]) {
+        const float* xr = xrow + off;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           pf2 xv[K];
           if constexpr (K == 2) {
-            const float4 x4 = *reinterpret_cast<const float4*>(xrow);
+            const float4 x4 = *reinterpret_cast<const float4*>(xr + kk * XS);
             xv[0] = pk(x4.x, x4.y);
             xv[1] = pk(x4.z, x4.w);
           } else {
-            const float2 x2 = *reinterpret_cast<const float2*>(xrow);
+            const float2 x2 = *reinterpret_cast<const float2*>(xr + kk * XS);
             xv[0] = pk(x2.x, x2.y);
           }
 #pragma unroll
           for (int q = 0; q < K; ++q)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qn[4 * kk + jj]), acc[q][jj]);
-          xrow += XS;
+            for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qq[4 * kk + jj]), acc[q][jj]);
         }
-        xp += 4 * XS;
+        xrow += 4 * XS;
+        off = (off + RW * RG) & 31;
+      };
+      float qa[16], qb[16];
+      uint32_t taddr = tlane;
+      tmem_ld16(taddr, qa);
+      int kc = 0;
+      for (; kc + 2 <= CG; kc += 2) {
+        tmem_wait_ld();
+        tmem_ld16(taddr + 16, qb);
+        contract4(qa);
+        tmem_wait_ld();
+        taddr += 32;
+        if (kc + 2 < CG) tmem_ld16(taddr, qa);
+        contract4(qb);
+      }
+      if (kc < CG) {
+        tmem_wait_ld();
+        contract4(qa);
       }
     }
 
