@@ -328,7 +328,7 @@ def run_gpu_arm(args):
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,
-                         "kernel": "ccvm::sde_kernel<DL, adam, TB=4>", "kernel_ms": solve_avg_ms,
+                         "kernel": "ccvm::sde_tmem_kernel<DL, adam>", "kernel_ms": solve_avg_ms,
                          "peak_source": "measured in-process: register-only FFMA2 probe (ccvm_microbench_fp32); "
                                         "MEASURED_PEAKS.json has no FP32 SIMT figure (HBM/bf16 only)",
                          "algorithmic_flops_per_launch": flops_per_launch},

@@ -187,7 +187,7 @@ static int regs_one() {
 // ---- TMEM path (n <= 128): see sde_kernel_tmem.cuh
 struct TmemPlan {
   TmemLaunch L;
-  int cg, threads, ctas;
+  int cg, threads, ctas, split;
   size_t smem;
 };
 
@@ -222,9 +222,14 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, TmemPlan& P
   if (smem_of(xs) > (size_t)di.max_smem) return fail(CCVM_E_TOO_LARGE, "TMEM path: panel does not fit shared memory");
   int tcols = 32;
   while (tcols < 4 * np) tcols *= 2;
+  // SPLIT (c / s on different threads) doubles the warps but costs 43% more instructions while the
+  // FMA pipe is already the limiter (profiles/): off unless asked for.
+  P.split = d.solver == CCVM_SOLVER_DL && getenv("CCVM_SPLIT") != nullptr;
+  P.L.phase_ns = 0;
+  if (const char* e = getenv("CCVM_PHASE_NS")) P.L.phase_ns = atoi(e);
   P.L.rg = rg;
   P.L.ng = ng;
-  P.L.gt = ng > 1 ? 128 : ((rg * cg + 31) / 32) * 32;
+  P.L.gt = P.split ? 256 : (ng > 1 ? 128 : ((rg * cg + 31) / 32) * 32);
   P.L.xs = xs;
   P.L.tcols = tcols;
   P.cg = cg;
@@ -234,9 +239,9 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, TmemPlan& P
   return CCVM_OK;
 }
 
-template <int SOLVER, bool ADAM>
-static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  auto kern = sde_tmem_kernel<SOLVER, ADAM>;
+template <int SOLVER, bool ADAM, bool SPLIT>
+static int launch_tmem_one(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
+  auto kern = sde_tmem_kernel<SOLVER, ADAM, SPLIT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
   CUDA_TRY(cudaGetLastError());
@@ -244,10 +249,24 @@ static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
 }
 
 template <int SOLVER, bool ADAM>
-static int regs_tmem() {
+static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
+  if constexpr (SOLVER == SOLVER_DL) {
+    if (P.split) return launch_tmem_one<SOLVER, ADAM, true>(p, P, st);
+  }
+  return launch_tmem_one<SOLVER, ADAM, false>(p, P, st);
+}
+
+template <int SOLVER, bool ADAM>
+static int regs_tmem(bool split = false) {
   cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM>) != cudaSuccess) return -1;
-  return fa.numRegs;
+  cudaError_t e;
+  if constexpr (SOLVER == SOLVER_DL) {
+    e = split ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, true>)
+              : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, false>);
+  } else {
+    e = cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, false>);
+  }
+  return e == cudaSuccess ? fa.numRegs : -1;
 }
 
 static int validate_solve(const ccvm_solve_desc* d) {
@@ -308,7 +327,7 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
     info5[3] = (int)P.smem;
     const bool a = d->algorithm == CCVM_ALG_ADAM;
     int r = -1;
-    if (d->solver == SOLVER_DL) r = a ? regs_tmem<SOLVER_DL, true>() : regs_tmem<SOLVER_DL, false>();
+    if (d->solver == SOLVER_DL) r = a ? regs_tmem<SOLVER_DL, true>(P.split) : regs_tmem<SOLVER_DL, false>(P.split);
     if (d->solver == SOLVER_MF) r = a ? regs_tmem<SOLVER_MF, true>() : regs_tmem<SOLVER_MF, false>();
     if (d->solver == SOLVER_LV) r = a ? regs_tmem<SOLVER_LV, true>() : regs_tmem<SOLVER_LV, false>();
     if (d->solver == SOLVER_PLV) r = a ? regs_tmem<SOLVER_PLV, true>() : regs_tmem<SOLVER_PLV, false>();

@@ -30,6 +30,7 @@ struct TmemLaunch {
   int gt;      // threads per group (128 when ng > 1)
   int xs;      // floats per k-row of a group's X panel
   int tcols;   // TMEM columns to allocate (power of two >= 4*NP, >= 32)
+  int phase_ns;  // start delay of odd groups, so that groups alternate contraction / update phases
 };
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
@@ -85,16 +86,24 @@ __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4]
   }
 }
 
-template <int SOLVER, bool ADAM>
-__global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
+// SPLIT (DL only): the c and s quadratures of a tile belong to two different threads (t and
+// t + 128 inside a 256-thread group).  They share the TMEM lane (same columns) and the X rows, so
+// the shared-memory traffic is unchanged while the SM holds twice as many warps to hide the
+// fixed-latency chains of the noise / update phase.
+template <int SOLVER, bool ADAM, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
   constexpr int K = SolverTraits<SOLVER>::K;
+  constexpr int KT = SPLIT ? 1 : K;  // quadratures handled by one thread
   constexpr int RW = 2 * K;  // floats per (k, trajectory pair): (b0,b1) or (c0,c1,s0,s1)
+  static_assert(!SPLIT || SOLVER == SOLVER_DL, "SPLIT is a DL layout");
 
   extern __shared__ __align__(16) float smem[];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x;
   const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = L.xs, T = p.iterations;
-  const int grp = tid / L.gt, l = tid - grp * L.gt;  // group and lane-in-group (== TMEM lane)
+  const int grp = tid / L.gt, lg = tid - grp * L.gt;
+  const int half = SPLIT ? (lg >> 7) : 0;   // SPLIT: 0 = c thread, 1 = s thread
+  const int l = SPLIT ? (lg & 127) : lg;    // lane in group == TMEM lane
   const int warp = tid >> 5;
 
   float* hv = smem;                                   // [NP]
@@ -121,14 +130,14 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
     }
     hv[j] = h;
   }
-  for (int i = l; i < 2 * NP * XS; i += L.gt) X[i] = 0.f;
+  for (int i = lg; i < 2 * NP * XS; i += L.gt) X[i] = 0.f;
 
   const int rg = l % RG, cg = l / RG;
   const bool active = cg < CG;
   const int cgc = active ? cg : 0;
   const int j0 = 4 * cgc;
   const uint32_t tlane = tbase + ((uint32_t)((l >> 5) * 32) << 16);  // this warp's TMEM lane quadrant
-  if (grp == 0) {
+  if (grp == 0 && half == 0) {
     // every lane stores its own copy of the 4 columns it contracts against
     for (int k = 0; k < NP; ++k) {
       float qv[4];
@@ -157,8 +166,8 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
   }
 
   pf2 st[2][4];             // st[0] = c | mu, st[1] = s | sigma  (x: trajectory gb0, y: gb0+1)
-  pf2 am[K][4], avv[K][4];  // Adam moments of the tracked arrays
-  pf2 W[K][4];              // noise of the current iteration
+  pf2 am[KT][4], avv[KT][4];  // Adam moments of the tracked arrays
+  pf2 W[KT][4];               // noise of the current iteration
   pf2 meas[4];              // MF: clamped measurement
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
@@ -166,7 +175,7 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
     st[1][jj] = dup(SOLVER == SOLVER_MF ? 0.5f : 0.f);
     meas[jj] = dup(0.f);
 #pragma unroll
-    for (int q = 0; q < K; ++q) {
+    for (int q = 0; q < KT; ++q) {
       am[q][jj] = dup(0.f);
       avv[q][jj] = dup(0.f);
       W[q][jj] = dup(0.f);
@@ -178,13 +187,14 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
   auto draw = [&](int t) {
     if (p.noise == nullptr) {
 #pragma unroll
-      for (int q = 0; q < K; ++q)
+      for (int q = 0; q < KT; ++q)
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const unsigned long long gb = (unsigned long long)(p.traj_base + gb0 + i);
+          const uint32_t qi = (uint32_t)(q + half);  // which quadrature's stream
           const uint4 r = philox4x32_10(
               make_uint4((uint32_t)gb, (uint32_t)t,
-                         (uint32_t)cgc | ((uint32_t)q << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
+                         (uint32_t)cgc | (qi << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
               key);
           float n0, n1, n2, n3;
           box_muller(r.x, r.y, n0, n1);
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
         }
     } else {
 #pragma unroll
-      for (int q = 0; q < K; ++q)
+      for (int q = 0; q < KT; ++q)
 #pragma unroll
         for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -206,7 +216,8 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
             float w = 0.f;
             const long long b = gb0 + i;
             if (colok[jj] && b < p.batch)
-              w = p.noise[(((size_t)t * K + q) * N + (j0 + jj)) * (size_t)p.noise_batch + (size_t)(p.traj_base + b)];
+              w = p.noise[(((size_t)t * K + (q + half)) * N + (j0 + jj)) * (size_t)p.noise_batch +
+                          (size_t)(p.traj_base + b)];
             if (i) W[q][jj].y = w; else W[q][jj].x = w;
           }
     }
@@ -218,8 +229,8 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
     if (!active) return;
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      float* dst = X + ((size_t)buf * NP + (j0 + jj)) * XS + xoff + RW * rg;
-      if constexpr (K == 2) *reinterpret_cast<float4*>(dst) = make_float4(a[jj].x, a[jj].y, b[jj].x, b[jj].y);
+      float* dst = X + ((size_t)buf * NP + (j0 + jj)) * XS + xoff + RW * rg + 2 * half;
+      if constexpr (K == 2 && !SPLIT) *reinterpret_cast<float4*>(dst) = make_float4(a[jj].x, a[jj].y, b[jj].x, b[jj].y);
       else *reinterpret_cast<float2*>(dst) = make_float2(a[jj].x, a[jj].y);
     }
   };
@@ -239,6 +250,7 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
   group_barrier(bar_id, bar_n);
 
   // ------------------------------------------------------------------ main loop
+  if ((grp & 1) && L.phase_ns > 0) __nanosleep(L.phase_ns);
   for (int t = 0; t < T; ++t) {
     const int buf = t & 1;
     const float4 ca = sa, cb = sb;
@@ -248,22 +260,22 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
     }
 
     // ---- drift contraction: acc = h + X . Qs   (Qs from TMEM, X from shared memory)
-    pf2 acc[K][4];
+    pf2 acc[KT][4];
 #pragma unroll
-    for (int q = 0; q < K; ++q)
+    for (int q = 0; q < KT; ++q)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) acc[q][jj] = dup(hreg[jj]);
     {
       // four k's against one 16-column TMEM chunk; two chunk buffers ping-pong so that the next
       // tcgen05.ld is in flight while the current chunk is consumed (no register copies)
-      const float* xrow = X + (size_t)buf * NP * XS + RW * rg;
+      const float* xrow = X + (size_t)buf * NP * XS + RW * rg + 2 * half;
       int off = 0;
       auto contract4 = [&](const float (&qq)[16]) {
         const float* xr = xrow + off;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          pf2 xv[K];
-          if constexpr (K == 2) {
+          pf2 xv[KT];
+          if constexpr (KT == 2) {
             const float4 x4 = *reinterpret_cast<const float4*>(xr + kk * XS);
             xv[0] = pk(x4.x, x4.y);
             xv[1] = pk(x4.z, x4.w);
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
             xv[0] = pk(x2.x, x2.y);
           }
 #pragma unroll
-          for (int q = 0; q < K; ++q)
+          for (int q = 0; q < KT; ++q)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qq[4 * kk + jj]), acc[q][jj]);
         }
@@ -299,7 +311,25 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
     }
 
     // ---- elementwise SDE step (same arithmetic as sde_kernel.cuh)
-    if constexpr (SOLVER == SOLVER_DL) {
+    if constexpr (SOLVER == SOLVER_DL && SPLIT) {
+      draw(t);
+      if constexpr (ADAM) adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
+      const pf2 gain = dup(ca.x), dlin = dup(half ? ca.z : ca.y), nsc = dup(half ? cb.x : ca.w);
+      const pf2 mdt = dup(-p.dt), hf = dup(0.5f);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        // the other quadrature of the same trajectories, as it was at the start of this iteration
+        const float2 o2 = *reinterpret_cast<const float2*>(X + ((size_t)buf * NP + (j0 + jj)) * XS + xoff + RW * rg +
+                                                            2 * (1 - half));
+        const pf2 own = st[0][jj], oth = pk(o2.x, o2.y);
+        const pf2 r2 = half ? fma2(oth, oth, mul2(own, own)) : fma2(own, own, mul2(oth, oth));  // c*c + s*s
+        const pf2 rt = sqrt2(add2(r2, hf));
+        const pf2 u = fma2(r2, mdt, dlin);
+        const pf2 nz = mul2(mul2(rt, nsc), W[0][jj]);
+        st[0][jj] = add2(own, fma2(own, u, fma2(gain, acc[0][jj], nz)));
+      }
+      stage(buf ^ 1, st[0], st[0]);
+    } else if constexpr (SOLVER == SOLVER_DL) {
       draw(t);
       if constexpr (ADAM) {
         adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
@@ -376,8 +406,8 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
               const long long b = gb0 + i;
-              if (b < p.batch && colok[jj])
-                p.samples[(((size_t)a * p.num_samples + sidx) * p.batch + b) * N + j0 + jj] =
+              if (b < p.batch && colok[jj] && (!SPLIT || a == 0))
+                p.samples[(((size_t)(a + half) * p.num_samples + sidx) * p.batch + b) * N + j0 + jj] =
                     i ? st[a][jj].y : st[a][jj].x;
             }
       }
@@ -397,7 +427,9 @@ __global__ void __launch_bounds__(256, 1) sde_tmem_kernel(const SdeParams p, con
         const size_t o = (size_t)b * N + j0 + jj;
         const float v0 = i ? st[0][jj].y : st[0][jj].x, v1 = i ? st[1][jj].y : st[1][jj].x;
         const float vm = i ? meas[jj].y : meas[jj].x;
-        if constexpr (SOLVER == SOLVER_DL) {
+        if constexpr (SOLVER == SOLVER_DL && SPLIT) {
+          if (half) p.out1[o] = v0; else p.out0[o] = clampf(v0, -sclamp[jj], sclamp[jj]);
+        } else if constexpr (SOLVER == SOLVER_DL) {
           p.out0[o] = clampf(v0, -sclamp[jj], sclamp[jj]);
           p.out1[o] = v1;
         } else if constexpr (SOLVER == SOLVER_MF) {

@@ -1,0 +1,35 @@
+"""Print the handful of ncu raw metrics that matter for the SDE kernel from a .ncu-rep file."""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "sm__cycles_elapsed.avg", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+]
+STALL = "smsp__average_warps_issue_stalled_"
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for vals in rows[2:]:
+        rec = dict(zip(hdr, vals))
+        print("kernel:", rec.get("Kernel Name", "?")[:100])
+        for k in KEYS:
+            if k in rec:
+                print(f"  {k:90s} {rec[k]:>16s} {units[hdr.index(k)]}")
+        stalls = sorted(((float(v), h[len(STALL):-len('_per_issue_active.ratio')]) for h, v in rec.items()
+                         if h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and v), reverse=True)
+        print("  stalls per issued instruction:", ", ".join(f"{n}={v:.2f}" for v, n in stalls[:8]))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
