@@ -184,25 +184,41 @@ static int regs_one() {
 }
 
 
-// ---- TMEM path (n <= 128): see sde_kernel_tmem.cuh
+// ---- tiled paths (sde_kernel_tmem.cuh): Q slice from TMEM (n <= 128) or streamed from L2 (any n)
 struct TmemPlan {
   TmemLaunch L;
-  int cg, threads, ctas, split;
+  int cg, threads, ctas, qsrc;
   size_t smem;
 };
 
-static bool tmem_path_applies(const ccvm_solve_desc& d) {
-  return d.n <= 128 && getenv("CCVM_NO_TMEM") == nullptr;
+enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2 };
+
+static int choose_path(const ccvm_solve_desc& d) {
+  if (getenv("CCVM_LEGACY")) return PATH_LEGACY;  // first-generation shared-memory kernel (n <~ 160)
+  if (d.n <= 128 && getenv("CCVM_NO_TMEM") == nullptr) return PATH_TMEM;
+  return PATH_GMEM;
 }
 
-static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, TmemPlan& P) {
+static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, TmemPlan& P) {
   const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1, RW = 2 * K;
   const int cg = (d.n + 3) / 4, np = 4 * cg;
-  const int rg_max = 128 / cg;
+  const int max_threads = path == PATH_TMEM ? 256 : 512;
+  const int lanes = path == PATH_TMEM ? 128 : max_threads;   // threads one group may span
+  if (cg > lanes) return fail(CCVM_E_TOO_LARGE, "n=%d exceeds the tiled SIMT path (n <= %d)", d.n, 4 * lanes);
+  const int rg_max = lanes / cg;
   const int share = (d.batch + di.sms - 1) / di.sms;
   const int pairs = (share + 1) / 2;
-  int ng = pairs <= rg_max ? 1 : 2;
-  int rg = (pairs + ng - 1) / ng;
+  auto round32 = [](int x) { return ((x + 31) / 32) * 32; };
+  int ng = 1, rg = pairs < rg_max ? pairs : rg_max;
+  if (pairs > rg_max) {
+    // a second, independently synchronised group if the CTA has room for it
+    const int rg2 = (pairs + 1) / 2 < rg_max ? (pairs + 1) / 2 : rg_max;
+    const int gt2 = path == PATH_TMEM ? 128 : round32(rg2 * cg);
+    if (2 * gt2 <= max_threads) {
+      ng = 2;
+      rg = rg2;
+    }
+  }
   if (const char* e = getenv("CCVM_NG")) {
     const int v = atoi(e);
     if (v == 1 || v == 2) ng = v;
@@ -213,25 +229,32 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, TmemPlan& P
   }
   if (rg > rg_max) rg = rg_max;
   if (rg < 1) rg = 1;
-  int xs = ((RW * rg + 32 + 3) / 4) * 4;
+  if (ng == 2 && path != PATH_TMEM && 2 * round32(rg * cg) > max_threads) ng = 1;
+  int xs = 0, xmask = 31;
   auto smem_of = [&](int xs_) { return ((size_t)2 * np + (size_t)ng * 2 * np * xs_) * sizeof(float); };
-  while (smem_of(xs) > (size_t)di.max_smem && rg > 1) {
-    --rg;
+  for (;;) {
+    xmask = 31;
     xs = ((RW * rg + 32 + 3) / 4) * 4;
+    if (smem_of(xs) <= (size_t)di.max_smem) break;
+    xmask = 0;  // drop the bank-spreading slack before giving up trajectories
+    xs = ((RW * rg + 3) / 4) * 4;
+    if (smem_of(xs) <= (size_t)di.max_smem) break;
+    if (ng == 2) { ng = 1; continue; }
+    if (rg == 1) return fail(CCVM_E_TOO_LARGE, "n=%d: the state panel does not fit shared memory", d.n);
+    --rg;
   }
-  if (smem_of(xs) > (size_t)di.max_smem) return fail(CCVM_E_TOO_LARGE, "TMEM path: panel does not fit shared memory");
   int tcols = 32;
   while (tcols < 4 * np) tcols *= 2;
-  // SPLIT (c / s on different threads) doubles the warps but costs 43% more instructions while the
-  // FMA pipe is already the limiter (profiles/): off unless asked for.
-  P.split = d.solver == CCVM_SOLVER_DL && getenv("CCVM_SPLIT") != nullptr;
-  P.L.phase_ns = 0;
-  if (const char* e = getenv("CCVM_PHASE_NS")) P.L.phase_ns = atoi(e);
+  memset(&P.L, 0, sizeof(P.L));
   P.L.rg = rg;
   P.L.ng = ng;
-  P.L.gt = P.split ? 256 : (ng > 1 ? 128 : ((rg * cg + 31) / 32) * 32);
+  P.L.gt = path == PATH_TMEM ? (ng > 1 ? 128 : round32(rg * cg)) : round32(rg * cg);
   P.L.xs = xs;
+  P.L.xmask = xmask;
   P.L.tcols = tcols;
+  P.L.phase_ns = 0;
+  if (const char* e = getenv("CCVM_PHASE_NS")) P.L.phase_ns = atoi(e);
+  P.qsrc = path == PATH_TMEM ? QSRC_TMEM : QSRC_GMEM;
   P.cg = cg;
   P.threads = ng * P.L.gt;
   P.ctas = (d.batch + ng * 2 * rg - 1) / (ng * 2 * rg);
@@ -239,33 +262,40 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, TmemPlan& P
   return CCVM_OK;
 }
 
-template <int SOLVER, bool ADAM, bool SPLIT>
-static int launch_tmem_one(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  auto kern = sde_tmem_kernel<SOLVER, ADAM, SPLIT>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-  kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
+// Qs[k][j] = -alpha_k alpha_j Q_kj, zero padded to NP x NP (QSRC_GMEM operand)
+__global__ void scale_q_kernel(const float* __restrict__ q, const float* __restrict__ svec, float s, float a_half,
+                               int n, int np, float* __restrict__ qs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= np * np) return;
+  const int k = idx / np, j = idx - k * np;
+  float val = 0.f;
+  if (k < n && j < n) {
+    const float ak = a_half / (svec ? svec[k] : s), aj = a_half / (svec ? svec[j] : s);
+    val = -ak * aj * q[k * n + j];
+  }
+  qs[idx] = val;
+}
+
+template <int SOLVER, bool ADAM>
+static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
+  if (P.qsrc == QSRC_TMEM) {
+    auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
+  } else {
+    auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
+  }
   CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
 }
 
 template <int SOLVER, bool ADAM>
-static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  if constexpr (SOLVER == SOLVER_DL) {
-    if (P.split) return launch_tmem_one<SOLVER, ADAM, true>(p, P, st);
-  }
-  return launch_tmem_one<SOLVER, ADAM, false>(p, P, st);
-}
-
-template <int SOLVER, bool ADAM>
-static int regs_tmem(bool split = false) {
+static int regs_tmem(int qsrc) {
   cudaFuncAttributes fa;
-  cudaError_t e;
-  if constexpr (SOLVER == SOLVER_DL) {
-    e = split ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, true>)
-              : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, false>);
-  } else {
-    e = cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, false>);
-  }
+  cudaError_t e = qsrc == QSRC_TMEM ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM>)
+                                    : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM>);
   return e == cudaSuccess ? fa.numRegs : -1;
 }
 
@@ -318,19 +348,20 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
   if (rc) return rc;
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
-  if (tmem_path_applies(*d)) {
+  const int path = choose_path(*d);
+  if (path != PATH_LEGACY) {
     TmemPlan P;
-    if ((rc = plan_tmem(*d, di, P))) return rc;
+    if ((rc = plan_tmem(*d, di, path, P))) return rc;
     info5[0] = P.threads;
     info5[1] = P.ctas;
     info5[2] = P.L.ng * 2 * P.L.rg;
     info5[3] = (int)P.smem;
     const bool a = d->algorithm == CCVM_ALG_ADAM;
     int r = -1;
-    if (d->solver == SOLVER_DL) r = a ? regs_tmem<SOLVER_DL, true>(P.split) : regs_tmem<SOLVER_DL, false>(P.split);
-    if (d->solver == SOLVER_MF) r = a ? regs_tmem<SOLVER_MF, true>() : regs_tmem<SOLVER_MF, false>();
-    if (d->solver == SOLVER_LV) r = a ? regs_tmem<SOLVER_LV, true>() : regs_tmem<SOLVER_LV, false>();
-    if (d->solver == SOLVER_PLV) r = a ? regs_tmem<SOLVER_PLV, true>() : regs_tmem<SOLVER_PLV, false>();
+    if (d->solver == SOLVER_DL) r = a ? regs_tmem<SOLVER_DL, true>(P.qsrc) : regs_tmem<SOLVER_DL, false>(P.qsrc);
+    if (d->solver == SOLVER_MF) r = a ? regs_tmem<SOLVER_MF, true>(P.qsrc) : regs_tmem<SOLVER_MF, false>(P.qsrc);
+    if (d->solver == SOLVER_LV) r = a ? regs_tmem<SOLVER_LV, true>(P.qsrc) : regs_tmem<SOLVER_LV, false>(P.qsrc);
+    if (d->solver == SOLVER_PLV) r = a ? regs_tmem<SOLVER_PLV, true>(P.qsrc) : regs_tmem<SOLVER_PLV, false>(P.qsrc);
     info5[4] = r;
     return CCVM_OK;
   }
@@ -363,12 +394,13 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   if (rc) return rc;
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
-  const bool use_tmem = tmem_path_applies(*d);
+  const int path = choose_path(*d);
+  const bool use_tmem = path != PATH_LEGACY;  // tiled kernel (TMEM or streamed Q)
   LaunchPlan L;
   TmemPlan TP;
   memset(&L, 0, sizeof(L));
   if (use_tmem) {
-    if ((rc = plan_tmem(*d, di, TP))) return rc;
+    if ((rc = plan_tmem(*d, di, path, TP))) return rc;
     L.cg = TP.cg;
   } else if ((rc = plan_launch(*d, di, L))) {
     return rc;
@@ -435,6 +467,14 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   p.off_lo = (uint32_t)d->offset;
   p.off_hi = (uint32_t)(d->offset >> 32);
 
+  float* qs_scratch = nullptr;
+  if (use_tmem && TP.qsrc == QSRC_GMEM) {
+    const int np = 4 * TP.cg;
+    CUDA_TRY(cudaMallocAsync((void**)&qs_scratch, (size_t)np * np * sizeof(float), st));
+    scale_q_kernel<<<(np * np + 255) / 256, 256, 0, st>>>(p.q, p.drift_s_vec, p.drift_s, p.a_half, p.n, np, qs_scratch);
+    CUDA_TRY(cudaGetLastError());
+    TP.L.qs = qs_scratch;
+  }
   if (use_tmem) {
     switch (d->solver * 2 + (adam ? 1 : 0)) {
       case 0: rc = launch_tmem<SOLVER_DL, false>(p, TP, st); break;
@@ -457,6 +497,7 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
     case 6: rc = launch_tb<SOLVER_PLV, false>(p, L, st); break;
     default: rc = launch_tb<SOLVER_PLV, true>(p, L, st); break;
   }
+  if (qs_scratch) cudaFreeAsync(qs_scratch, st);
   cudaError_t fe = cudaFreeAsync(sched, st);
   if (rc) return rc;
   if (fe != cudaSuccess) return fail(CCVM_E_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(fe));

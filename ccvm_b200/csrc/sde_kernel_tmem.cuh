@@ -27,11 +27,20 @@ namespace ccvm {
 struct TmemLaunch {
   int rg;      // trajectory pairs per group
   int ng;      // groups per CTA
-  int gt;      // threads per group (128 when ng > 1)
+  int gt;      // threads per group (TMEM source: 128 when ng > 1)
   int xs;      // floats per k-row of a group's X panel
-  int tcols;   // TMEM columns to allocate (power of two >= 4*NP, >= 32)
-  int phase_ns;  // start delay of odd groups, so that groups alternate contraction / update phases
+  int tcols;   // TMEM columns to allocate (power of two >= 4*NP, >= 32); unused for QSRC_GMEM
+  int phase_ns;  // start delay of odd groups (experiment knob; 0 in production)
+  int xmask;        // 31: per-column-group bank offsets inside an X row (needs 32 floats of slack); 0: none
+  const float* qs;  // QSRC_GMEM: the scaled matrix Qs[NP][NP] (zero padded) in global memory
 };
+
+// Where the thread's Q slice comes from.
+//   QSRC_TMEM (n <= 128): the thread's own TMEM lane (tcgen05.ld), see the header comment.
+//   QSRC_GMEM (any n):    streamed from global memory / L2 with read-only 128-bit loads; the matrix
+//                         is too large for on-chip replication, so it stays L2-resident (4 MB at
+//                         n = 1024) and every CTA re-reads it once per iteration.
+enum : int { QSRC_TMEM = 0, QSRC_GMEM = 1 };
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
@@ -86,16 +95,16 @@ __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4]
   }
 }
 
-// SPLIT (DL only): the c and s quadratures of a tile belong to two different threads (t and
-// t + 128 inside a 256-thread group).  They share the TMEM lane (same columns) and the X rows, so
-// the shared-memory traffic is unchanged while the SM holds twice as many warps to hide the
-// fixed-latency chains of the noise / update phase.
-template <int SOLVER, bool ADAM, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
+// (A variant that gave the c and s quadratures of a DL tile to different threads -- 16 warps per SM
+// instead of 8 -- was measured and dropped: 43 % more instructions for a loop that is already
+// FMA-pipe-bound, profiles/r1_ncu_sde_dl_tmem_v3.txt.)
+template <int SOLVER, bool ADAM, int QSRC>
+__global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
+    sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
   constexpr int K = SolverTraits<SOLVER>::K;
-  constexpr int KT = SPLIT ? 1 : K;  // quadratures handled by one thread
+  constexpr int KT = K;      // quadratures handled by one thread
+  constexpr bool SPLIT = false;
   constexpr int RW = 2 * K;  // floats per (k, trajectory pair): (b0,b1) or (c0,c1,s0,s1)
-  static_assert(!SPLIT || SOLVER == SOLVER_DL, "SPLIT is a DL layout");
 
   extern __shared__ __align__(16) float smem[];
   __shared__ uint32_t tmem_slot;
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const Sd
   float* X = av + NP + (size_t)grp * 2 * NP * XS;     // this group's [2][NP][XS] panel
 
   // ------------------------------------------------------------------ prologue
-  if (warp == 0) tmem_alloc(&tmem_slot, L.tcols);
+  if (QSRC == QSRC_TMEM && warp == 0) tmem_alloc(&tmem_slot, L.tcols);
   for (int j = tid; j < NP; j += blockDim.x) {
     float a = 0.f;
     if (j < N) a = p.a_half / (p.drift_s_vec ? p.drift_s_vec[j] : p.drift_s);
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const Sd
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = tmem_slot;
+  const uint32_t tbase = QSRC == QSRC_TMEM ? tmem_slot : 0u;
   for (int j = tid; j < NP; j += blockDim.x) {
     float h = 0.f;
     if (j < N) {
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const Sd
   const int cgc = active ? cg : 0;
   const int j0 = 4 * cgc;
   const uint32_t tlane = tbase + ((uint32_t)((l >> 5) * 32) << 16);  // this warp's TMEM lane quadrant
-  if (grp == 0 && half == 0) {
+  if (QSRC == QSRC_TMEM && grp == 0 && half == 0) {
     // every lane stores its own copy of the 4 columns it contracts against
     for (int k = 0; k < NP; ++k) {
       float qv[4];
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const Sd
   };
 
   // stores the tile's contraction input for the next iteration: X[buf][k = j0+jj][rg][2K]
-  const int xoff = (cgc * RW * RG) & 31;
+  const int xoff = (cgc * RW * RG) & L.xmask;
   auto stage = [&](int buf, const pf2 (&a)[4], const pf2 (&b)[4]) {
     if (!active) return;
 #pragma unroll
@@ -289,47 +298,43 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const Sd
             for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qq[4 * kk + jj]), acc[q][jj]);
         }
         xrow += 4 * XS;
-        off = (off + RW * RG) & 31;
+        off = (off + RW * RG) & L.xmask;
       };
       float qa[16], qb[16];
-      uint32_t taddr = tlane;
-      tmem_ld16(taddr, qa);
+      // chunk c = rows 4c..4c+3 of the thread's 4 columns
+      const float* qg = QSRC == QSRC_GMEM ? L.qs + j0 : nullptr;
+      auto load_chunk = [&](int c, float (&dst)[16]) {
+        if constexpr (QSRC == QSRC_TMEM) {
+          tmem_ld16(tlane + 16 * c, dst);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(qg + (size_t)(4 * c + kk) * NP));
+            dst[4 * kk] = v.x; dst[4 * kk + 1] = v.y; dst[4 * kk + 2] = v.z; dst[4 * kk + 3] = v.w;
+          }
+        }
+      };
+      auto wait_chunk = [&]() {
+        if constexpr (QSRC == QSRC_TMEM) tmem_wait_ld();
+      };
+      load_chunk(0, qa);
       int kc = 0;
       for (; kc + 2 <= CG; kc += 2) {
-        tmem_wait_ld();
-        tmem_ld16(taddr + 16, qb);
+        wait_chunk();
+        load_chunk(kc + 1, qb);
         contract4(qa);
-        tmem_wait_ld();
-        taddr += 32;
-        if (kc + 2 < CG) tmem_ld16(taddr, qa);
+        wait_chunk();
+        if (kc + 2 < CG) load_chunk(kc + 2, qa);
         contract4(qb);
       }
       if (kc < CG) {
-        tmem_wait_ld();
+        wait_chunk();
         contract4(qa);
       }
     }
 
     // ---- elementwise SDE step (same arithmetic as sde_kernel.cuh)
-    if constexpr (SOLVER == SOLVER_DL && SPLIT) {
-      draw(t);
-      if constexpr (ADAM) adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
-      const pf2 gain = dup(ca.x), dlin = dup(half ? ca.z : ca.y), nsc = dup(half ? cb.x : ca.w);
-      const pf2 mdt = dup(-p.dt), hf = dup(0.5f);
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        // the other quadrature of the same trajectories, as it was at the start of this iteration
-        const float2 o2 = *reinterpret_cast<const float2*>(X + ((size_t)buf * NP + (j0 + jj)) * XS + xoff + RW * rg +
-                                                            2 * (1 - half));
-        const pf2 own = st[0][jj], oth = pk(o2.x, o2.y);
-        const pf2 r2 = half ? fma2(oth, oth, mul2(own, own)) : fma2(own, own, mul2(oth, oth));  // c*c + s*s
-        const pf2 rt = sqrt2(add2(r2, hf));
-        const pf2 u = fma2(r2, mdt, dlin);
-        const pf2 nz = mul2(mul2(rt, nsc), W[0][jj]);
-        st[0][jj] = add2(own, fma2(own, u, fma2(gain, acc[0][jj], nz)));
-      }
-      stage(buf ^ 1, st[0], st[0]);
-    } else if constexpr (SOLVER == SOLVER_DL) {
+    if constexpr (SOLVER == SOLVER_DL) {
       draw(t);
       if constexpr (ADAM) {
         adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
@@ -427,9 +432,7 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const Sd
         const size_t o = (size_t)b * N + j0 + jj;
         const float v0 = i ? st[0][jj].y : st[0][jj].x, v1 = i ? st[1][jj].y : st[1][jj].x;
         const float vm = i ? meas[jj].y : meas[jj].x;
-        if constexpr (SOLVER == SOLVER_DL && SPLIT) {
-          if (half) p.out1[o] = v0; else p.out0[o] = clampf(v0, -sclamp[jj], sclamp[jj]);
-        } else if constexpr (SOLVER == SOLVER_DL) {
+        if constexpr (SOLVER == SOLVER_DL) {
           p.out0[o] = clampf(v0, -sclamp[jj], sclamp[jj]);
           p.out1[o] = v1;
         } else if constexpr (SOLVER == SOLVER_MF) {
@@ -442,9 +445,11 @@ __global__ void __launch_bounds__(SPLIT ? 512 : 256, 1) sde_tmem_kernel(const Sd
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_free(tbase, L.tcols);
+  if constexpr (QSRC == QSRC_TMEM) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tbase, L.tcols);
+  }
 }
 
 }  // namespace ccvm

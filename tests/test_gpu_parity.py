@@ -36,6 +36,9 @@ CASES = [
     ("plv", False, 70, 300, 400, 1e-3), ("plv", True, 70, 300, 400, 1e-3),
     ("dl", False, 20, 1000, 1500, 1e-3), ("mf", False, 33, 129, 300, 1e-3),   # ragged: n % 4 != 0, odd batch
     ("lv", False, 128, 64, 100, 1e-3), ("dl", False, 1, 3, 50, 1e-3), ("plv", True, 5, 1, 50, 1e-3),
+    # n > 128: the Q slice no longer fits a TMEM lane -> streamed from L2 (QSRC_GMEM)
+    ("dl", False, 200, 40, 120, 1e-3), ("dl", True, 131, 33, 100, 2e-3), ("mf", True, 250, 64, 150, 1e-3),
+    ("lv", False, 300, 16, 80, 1e-3), ("plv", False, 513, 6, 40, 1e-3),
 ]
 
 
@@ -184,3 +187,19 @@ def test_philox_statistical_equivalence(solver):
     both_opt = p_ref["optimal"] > 0 and p_gpu["optimal"] > 0
     if both_opt:
         assert abs((-e_ref).max().item() - (-e_gpu).max().item()) <= 1e-3 * abs(opt)
+
+
+@pytest.mark.parametrize("env", ["CCVM_NO_TMEM", "CCVM_LEGACY"])
+@pytest.mark.parametrize("solver,adam", [("dl", True), ("mf", False), ("plv", True)])
+def test_alternate_kernel_paths(monkeypatch, env, solver, adam):
+    """The streamed-Q kernel and the first-generation shared-memory kernel stay parity-green at a
+    size the TMEM kernel normally takes (selected through the library's environment switches)."""
+    monkeypatch.setenv(env, "1")
+    test_replay_parity_vs_oracle(solver, adam, 70, 100, 200, 2e-3 if (solver == "dl" and adam) else 1e-3)
+
+
+def test_large_n_limits():
+    q, v, _ = instance(24, 1, 0.05)
+    with pytest.raises(nat.NativeError, match="exceeds the tiled SIMT path"):
+        E.solve(nat.SOLVER_LANGEVIN, nat.ALG_ORIGINAL, torch.zeros(2052, 2052).cuda(), torch.zeros(2052).cuda(), 4, 2,
+                s=0.5, dt=0.002, sigma=0.5, feedback_scale=1.0, seed=1, offset=0)
