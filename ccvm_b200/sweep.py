@@ -1,0 +1,58 @@
+"""Instance sweeps: many BoxQP instances through one solver, optionally sharded over the ranks of a
+``torch.distributed`` job (one process per GPU).  Instances are independent, so the shards need no
+data-path collective; the per-instance metadata records are gathered once at the end.
+
+Reference counterpart: the user loop of ``examples/ccvm_boxqp_*.py`` + ``metadata.py`` (a Python
+``for`` over instance files); the multi-GPU part has none."""
+import torch
+import torch.distributed as dist
+
+from . import parallel
+
+
+def synthetic_instance(n, seed, scaling_multiplier, device="cuda", name=None):
+    """Synthetic dense BoxQP fitted to the bundled instances: symmetric Gaussian Q with
+    off-diagonal std 28.5/sqrt(N), V std 20, reference sign convention, scaled like
+    ``instance.scale_coefs(solver.get_scaling_factor(Q))``.  No Gurobi optimum exists, so
+    ``optimal_sol`` is left at 0 and must be filled from the best value found."""
+    from .problem_classes.boxqp import ProblemInstance
+    from . import engine
+    g = torch.Generator().manual_seed(1000 + seed)
+    a = torch.randn(n, n, generator=g)
+    q = -((a + a.T) / 2 ** 0.5 * (28.5 / n ** 0.5)).float()
+    v = -(20.0 * torch.randn(n, generator=g)).float()
+    inst = ProblemInstance(device=device, instance_type="test", name=name or f"synthetic{n:03d}-{seed}")
+    inst.problem_size = n
+    inst.q_matrix, inst.v_vector = q.to(device), v.to(device)
+    inst.optimal_sol = inst.best_sol = 0.0
+    inst.num_frac_values, inst.solution_vector, inst.optimality = 0, [], False
+    inst.scale_coefs(engine.scaling_factor(inst.q_matrix, scaling_multiplier))
+    return inst
+
+
+def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=None, gather=True, **call_kwargs):
+    """Solve ``instances`` (a sequence, or a callable index -> instance so that ranks only build
+    their own) with ``solver``; returns the list of metadata dicts of ALL instances in order (on
+    every rank when ``gather``), each extended with ``best_index`` and ``rank``."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    if world_size is None:
+        world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    count = instances[0] if isinstance(instances, tuple) else len(instances)
+    getter = instances[1] if isinstance(instances, tuple) else instances.__getitem__
+    local = {}
+    for k in range(count):
+        if parallel.instance_owner(k, world_size) != rank:
+            continue
+        sol = solver(instance=getter(k), post_processor=post_processor, **call_kwargs)
+        rec = sol.get_metadata_dict()
+        rec["best_index"], rec["rank"], rec["index"] = sol.best_index, rank, k
+        local[k] = rec
+    if world_size == 1 or not gather:
+        return [local[k] for k in sorted(local)]
+    shards = [None] * world_size
+    dist.all_gather_object(shards, local)
+    merged = {}
+    for sh in shards:
+        merged.update(sh)
+    return [merged[k] for k in sorted(merged)]

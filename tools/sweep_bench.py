@@ -1,0 +1,94 @@
+"""Instance-sweep benchmark (BASELINE.json configs[1] / configs[4] style): synthetic BoxQP instances of
+several sizes through MF / Langevin / PumpedLangevin (+grad-descent) and DL, batch 1000, 1500
+iterations, sharded round-robin over the ranks of a torchrun job.  Prints one JSON line per solver
+with wall time, aggregate trajectory-steps/s and the TTS(50 %) per size, where "optimal" is the best
+objective found by any run on that instance (no Gurobi optimum exists for synthetic instances)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ccvm_b200 import sweep, tts  # noqa: E402
+from ccvm_b200.solvers import DLSolver, MFSolver, LangevinSolver, PumpedLangevinSolver  # noqa: E402
+
+KEYS = {
+    "mf": (MFSolver, dict(pump=0.0, feedback_scale=4000, j=5.0, S=20.0, dt=0.0025), "grad-descent"),
+    "langevin": (LangevinSolver, dict(dt=0.002, S=0.5, sigma=0.5, feedback_scale=1.0), "grad-descent"),
+    "pumped_langevin": (PumpedLangevinSolver, dict(pump=2.0, dt=0.002, S=0.5, sigma=0.5, feedback_scale=1.0), "grad-descent"),
+    "dl": (DLSolver, dict(pump=8.0, dt=0.001, noise_ratio=10, feedback_scale=100), None),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="20,30,40,50,60,70")
+    ap.add_argument("--per-size", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=1000)
+    ap.add_argument("--iters", type=int, default=1500)
+    ap.add_argument("--solvers", default="mf,langevin,pumped_langevin,dl")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+    sizes = [int(x) for x in args.sizes.split(",")]
+    specs = [(n, k) for n in sizes for k in range(args.per_size)]
+    all_md = {}
+    for name in args.solvers.split(","):
+        cls, key, pp = KEYS[name]
+        solver = cls(device="cuda", batch_size=args.batch)
+        solver.parameter_key = {n: dict(key, iterations=args.iters) for n in sizes}
+        cache = {}
+
+        def get(i, solver=solver, cache=cache):
+            if i not in cache:
+                n, k = specs[i]
+                cache[i] = sweep.synthetic_instance(n, k, solver._scaling_multiplier)
+            return cache[i]
+
+        for i in range(len(specs)):      # build this rank's instances outside the timed region
+            if i % world == rank:
+                get(i)
+        sweep.solve_sweep(solver, (min(len(specs), 2 * world), get), post_processor=pp)  # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        md = sweep.solve_sweep(solver, (len(specs), get), post_processor=pp)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        all_md[name] = md
+        if rank == 0:
+            steps = len(specs) * args.batch * args.iters
+            print(json.dumps({"solver": name, "post_processor": pp, "instances": len(specs), "sizes": sizes,
+                              "batch": args.batch, "iterations": args.iters, "n_gpus": world, "wall_s": wall,
+                              "ms_per_instance": wall / len(specs) * 1e3, "traj_steps_per_s": steps / wall,
+                              "sum_kernel_solve_time_s": sum(r["solve_time"] * r["batch_size"] for r in md)}), flush=True)
+    if rank == 0:
+        # success against the best value any solver found on each instance
+        best = {}
+        for md in all_md.values():
+            for r in md:
+                best[r["index"]] = max(best.get(r["index"], -1e30), r["best_objective_value"])
+        for name, md in all_md.items():
+            probs = {}
+            for r in md:
+                # a run "succeeds" when its batch contains a trajectory within 0.1 % of the best known value;
+                # the per-trajectory fraction needs the objective tensor, so this table uses best-of-batch hits
+                hit = (best[r["index"]] - r["best_objective_value"]) <= 1e-3 * abs(best[r["index"]])
+                probs.setdefault(r["problem_size"], []).append(1.0 if hit else 0.0)
+            print(json.dumps({"solver": name, "best_of_batch_hit_rate": {n: sum(v) / len(v) for n, v in probs.items()},
+                              "r99_at_p": {p: tts.calc_r99(p) for p in (0.1, 0.5, 0.9)}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
