@@ -23,6 +23,7 @@ EXPORTS = (
     "ccvm_postprocess_adam", "ccvm_solution_stats", "ccvm_scaling_factor", "ccvm_solve_host",
     "ccvm_microbench_fp32", "ccvm_query_launch", "ccvm_abi_version", "ccvm_last_error",
     "ccvm_eval_hook", "ccvm_change_variables", "ccvm_fit_to_constraints", "ccvm_scale_coefs",
+    "ccvm_solve_batch", "ccvm_solution_stats_batch",
 )
 
 _fp = C.c_void_p  # device / host pointers travel as plain addresses
@@ -90,6 +91,8 @@ def load():
     lib.ccvm_last_error.restype = C.c_char_p
     lib.ccvm_abi_version.restype = C.c_int
     lib.ccvm_solve.argtypes = [C.POINTER(SolveDesc), _fp]
+    lib.ccvm_solve_batch.argtypes = [C.POINTER(SolveDesc), C.c_int32, _fp]
+    lib.ccvm_solution_stats_batch.argtypes = [_fp, _fp, _fp, C.c_int32, _fp, _fp]
     lib.ccvm_epilogue.argtypes = [C.POINTER(EpilogueDesc), _fp]
     lib.ccvm_compute_energy.argtypes = [_fp, _fp, _fp, C.c_double, C.c_int32, C.c_int32, _fp, _fp]
     lib.ccvm_postprocess_grad_descent.argtypes = [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32,

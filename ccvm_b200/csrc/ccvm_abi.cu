@@ -8,6 +8,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/ccvm_b200.h"
 #include "sde_kernel.cuh"
 #include "sde_kernel_tmem.cuh"
@@ -74,8 +76,7 @@ struct SchedArgs {
   double pump, dt, noise_ratio, j, fs, g, beta1, beta2;
 };
 
-__global__ void build_schedule_kernel(SchedArgs a, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void schedule_row(const SchedArgs& a, int i, float* __restrict__ out) {
   if (i >= a.iterations) return;
   const double t = (double)(i + 1), T = (double)a.iterations;
   const double rate = a.flag ? t / T : 1.0;
@@ -106,6 +107,10 @@ __global__ void build_schedule_kernel(SchedArgs a, float* __restrict__ out) {
   float4* o = reinterpret_cast<float4*>(out + (size_t)i * SCHED_W);
   o[0] = make_float4(r[0], r[1], r[2], r[3]);
   o[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+
+__global__ void build_schedule_kernel(SchedArgs a, float* __restrict__ out) {
+  schedule_row(a, blockIdx.x * blockDim.x + threadIdx.x, out);
 }
 
 // ------------------------------------------------------------------------ launch plan
@@ -199,14 +204,16 @@ static int choose_path(const ccvm_solve_desc& d) {
   return PATH_GMEM;
 }
 
-static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, TmemPlan& P) {
+// `share_hint` > 0 overrides the trajectories-per-SM estimate (batched launches plan every
+// instance against the load of the whole batch, not its own).
+static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, TmemPlan& P, int share_hint = 0) {
   const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1, RW = 2 * K;
   const int cg = (d.n + 3) / 4, np = 4 * cg;
   const int max_threads = path == PATH_TMEM ? 256 : 512;
   const int lanes = path == PATH_TMEM ? 128 : max_threads;   // threads one group may span
   if (cg > lanes) return fail(CCVM_E_TOO_LARGE, "n=%d exceeds the tiled SIMT path (n <= %d)", d.n, 4 * lanes);
   const int rg_max = lanes / cg;
-  const int share = (d.batch + di.sms - 1) / di.sms;
+  const int share = share_hint > 0 ? share_hint : (d.batch + di.sms - 1) / di.sms;
   const int pairs = (share + 1) / 2;
   auto round32 = [](int x) { return ((x + 31) / 32) * 32; };
   int ng = 1, rg = pairs < rg_max ? pairs : rg_max;
@@ -343,6 +350,62 @@ static void resolve_saturation(const ccvm_solve_desc& d, SdeParams& p) {
   }
 }
 
+static void fill_params(const ccvm_solve_desc* d, const float* sched, int cg, SdeParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.q = d->q;
+  p.v = d->v;
+  resolve_saturation(*d, p);
+  p.sched = sched;
+  p.noise = d->rng_mode == CCVM_RNG_REPLAY ? d->noise : nullptr;
+  p.noise_batch = d->noise_batch;
+  p.traj_base = d->traj_base;
+  p.out0 = d->out0;
+  p.out1 = d->out1;
+  p.out2 = d->out2;
+  p.samples = d->evolution_step > 0 ? d->samples : nullptr;
+  p.evolution_step = d->evolution_step > 0 ? d->evolution_step : 0;
+  p.num_samples = d->num_samples;
+  p.n = d->n;
+  p.batch = d->batch;
+  p.iterations = d->iterations;
+  p.cg = cg;
+  p.a_half = (float)((d->upper - d->lower) * 0.5);
+  p.b_half = (float)((d->upper + d->lower) * 0.5);
+  p.dt = (float)d->dt;
+  p.fs = (float)d->feedback_scale;
+  p.g2 = (float)(d->g * d->g);
+  p.sig = (float)(d->sigma * sqrt(d->dt));
+  p.dtfs = (float)(d->dt * d->feedback_scale);
+  p.beta1 = (float)d->beta1;
+  p.beta2 = (float)d->beta2;
+  p.omb1 = (float)(1.0 - d->beta1);
+  p.omb2 = (float)(1.0 - d->beta2);
+  p.adam_alpha = (float)d->alpha;
+  p.add_assign = d->add_assign != 0;
+  p.beta2_is_one = d->beta2 == 1.0;
+  p.seed_lo = (uint32_t)d->seed;
+  p.seed_hi = (uint32_t)(d->seed >> 32);
+  p.off_lo = (uint32_t)d->offset;
+  p.off_hi = (uint32_t)(d->offset >> 32);
+}
+
+static SchedArgs sched_args(const ccvm_solve_desc* d) {
+  SchedArgs sa;
+  sa.solver = d->solver;
+  sa.adam = d->algorithm == CCVM_ALG_ADAM;
+  sa.iterations = d->iterations;
+  sa.flag = d->solver == CCVM_SOLVER_LANGEVIN ? 0 : (d->pump_rate_flag != 0);
+  sa.pump = d->pump;
+  sa.dt = d->dt;
+  sa.noise_ratio = d->noise_ratio;
+  sa.j = d->j;
+  sa.fs = d->feedback_scale;
+  sa.g = d->g;
+  sa.beta1 = d->beta1;
+  sa.beta2 = d->beta2;
+  return sa;
+}
+
 extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
   int rc = validate_solve(d);
   if (rc) return rc;
@@ -410,62 +473,15 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
 
   float* sched = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&sched, (size_t)d->iterations * SCHED_W * sizeof(float), st));
-  SchedArgs sa;
-  sa.solver = d->solver;
-  sa.adam = adam;
-  sa.iterations = d->iterations;
-  sa.flag = d->solver == CCVM_SOLVER_LANGEVIN ? 0 : (d->pump_rate_flag != 0);
-  sa.pump = d->pump;
-  sa.dt = d->dt;
-  sa.noise_ratio = d->noise_ratio;
-  sa.j = d->j;
-  sa.fs = d->feedback_scale;
-  sa.g = d->g;
-  sa.beta1 = d->beta1;
-  sa.beta2 = d->beta2;
+  const SchedArgs sa = sched_args(d);
   build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(sa, sched);
   CUDA_TRY(cudaGetLastError());
 
   SdeParams p;
-  memset(&p, 0, sizeof(p));
-  p.q = d->q;
-  p.v = d->v;
-  resolve_saturation(*d, p);
-  p.sched = sched;
-  p.noise = d->rng_mode == CCVM_RNG_REPLAY ? d->noise : nullptr;
-  p.noise_batch = d->noise_batch;
-  p.traj_base = d->traj_base;
-  p.out0 = d->out0;
-  p.out1 = d->out1;
-  p.out2 = d->out2;
-  p.samples = d->evolution_step > 0 ? d->samples : nullptr;
-  p.evolution_step = d->evolution_step > 0 ? d->evolution_step : 0;
-  p.num_samples = d->num_samples;
-  p.n = d->n;
-  p.batch = d->batch;
-  p.iterations = d->iterations;
+  fill_params(d, sched, L.cg, p);
   p.rg = L.rg;
-  p.cg = L.cg;
   p.xs = L.xs;
   p.use_tma = L.use_tma;
-  p.a_half = (float)((d->upper - d->lower) * 0.5);
-  p.b_half = (float)((d->upper + d->lower) * 0.5);
-  p.dt = (float)d->dt;
-  p.fs = (float)d->feedback_scale;
-  p.g2 = (float)(d->g * d->g);
-  p.sig = (float)(d->sigma * sqrt(d->dt));
-  p.dtfs = (float)(d->dt * d->feedback_scale);
-  p.beta1 = (float)d->beta1;
-  p.beta2 = (float)d->beta2;
-  p.omb1 = (float)(1.0 - d->beta1);
-  p.omb2 = (float)(1.0 - d->beta2);
-  p.adam_alpha = (float)d->alpha;
-  p.add_assign = d->add_assign != 0;
-  p.beta2_is_one = d->beta2 == 1.0;
-  p.seed_lo = (uint32_t)d->seed;
-  p.seed_hi = (uint32_t)(d->seed >> 32);
-  p.off_lo = (uint32_t)d->offset;
-  p.off_hi = (uint32_t)(d->offset >> 32);
 
   float* qs_scratch = nullptr;
   if (use_tmem && TP.qsrc == QSRC_GMEM) {
@@ -502,6 +518,119 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   if (rc) return rc;
   if (fe != cudaSuccess) return fail(CCVM_E_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(fe));
   return CCVM_OK;
+}
+
+
+// ------------------------------------------------------------------ batched instances
+struct SchedJob {
+  SchedArgs a;
+  long long offset;  // first row of this problem in the shared schedule table
+};
+
+__global__ void build_schedule_batch_kernel(const SchedJob* __restrict__ jobs, float* __restrict__ out);
+
+extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, void* stream) {
+  if (!descs || count < 1) return fail(CCVM_E_INVALID, "ccvm_solve_batch needs at least one descriptor");
+  DeviceInfo di;
+  int rc = device_info(di);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int solver = descs[0].solver, alg = descs[0].algorithm;
+  std::vector<int> batched, single;
+  for (int i = 0; i < count; ++i) {
+    if ((rc = validate_solve(&descs[i]))) return rc;
+    if (descs[i].solver != solver || descs[i].algorithm != alg)
+      return fail(CCVM_E_INVALID, "all descriptors of a batch must share solver and algorithm");
+    if (descs[i].rng_mode != CCVM_RNG_PHILOX || descs[i].evolution_step > 0)
+      return fail(CCVM_E_INVALID, "batched solves use Philox noise and no evolution sampling");
+    (choose_path(descs[i]) == PATH_TMEM ? batched : single).push_back(i);
+  }
+  for (int i : single)
+    if ((rc = ccvm_solve(&descs[i], stream))) return rc;
+  if (batched.empty()) return CCVM_OK;
+
+  // plans, schedule table offsets
+  std::vector<TmemPlan> plans(batched.size());
+  std::vector<SchedJob> jobs(batched.size());
+  long long rows = 0, total_traj = 0;
+  int max_t = 0;
+  for (int i : batched) total_traj += descs[i].batch;
+  const int share = (int)((total_traj + di.sms - 1) / di.sms);
+  for (size_t b = 0; b < batched.size(); ++b) {
+    const ccvm_solve_desc& d = descs[batched[b]];
+    if ((rc = plan_tmem(d, di, PATH_TMEM, plans[b], share))) return rc;
+    jobs[b].a = sched_args(&d);
+    jobs[b].offset = rows;
+    rows += d.iterations;
+    if (d.iterations > max_t) max_t = d.iterations;
+  }
+  float* sched = nullptr;
+  SchedJob* d_jobs = nullptr;
+  BatchItem* d_items = nullptr;
+  int2* d_map = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&sched, (size_t)rows * SCHED_W * sizeof(float), st));
+  CUDA_TRY(cudaMallocAsync((void**)&d_jobs, jobs.size() * sizeof(SchedJob), st));
+  CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(SchedJob), cudaMemcpyHostToDevice, st));
+  build_schedule_batch_kernel<<<dim3((max_t + 127) / 128, (unsigned)jobs.size()), 128, 0, st>>>(d_jobs, sched);
+  CUDA_TRY(cudaGetLastError());
+
+  // items + CTA maps, bucketed by block size so small instances do not pay for big blocks
+  std::vector<BatchItem> items(batched.size());
+  const int bucket_threads[4] = {32, 64, 128, 256};
+  std::vector<int2> maps[4];
+  size_t bucket_smem[4] = {0, 0, 0, 0};
+  for (size_t b = 0; b < batched.size(); ++b) {
+    const ccvm_solve_desc& d = descs[batched[b]];
+    fill_params(&d, sched + jobs[b].offset * SCHED_W, plans[b].cg, items[b].p);
+    items[b].L = plans[b].L;
+    int k = 0;
+    while (bucket_threads[k] < plans[b].threads) ++k;
+    for (int c = 0; c < plans[b].ctas; ++c) maps[k].push_back(make_int2((int)b, c));
+    if (plans[b].smem > bucket_smem[k]) bucket_smem[k] = plans[b].smem;
+  }
+  size_t total_ctas = 0;
+  for (int k = 0; k < 4; ++k) total_ctas += maps[k].size();
+  CUDA_TRY(cudaMallocAsync((void**)&d_items, items.size() * sizeof(BatchItem), st));
+  CUDA_TRY(cudaMallocAsync((void**)&d_map, total_ctas * sizeof(int2), st));
+  CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(BatchItem), cudaMemcpyHostToDevice, st));
+  size_t off = 0;
+  const bool adam = alg == CCVM_ALG_ADAM;
+  for (int k = 0; k < 4 && !rc; ++k) {
+    if (maps[k].empty()) continue;
+    const size_t n = maps[k].size();
+    CUDA_TRY(cudaMemcpyAsync(d_map + off, maps[k].data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
+#define BATCH_LAUNCH(S, A)                                                                                 \
+  {                                                                                                        \
+    auto kern = sde_tmem_batch_kernel<S, A>;                                                               \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem[k]); \
+    if (e != cudaSuccess) rc = fail(CCVM_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));      \
+    else kern<<<(unsigned)n, bucket_threads[k], bucket_smem[k], st>>>(d_items, d_map + off);               \
+  }
+    switch (solver * 2 + (adam ? 1 : 0)) {
+      case 0: BATCH_LAUNCH(SOLVER_DL, false) break;
+      case 1: BATCH_LAUNCH(SOLVER_DL, true) break;
+      case 2: BATCH_LAUNCH(SOLVER_MF, false) break;
+      case 3: BATCH_LAUNCH(SOLVER_MF, true) break;
+      case 4: BATCH_LAUNCH(SOLVER_LV, false) break;
+      case 5: BATCH_LAUNCH(SOLVER_LV, true) break;
+      case 6: BATCH_LAUNCH(SOLVER_PLV, false) break;
+      default: BATCH_LAUNCH(SOLVER_PLV, true) break;
+    }
+#undef BATCH_LAUNCH
+    if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(CCVM_E_CUDA, "batched launch failed");
+    off += n;
+  }
+  cudaFreeAsync(d_map, st);
+  cudaFreeAsync(d_items, st);
+  cudaFreeAsync(d_jobs, st);
+  cudaFreeAsync(sched, st);
+  return rc;
+}
+
+__global__ void build_schedule_batch_kernel(const SchedJob* __restrict__ jobs, float* __restrict__ out) {
+  const SchedJob job = jobs[blockIdx.y];
+  if (blockIdx.x * blockDim.x >= job.a.iterations) return;
+  schedule_row(job.a, blockIdx.x * blockDim.x + threadIdx.x, out + job.offset * SCHED_W);
 }
 
 // ------------------------------------------------------------------------- epilogue
@@ -724,8 +853,8 @@ struct StatsOut {
   int counts[7];
 };
 
-__global__ void __launch_bounds__(1024) stats_kernel(const float* __restrict__ energy, int batch, float optimal,
-                                                     StatsOut* out) {
+__device__ __forceinline__ void stats_body(const float* __restrict__ energy, int batch, float optimal,
+                                           StatsOut* out) {
   __shared__ float s_best[32];
   __shared__ int s_arg[32];
   __shared__ int s_cnt[7];
@@ -781,6 +910,30 @@ __global__ void __launch_bounds__(1024) stats_kernel(const float* __restrict__ e
     out->arg_best = ba == 0x7fffffff ? 0 : ba;
     for (int k = 0; k < 7; ++k) out->counts[k] = s_cnt[k];
   }
+}
+
+__global__ void __launch_bounds__(1024) stats_kernel(const float* __restrict__ energy, int batch, float optimal,
+                                                     StatsOut* out) {
+  stats_body(energy, batch, optimal, out);
+}
+
+// one block per instance: energies concatenated, instance i = energy[offsets[i] .. offsets[i+1])
+__global__ void __launch_bounds__(1024) stats_batch_kernel(const float* __restrict__ energy,
+                                                           const long long* __restrict__ offsets,
+                                                           const float* __restrict__ optimal, StatsOut* out) {
+  const int i = blockIdx.x;
+  const long long lo = offsets[i];
+  stats_body(energy + lo, (int)(offsets[i + 1] - lo), optimal[i], out + i);
+}
+
+extern "C" int ccvm_solution_stats_batch(const float* energy, const int64_t* offsets, const float* optimal_values,
+                                         int32_t count, void* result, void* stream) {
+  if (!energy || !offsets || !optimal_values || !result || count < 1)
+    return fail(CCVM_E_INVALID, "bad argument to ccvm_solution_stats_batch");
+  stats_batch_kernel<<<count, 1024, 0, (cudaStream_t)stream>>>(energy, (const long long*)offsets, optimal_values,
+                                                              (StatsOut*)result);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
 }
 
 extern "C" int ccvm_solution_stats(const float* energy, int32_t batch, double optimal_value, void* result,

@@ -98,19 +98,22 @@ __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4]
 // (A variant that gave the c and s quadratures of a DL tile to different threads -- 16 warps per SM
 // instead of 8 -- was measured and dropped: 43 % more instructions for a loop that is already
 // FMA-pipe-bound, profiles/r1_ncu_sde_dl_tmem_v3.txt.)
+// The body is shared by the single-problem kernel and the batched (many instances per launch)
+// kernel: `cta` is the CTA's index inside ITS problem; threads beyond ng*gt (batched launches use
+// one block size for a whole bucket of problems) only take part in the CTA-wide barriers.
 template <int SOLVER, bool ADAM, int QSRC>
-__global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
-    sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
+__device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaunch& L, const int cta, float* smem,
+                                              uint32_t* tmem_slot_p) {
   constexpr int K = SolverTraits<SOLVER>::K;
   constexpr int KT = K;      // quadratures handled by one thread
   constexpr bool SPLIT = false;
   constexpr int RW = 2 * K;  // floats per (k, trajectory pair): (b0,b1) or (c0,c1,s0,s1)
 
-  extern __shared__ __align__(16) float smem[];
-  __shared__ uint32_t tmem_slot;
+  uint32_t& tmem_slot = *tmem_slot_p;
   const int tid = threadIdx.x;
   const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = L.xs, T = p.iterations;
-  const int grp = tid / L.gt, lg = tid - grp * L.gt;
+  const bool idle = tid >= L.ng * L.gt;
+  const int grp = idle ? 0 : tid / L.gt, lg = tid - grp * L.gt;
   const int half = SPLIT ? (lg >> 7) : 0;   // SPLIT: 0 = c thread, 1 = s thread
   const int l = SPLIT ? (lg & 127) : lg;    // lane in group == TMEM lane
   const int warp = tid >> 5;
@@ -139,14 +142,15 @@ __global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
     }
     hv[j] = h;
   }
-  for (int i = lg; i < 2 * NP * XS; i += L.gt) X[i] = 0.f;
+  if (!idle)
+    for (int i = lg; i < 2 * NP * XS; i += L.gt) X[i] = 0.f;
 
   const int rg = l % RG, cg = l / RG;
   const bool active = cg < CG;
   const int cgc = active ? cg : 0;
   const int j0 = 4 * cgc;
   const uint32_t tlane = tbase + ((uint32_t)((l >> 5) * 32) << 16);  // this warp's TMEM lane quadrant
-  if (QSRC == QSRC_TMEM && grp == 0 && half == 0) {
+  if (QSRC == QSRC_TMEM && !idle && grp == 0 && half == 0) {
     // every lane stores its own copy of the 4 columns it contracts against
     for (int k = 0; k < NP; ++k) {
       float qv[4];
@@ -163,8 +167,9 @@ __global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
   __syncthreads();
   tc_fence_after();
 
+  if (!idle) {
   // ------------------------------------------------------------------ thread tile
-  const long long gb0 = ((long long)blockIdx.x * L.ng + grp) * (2 * RG) + 2 * rg;  // first of 2 trajectories
+  const long long gb0 = ((long long)cta * L.ng + grp) * (2 * RG) + 2 * rg;  // first of 2 trajectories
   float hreg[4], sclamp[4];
   bool colok[4];
 #pragma unroll
@@ -445,11 +450,46 @@ __global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
       }
     }
   }
+  }  // !idle
   if constexpr (QSRC == QSRC_TMEM) {
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_free(tbase, L.tcols);
   }
+}
+
+template <int SOLVER, bool ADAM, int QSRC>
+__global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
+    sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ uint32_t tmem_slot;
+  sde_tile_body<SOLVER, ADAM, QSRC>(p, L, blockIdx.x, smem, &tmem_slot);
+}
+
+// One launch over MANY problem instances (grid = sum of the instances' CTAs): the reference's user
+// loop over instance files (examples/ccvm_boxqp_*.py) folded into the grid.  Each CTA looks up
+// (instance, CTA index inside the instance) and runs the same body with that instance's parameters.
+struct BatchItem {
+  SdeParams p;
+  TmemLaunch L;
+};
+
+template <int SOLVER, bool ADAM>
+__global__ void __launch_bounds__(256, 1)
+    sde_tmem_batch_kernel(const BatchItem* __restrict__ items, const int2* __restrict__ cta_map) {
+  extern __shared__ __align__(16) float smem[];
+  __shared__ uint32_t tmem_slot;
+  __shared__ BatchItem s_item;
+  const int2 m = cta_map[blockIdx.x];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(items + m.x);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&s_item);
+    for (int i = threadIdx.x; i < (int)(sizeof(BatchItem) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const SdeParams p = s_item.p;
+  const TmemLaunch L = s_item.L;
+  sde_tile_body<SOLVER, ADAM, QSRC_TMEM>(p, L, m.y, smem, &tmem_slot);
 }
 
 }  // namespace ccvm

@@ -28,14 +28,22 @@ def next_philox_stream(device, increment):
     return seed & 0xFFFFFFFFFFFFFFFF, offset
 
 
-def solve(solver, algorithm, q, v, batch, iterations, *, lower=0.0, upper=1.0, s=1.0, s_vec=None,
-          pump=0.0, dt=0.0, noise_ratio=1.0, j=1.0, sigma=0.0, feedback_scale=1.0, g=0.0,
-          pump_rate_flag=True, hyperparameters=None, noise=None, seed=None, offset=None,
-          traj_base=0, evolution_step=None, num_samples=0):
-    """Run one ``_solve`` / ``_solve_adam`` loop on the GPU.  Returns (outputs, samples):
-    outputs is the tuple of (B, N) state tensors documented in ccvm_b200.h."""
+class PlannedSolve:
+    """A filled ``ccvm_solve_desc`` together with the tensors its pointers refer to."""
+
+    __slots__ = ("desc", "outputs", "samples", "device", "_keep")
+
+    def __init__(self, desc, outputs, samples, device, keep):
+        self.desc, self.outputs, self.samples, self.device, self._keep = desc, outputs, samples, device, keep
+
+
+def plan_solve(solver, algorithm, q, v, batch, iterations, *, lower=0.0, upper=1.0, s=1.0, s_vec=None,
+               pump=0.0, dt=0.0, noise_ratio=1.0, j=1.0, sigma=0.0, feedback_scale=1.0, g=0.0,
+               pump_rate_flag=True, hyperparameters=None, noise=None, seed=None, offset=None,
+               traj_base=0, evolution_step=None, num_samples=0):
+    """Fill the descriptor of one ``_solve`` / ``_solve_adam`` loop and allocate its outputs without
+    launching anything (``solve`` launches one, ``solve_batch`` many in a single launch)."""
     nat.require_cuda()
-    lib = nat.load()
     dev = _device_of(q)
     n = int(q.shape[0])
     qc, vc = nat.as_f32(q, dev), nat.as_f32(v, dev)
@@ -81,10 +89,30 @@ def solve(solver, algorithm, q, v, batch, iterations, *, lower=0.0, upper=1.0, s
         n_state = 1 if solver in (nat.SOLVER_LANGEVIN, nat.SOLVER_PUMPED_LANGEVIN) else 2
         samples = torch.zeros((n_state, num_samples, batch, n), dtype=torch.float32, device=dev)
         d.evolution_step, d.num_samples, d.samples = int(evolution_step), int(num_samples), nat.ptr(samples)
+    return PlannedSolve(d, tuple(outs), samples, dev, (qc, vc, svc, nz))
+
+
+def solve(solver, algorithm, q, v, batch, iterations, **kwargs):
+    """Run one ``_solve`` / ``_solve_adam`` loop on the GPU.  Returns (outputs, samples):
+    outputs is the tuple of (B, N) state tensors documented in ccvm_b200.h."""
+    lib = nat.load()
+    plan = plan_solve(solver, algorithm, q, v, batch, iterations, **kwargs)
+    with torch.cuda.device(plan.device):
+        nat.check(lib.ccvm_solve(C.byref(plan.desc), nat.current_stream_ptr(plan.device)))
+    # inputs were kept alive until the launch was enqueued on the current stream
+    return plan.outputs, plan.samples
+
+
+def solve_batch(plans):
+    """Launch many planned solves (same solver and algorithm, Philox noise) as ONE grid over
+    instances x trajectory blocks (``ccvm_solve_batch``).  Outputs are those of the plans."""
+    if not plans:
+        return
+    lib = nat.load()
+    dev = plans[0].device
+    arr = (nat.SolveDesc * len(plans))(*[p.desc for p in plans])
     with torch.cuda.device(dev):
-        nat.check(lib.ccvm_solve(C.byref(d), nat.current_stream_ptr(dev)))
-    del qc, vc, svc, nz  # kept alive until the launch was enqueued on the current stream
-    return tuple(outs), samples
+        nat.check(lib.ccvm_solve_batch(arr, len(plans), nat.current_stream_ptr(dev)))
 
 
 def query_launch(desc):
@@ -105,7 +133,8 @@ def _vec_or_scalar(val, n, dev):
 
 
 def epilogue(state, q, v, *, map1=None, post_processor=None, pp_iterations=10, pp_step=None,
-             pp_lower=0.0, pp_upper=1.0, map2=None, scaled_by=1.0, want_energy=True, want_pv=True):
+             pp_lower=0.0, pp_upper=1.0, map2=None, scaled_by=1.0, want_energy=True, want_pv=True,
+             energy_out=None):
     """Fused tail of ``Solver.__call__``: x = state*m1s + m1o -> post-processor -> pv ;
     energy((pv*m2s + m2o)).  ``map1`` / ``map2`` are (scale, shift) or None."""
     nat.require_cuda()
@@ -135,7 +164,11 @@ def epilogue(state, q, v, *, map1=None, post_processor=None, pp_iterations=10, p
     d.pp_step, d.pp_lower, d.pp_upper = float(pp_step), float(pp_lower), float(pp_upper)
     d.scaled_by = float(scaled_by)
     pv = torch.empty((b, n), dtype=torch.float32, device=dev) if want_pv else None
-    en = torch.empty((b,), dtype=torch.float32, device=dev) if want_energy else None
+    en = None
+    if want_energy:
+        en = energy_out if energy_out is not None else torch.empty((b,), dtype=torch.float32, device=dev)
+        if en.numel() != b or en.dtype != torch.float32 or not en.is_contiguous() or en.device != dev:
+            raise ValueError("energy_out must be a contiguous fp32 tensor of batch elements on the state's device")
     d.problem_variables, d.energy = nat.ptr(pv), nat.ptr(en)
     with torch.cuda.device(dev):
         nat.check(lib.ccvm_epilogue(C.byref(d), nat.current_stream_ptr(dev)))
@@ -194,6 +227,26 @@ def solution_stats(energy, optimal_value):
     host = res.cpu()
     best = host[:1].view(torch.float32).item()
     return best, int(host[1]), [int(c) for c in host[2:9]]
+
+
+def solution_stats_batch(energy, offsets, optimal_values):
+    """Statistics of many instances with one kernel and ONE device->host copy.  ``energy`` is the
+    concatenation of the instances' energy vectors (device), ``offsets`` the count+1 boundaries,
+    ``optimal_values`` the per-instance optima.  Returns a list of (best, arg_best, counts[7])."""
+    nat.require_cuda()
+    dev = _device_of(energy)
+    count = len(optimal_values)
+    en = nat.as_f32(energy, dev)
+    off = torch.tensor(list(offsets), dtype=torch.int64).to(dev, non_blocking=True)
+    opt = torch.tensor(list(optimal_values), dtype=torch.float32).to(dev, non_blocking=True)
+    res = torch.empty((count, 9), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_solution_stats_batch(nat.ptr(en), nat.ptr(off), nat.ptr(opt), count,
+                                                       nat.ptr(res), nat.current_stream_ptr(dev)))
+    host = res.cpu()
+    best = host[:, 0].contiguous().view(torch.float32).tolist()
+    rest = host[:, 1:].tolist()
+    return [(best[i], rest[i][0], rest[i][1:]) for i in range(count)]
 
 
 def scaling_factor(q, multiplier):

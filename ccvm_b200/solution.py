@@ -3,7 +3,8 @@
 fractions, 65-146 there) are reduced on the device by one kernel and read back with a single
 36-byte copy instead of eight ``.item()`` synchronisations."""
 import os
-from dataclasses import dataclass, field, asdict
+import copy
+from dataclasses import dataclass, field, fields
 
 import torch
 
@@ -41,6 +42,8 @@ class Solution:
     solution_performance: dict = None
     best_objective_value: float = None
     best_index: int = field(default=None, repr=False)
+    # (best, arg_best, counts[7]) already reduced on the device by a batched launch (solve_many)
+    precomputed_stats: tuple = field(default=None, repr=False)
 
     def __post_init__(self):
         target = torch.device(self.device)
@@ -57,7 +60,10 @@ class Solution:
         obj = self.objective_values
         if not obj.is_cuda:
             obj = engine.to_engine_device(obj)
-        best, arg, counts = engine.solution_stats(obj, self.optimal_value)
+        if self.precomputed_stats is not None:
+            best, arg, counts = self.precomputed_stats
+        else:
+            best, arg, counts = engine.solution_stats(obj, self.optimal_value)
         self.best_objective_value = best
         self.best_index = arg
         n = obj.numel()
@@ -65,7 +71,7 @@ class Solution:
 
     def get_metadata_dict(self) -> dict:
         """All fields that take part in repr (i.e. everything but the tensors)."""
-        return {k: v for k, v in asdict(self).items() if self.__dataclass_fields__[k].repr}
+        return {f.name: copy.deepcopy(getattr(self, f.name)) for f in fields(self) if f.repr}
 
     def save_tensor_to_file(self, tensor_name, file_dir=".", file_name=None):
         """``torch.save`` one entry of ``variables`` to ``<file_dir>/<file_name>.pt``."""

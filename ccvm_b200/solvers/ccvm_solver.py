@@ -41,6 +41,16 @@ _GPU_POWER = {20: 28.93, 30: 29.8, 40: 31.09, 50: 31.29, 60: 31.49, 70: 32.28}
 _HOOKS = ("calculate_drift", "calculate_grads", "change_variables", "fit_to_constraints")
 
 
+class _PendingSolution:
+    """An instance whose solve was planned but not yet launched (``CCVMSolver.solve_many``)."""
+
+    __slots__ = ("instance", "batch_size", "iterations", "run_epilogue", "make_solution")
+
+    def __init__(self, instance, batch_size, iterations, run_epilogue, make_solution):
+        self.instance, self.batch_size, self.iterations = instance, batch_size, iterations
+        self.run_epilogue, self.make_solution = run_epilogue, make_solution
+
+
 class CCVMSolver(ABC):
     """Common behaviour of DLSolver, MFSolver, LangevinSolver and PumpedLangevinSolver.
 
@@ -67,6 +77,8 @@ class CCVMSolver(ABC):
         #: validation hook: a ``[iterations][K][N][batch]`` tensor of standard normals that the
         #: next solve consumes instead of Philox noise (K = 2 for DL, else 1).
         self.noise_source = None
+        #: list collecting planned (not yet launched) solves while ``solve_many`` is gathering a batch
+        self._deferred = None
 
     # ------------------------------------------------------------------ properties
     @property
@@ -214,11 +226,20 @@ class CCVMSolver(ABC):
         s_vec, s_val = (S if S.ndim == 1 else S[0], 0.0) if torch.is_tensor(S) and S.numel() > 1 else (None, float(S))
         lower, upper = self.solution_bounds
         num_samples, _ = self._evolution_plan(None, iterations, evolution_step_size, "unused")
-        outs, samples = engine.solve(
-            solver_id, algorithm, self.q_matrix, self.v_vector, batch_size, iterations,
-            lower=lower, upper=upper, s=s_val, s_vec=s_vec, hyperparameters=hyperparameters,
-            noise=self.noise_source, evolution_step=evolution_step_size or None,
-            num_samples=num_samples or 0, **scalars)
+        kwargs = dict(lower=lower, upper=upper, s=s_val, s_vec=s_vec, hyperparameters=hyperparameters,
+                      noise=self.noise_source, evolution_step=evolution_step_size or None,
+                      num_samples=num_samples or 0, **scalars)
+        if self._deferred is not None:
+            # solve_many: plan only; the whole batch of instances is launched as one grid later
+            if self.noise_source is not None or evolution_step_size:
+                raise ValueError("solve_many supports neither noise replay nor evolution sampling.")
+            plan = engine.plan_solve(solver_id, algorithm, self.q_matrix, self.v_vector, batch_size, iterations,
+                                     **kwargs)
+            self._deferred.append(plan)
+            self._samples = None
+            return plan.outputs
+        outs, samples = engine.solve(solver_id, algorithm, self.q_matrix, self.v_vector, batch_size, iterations,
+                                     **kwargs)
         self._samples = samples
         return outs
 
@@ -231,8 +252,9 @@ class CCVMSolver(ABC):
         num_samples, evolution_file = self._evolution_plan(instance, iterations, evolution_step_size,
                                                            evolution_file)
         self._samples = None
-        if self.device == "cuda":
-            torch.cuda.synchronize()
+        deferred = self._deferred is not None
+        if self.device == "cuda" and not deferred:
+            torch.cuda.current_stream().synchronize()  # stream-level: other streams may be solving too
         solve_time_start = time.time()
         if algorithm_parameters is None:
             outs = self._solve(*solve_args(False))
@@ -240,41 +262,104 @@ class CCVMSolver(ABC):
             outs = self._solve_adam(*solve_args(True), algorithm_parameters.to_dict())
         else:
             raise ValueError(f"Solver option type {type(algorithm_parameters)} is not supported.")
-        if self.device == "cuda":
-            torch.cuda.synchronize()  # the reference stops its clock without one
+        if self.device == "cuda" and not deferred:
+            torch.cuda.current_stream().synchronize()  # the reference stops its clock without one
         solve_time = (time.time() - solve_time_start) / batch_size
 
         state, map1, map2, make_variables = finish(outs)
+        q_matrix, v_vector = self.q_matrix, self.v_vector
+        scaled_by = _as_float(instance.scaled_by)
+
+        def run_epilogue(energy_out=None):
+            return engine.epilogue(state, q_matrix, v_vector, map1=map1, post_processor=post_processor,
+                                   pp_iterations=10, map2=map2, scaled_by=scaled_by, energy_out=energy_out)
+
+        def make_solution(pv, objval, solve_time, pp_time, stats=None):
+            return Solution(
+                problem_size=instance.problem_size,
+                batch_size=batch_size,
+                instance_name=instance.name,
+                iterations=iterations,
+                objective_values=objval,
+                solve_time=solve_time,
+                pp_time=pp_time,
+                optimal_value=instance.optimal_sol,
+                best_value=instance.best_sol,
+                num_frac_values=instance.num_frac_values,
+                solution_vector=instance.solution_vector,
+                variables=make_variables(pv),
+                device=self.device,
+                precomputed_stats=stats,
+            )
+
+        if deferred:
+            return _PendingSolution(instance, batch_size, iterations, run_epilogue, make_solution)
+
         pp_start = time.time()
-        pv, objval = engine.epilogue(
-            state, self.q_matrix, self.v_vector, map1=map1, post_processor=post_processor,
-            pp_iterations=10, map2=map2, scaled_by=_as_float(instance.scaled_by))
+        pv, objval = run_epilogue()
         pp_time = 0.0
         if post_processor:
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()
             pp_time = (time.time() - pp_start) / batch_size
 
         if evolution_step_size:
             self._write_evolution(evolution_file, objval)
 
-        solution = Solution(
-            problem_size=instance.problem_size,
-            batch_size=batch_size,
-            instance_name=instance.name,
-            iterations=iterations,
-            objective_values=objval,
-            solve_time=solve_time,
-            pp_time=pp_time,
-            optimal_value=instance.optimal_sol,
-            best_value=instance.best_sol,
-            num_frac_values=instance.num_frac_values,
-            solution_vector=instance.solution_vector,
-            variables=make_variables(pv),
-            device=self.device,
-        )
+        solution = make_solution(pv, objval, solve_time, pp_time)
         if evolution_step_size:
             solution.evolution_file = evolution_file
         return solution
+
+    # ------------------------------------------------------------- many instances
+    def solve_many(self, instances, post_processor=None, algorithm_parameters=None, **call_kwargs):
+        """Solve a sequence of instances with ONE solver-loop launch (grid over instances x
+        trajectory blocks, ``ccvm_solve_batch``), per-instance fused epilogues enqueued without any
+        host synchronisation, and one batched statistics kernel with a single device->host copy.
+
+        Returns the list of ``Solution`` objects ``[self(instance=i, ...) for i in instances]``
+        would return under the same generator state (the reference's user loop over instance
+        files, examples/ccvm_boxqp_dl.py:27-52), except that ``solve_time`` / ``pp_time`` are the
+        measured device times of the shared launches apportioned by each instance's share of the
+        drift work (batch x iterations x N^2) -- a batch-1000 solve fills a fraction of the GPU, so
+        concurrent instances are how the machine is kept busy."""
+        if self.device != "cuda":
+            raise engine.nat.NativeError(
+                "ccvm_b200 solves on CUDA only (device='cuda'); there is no CPU implementation.")
+        instances = list(instances)
+        if not instances:
+            return []
+        if call_kwargs.get("evolution_step_size"):
+            raise ValueError("solve_many does not support evolution sampling.")
+        self._deferred = []
+        try:
+            pending = [self(instance=inst, post_processor=post_processor,
+                            algorithm_parameters=algorithm_parameters, **call_kwargs) for inst in instances]
+            plans = self._deferred
+        finally:
+            self._deferred = None
+        dev = plans[0].device
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        engine.solve_batch(plans)
+        ev[1].record()
+        offsets = [0]
+        for p in pending:
+            offsets.append(offsets[-1] + p.batch_size)
+        energy = torch.empty(offsets[-1], dtype=torch.float32, device=dev)
+        pvs = [p.run_epilogue(energy[offsets[i]:offsets[i + 1]])[0] for i, p in enumerate(pending)]
+        ev[2].record()
+        stats = engine.solution_stats_batch(energy, offsets, [p.instance.optimal_sol for p in pending])
+        # solution_stats_batch ended with a device->host copy: the events have completed
+        t_solve, t_pp = ev[0].elapsed_time(ev[1]) * 1e-3, ev[1].elapsed_time(ev[2]) * 1e-3
+        work = [p.batch_size * p.iterations * p.instance.problem_size ** 2 for p in pending]
+        total = float(sum(work)) or 1.0
+        out = []
+        for i, p in enumerate(pending):
+            share = work[i] / total
+            out.append(p.make_solution(pvs[i], energy[offsets[i]:offsets[i + 1]],
+                                       t_solve * share / p.batch_size,
+                                       (t_pp * share / p.batch_size) if post_processor else 0.0, stats[i]))
+        return out
 
     # ----------------------------------------------------------- evolution sampling
     _EVOLUTION_TRAILING_TAB = True

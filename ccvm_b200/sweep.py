@@ -30,10 +30,17 @@ def synthetic_instance(n, seed, scaling_multiplier, device="cuda", name=None):
     return inst
 
 
-def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=None, gather=True, **call_kwargs):
-    """Solve ``instances`` (a sequence, or a callable index -> instance so that ranks only build
-    their own) with ``solver``; returns the list of metadata dicts of ALL instances in order (on
-    every rank when ``gather``), each extended with ``best_index`` and ``rank``."""
+def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=None, gather=True, chunk=1,
+                **call_kwargs):
+    """Solve ``instances`` (a sequence, or a ``(count, index -> instance)`` pair so that ranks only
+    build their own) with ``solver``; returns the list of metadata dicts of ALL instances in order
+    (on every rank when ``gather``), each extended with ``best_index``, ``rank`` and ``index``.
+
+    ``chunk`` > 1 solves that many instances of this rank per launch through
+    ``CCVMSolver.solve_many`` (one grid over instances x trajectory blocks, one statistics kernel,
+    one device->host copy per chunk): a batch-1000 solve occupies a fraction of the GPU's SMs, so
+    batching instances is what fills the machine.  Per-instance ``solve_time`` is then the chunk's
+    device time apportioned by drift work."""
     if rank is None:
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
     if world_size is None:
@@ -41,13 +48,22 @@ def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=No
     count = instances[0] if isinstance(instances, tuple) else len(instances)
     getter = instances[1] if isinstance(instances, tuple) else instances.__getitem__
     local = {}
-    for k in range(count):
-        if parallel.instance_owner(k, world_size) != rank:
-            continue
-        sol = solver(instance=getter(k), post_processor=post_processor, **call_kwargs)
+    mine = [k for k in range(count) if parallel.instance_owner(k, world_size) == rank]
+
+    def record(k, sol):
         rec = sol.get_metadata_dict()
         rec["best_index"], rec["rank"], rec["index"] = sol.best_index, rank, k
         local[k] = rec
+
+    if chunk <= 1:
+        for k in mine:
+            record(k, solver(instance=getter(k), post_processor=post_processor, **call_kwargs))
+    else:
+        for lo in range(0, len(mine), chunk):
+            ks = mine[lo:lo + chunk]
+            sols = solver.solve_many([getter(k) for k in ks], post_processor=post_processor, **call_kwargs)
+            for k, sol in zip(ks, sols):
+                record(k, sol)
     if world_size == 1 or not gather:
         return [local[k] for k in sorted(local)]
     shards = [None] * world_size

@@ -112,6 +112,18 @@ typedef struct ccvm_solve_desc {
 int ccvm_solve(const ccvm_solve_desc* desc, void* stream);
 
 /*
+ * Many instances in ONE launch (grid over instances x trajectory blocks).
+ *
+ * Replaces: the user-level loop over instance files around Solver.__call__
+ *           (examples/ccvm_boxqp_dl.py:27-52 and siblings).  `descs[i]` are
+ * ordinary ccvm_solve descriptors that may differ in n, batch, iterations, scalars and pointers but
+ * must share solver and algorithm, use CCVM_RNG_PHILOX and no evolution sampling.  Instances with
+ * n <= 128 are bucketed by CTA size and solved by one launch per bucket; larger ones fall back to
+ * one ccvm_solve each.  Results are identical to calling ccvm_solve on every descriptor.
+ */
+int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, void* stream);
+
+/*
  * The tail of Solver.__call__: optional affine change of variables, optional batched
  * post-processor, optional second change of variables (the DL double map), BoxQP energy.
  *
@@ -170,6 +182,18 @@ int ccvm_postprocess_adam(float* x, const float* q, const float* v, int32_t batc
  */
 int ccvm_solution_stats(const float* energy, int32_t batch, double optimal_value, void* result,
                         void* stream);
+
+/*
+ * ccvm_solution_stats for `count` instances in one launch (one 36-byte record each): the per-result
+ * Solution construction of a sweep (examples/ccvm_boxqp_plot.py:40-82 builds one Solution per
+ * instance, each with eight .item() syncs) becomes one kernel and one device->host copy.
+ * `energy` is the concatenation of the instances' energy vectors, instance i occupying
+ * [offsets[i], offsets[i+1]) (device int64[count+1]); `optimal_values` is device float[count];
+ * `result` is device memory of count x 9 x 4 bytes laid out as in ccvm_solution_stats.
+ */
+int ccvm_solution_stats_batch(const float* energy, const int64_t* offsets,
+                              const float* optimal_values, int32_t count, void* result,
+                              void* stream);
 
 /* Replaces CCVMSolver.get_scaling_factor (solvers/ccvm_solver.py:134-150):
  *   *out (device float) = sqrt(sum |Q_ij|) * multiplier. */

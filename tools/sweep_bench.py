@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1000)
     ap.add_argument("--iters", type=int, default=1500)
     ap.add_argument("--solvers", default="mf,langevin,pumped_langevin,dl")
+    ap.add_argument("--chunk", type=int, default=1, help="instances per batched launch (solve_many)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -55,19 +56,19 @@ def main():
         for i in range(len(specs)):      # build this rank's instances outside the timed region
             if i % world == rank:
                 get(i)
-        sweep.solve_sweep(solver, (min(len(specs), 2 * world), get), post_processor=pp)  # warm-up
+        sweep.solve_sweep(solver, (min(len(specs), 2 * world), get), post_processor=pp, chunk=args.chunk)  # warm-up
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        md = sweep.solve_sweep(solver, (len(specs), get), post_processor=pp)
+        md = sweep.solve_sweep(solver, (len(specs), get), post_processor=pp, chunk=args.chunk)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         all_md[name] = md
         if rank == 0:
             steps = len(specs) * args.batch * args.iters
             print(json.dumps({"solver": name, "post_processor": pp, "instances": len(specs), "sizes": sizes,
-                              "batch": args.batch, "iterations": args.iters, "n_gpus": world, "wall_s": wall,
+                              "batch": args.batch, "iterations": args.iters, "n_gpus": world, "chunk": args.chunk, "wall_s": wall,
                               "ms_per_instance": wall / len(specs) * 1e3, "traj_steps_per_s": steps / wall,
                               "sum_kernel_solve_time_s": sum(r["solve_time"] * r["batch_size"] for r in md)}), flush=True)
     if rank == 0:
