@@ -13,6 +13,7 @@
 #include "../../include/ccvm_b200.h"
 #include "sde_kernel.cuh"
 #include "sde_kernel_tmem.cuh"
+#include "sde_kernel_tc.cuh"
 
 using namespace ccvm;
 
@@ -196,10 +197,21 @@ struct TmemPlan {
   size_t smem;
 };
 
-enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2 };
+enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2, PATH_TC = 3 };
+
+// tcgen05 3xTF32 drift (sde_kernel_tc.cuh) where batch x N x N is a genuine dense GEMM:
+// n >= 256 and at least 1024 contraction rows (8 CTAs of 128 rows); CCVM_TC=0 / 1 overrides the
+// size rule (experiments and tests), evolution sampling stays on the SIMT path.
+static bool tc_eligible(const ccvm_solve_desc& d) {
+  if (d.n > TC_MAX_CHUNKS * TC_BN || d.evolution_step > 0) return false;
+  const long long rows = (long long)d.batch * (d.solver == CCVM_SOLVER_DL ? 2 : 1);
+  if (const char* e = getenv("CCVM_TC")) return atoi(e) != 0;
+  return d.n >= 256 && rows >= 1024;
+}
 
 static int choose_path(const ccvm_solve_desc& d) {
   if (getenv("CCVM_LEGACY")) return PATH_LEGACY;  // first-generation shared-memory kernel (n <~ 160)
+  if (tc_eligible(d)) return PATH_TC;
   if (d.n <= 128 && getenv("CCVM_NO_TMEM") == nullptr) return PATH_TMEM;
   return PATH_GMEM;
 }
@@ -304,6 +316,120 @@ static int regs_tmem(int qsrc) {
   cudaError_t e = qsrc == QSRC_TMEM ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM>)
                                     : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM>);
   return e == cudaSuccess ? fa.numRegs : -1;
+}
+
+// ------------------------------------------------------------------ tensor-core path
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+// fp32 [rows][cols] row-major, box = box_rows x 16 floats (one SWIZZLE_64B row)
+static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(CCVM_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CCVM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CCVM_OK;
+}
+
+struct TcPlan {
+  int np, rows, rows_p, n_aux, ctas;
+  size_t smem;
+};
+
+static void plan_tc(const ccvm_solve_desc& d, TcPlan& P) {
+  const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1;
+  P.np = ((d.n + TC_BN - 1) / TC_BN) * TC_BN;
+  P.rows = K * d.batch;
+  P.rows_p = ((P.rows + TC_BM - 1) / TC_BM) * TC_BM;
+  const bool adam = d.algorithm == CCVM_ALG_ADAM;
+  P.n_aux = (d.solver == CCVM_SOLVER_MF ? 2 : 0) + (adam ? 2 : 0);
+  P.ctas = P.rows_p / TC_BM;
+  P.smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)2 * P.np * sizeof(float);
+}
+
+template <int SOLVER, bool ADAM>
+static int launch_tc(const SdeParams& p, const TcParams& tc, const TcPlan& P, const CUtensorMap& mxh,
+                     const CUtensorMap& mxl, const CUtensorMap& mqh, const CUtensorMap& mql, cudaStream_t st) {
+  const size_t plane = (size_t)tc.rows_p * tc.np;
+  tc_init_state_kernel<SOLVER><<<(unsigned)((plane / 4 + 255) / 256), 256, 0, st>>>(p, tc, P.n_aux);
+  CUDA_TRY(cudaGetLastError());
+  auto kern = sde_tc_kernel<SOLVER, ADAM>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+  kern<<<P.ctas, TC_THREADS, P.smem, st>>>(p, tc, mxh, mxl, mqh, mql);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+template <int SOLVER, bool ADAM>
+static int regs_tc() {
+  cudaFuncAttributes fa;
+  return cudaFuncGetAttributes(&fa, sde_tc_kernel<SOLVER, ADAM>) == cudaSuccess ? fa.numRegs : -1;
+}
+
+// `p` carries everything but the launch geometry; sched is already being built on `st`
+static int solve_tc(const ccvm_solve_desc* d, SdeParams& p, cudaStream_t st) {
+  TcPlan P;
+  plan_tc(*d, P);
+  const size_t plane = (size_t)P.rows_p * P.np;
+  const size_t floats = 4 * plane + (size_t)P.n_aux * plane + 2 * (size_t)P.np * P.np + 2 * (size_t)P.np;
+  float* scratch = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&scratch, floats * sizeof(float), st));
+  TcParams tc;
+  tc.xh = scratch;
+  tc.xl = tc.xh + 2 * plane;
+  tc.aux = tc.xl + 2 * plane;
+  float* qt_hi = tc.aux + (size_t)P.n_aux * plane;
+  float* qt_lo = qt_hi + (size_t)P.np * P.np;
+  float* hvec = qt_lo + (size_t)P.np * P.np;
+  float* svec = hvec + P.np;
+  tc.hvec = hvec;
+  tc.svec = svec;
+  tc.np = P.np;
+  tc.rows = P.rows;
+  tc.rows_p = P.rows_p;
+  tc_prepare_q_kernel<<<P.np, 256, 0, st>>>(p.q, p.v, p.drift_s_vec, p.drift_s, p.clamp_s_vec, p.clamp_s, p.a_half,
+                                            p.b_half, p.n, P.np, qt_hi, qt_lo, hvec, svec);
+  int rc = CCVM_OK;
+  if (cudaGetLastError() != cudaSuccess) rc = fail(CCVM_E_CUDA, "tc_prepare_q_kernel launch failed");
+  CUtensorMap mxh, mxl, mqh, mql;
+  if (!rc) rc = make_map_2d(&mxh, tc.xh, 2ull * P.rows_p, P.np, TC_BM);
+  if (!rc) rc = make_map_2d(&mxl, tc.xl, 2ull * P.rows_p, P.np, TC_BM);
+  if (!rc) rc = make_map_2d(&mqh, qt_hi, P.np, P.np, TC_BN);
+  if (!rc) rc = make_map_2d(&mql, qt_lo, P.np, P.np, TC_BN);
+  if (!rc) {
+    const bool adam = d->algorithm == CCVM_ALG_ADAM;
+    switch (d->solver * 2 + (adam ? 1 : 0)) {
+      case 0: rc = launch_tc<SOLVER_DL, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      case 1: rc = launch_tc<SOLVER_DL, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      case 2: rc = launch_tc<SOLVER_MF, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      case 3: rc = launch_tc<SOLVER_MF, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      case 4: rc = launch_tc<SOLVER_LV, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      case 5: rc = launch_tc<SOLVER_LV, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      case 6: rc = launch_tc<SOLVER_PLV, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      default: rc = launch_tc<SOLVER_PLV, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+    }
+  }
+  cudaFreeAsync(scratch, st);
+  return rc;
 }
 
 static int validate_solve(const ccvm_solve_desc* d) {
@@ -412,6 +538,22 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
   const int path = choose_path(*d);
+  if (path == PATH_TC) {
+    TcPlan P;
+    plan_tc(*d, P);
+    info5[0] = TC_THREADS;
+    info5[1] = P.ctas;
+    info5[2] = TC_BM / (d->solver == CCVM_SOLVER_DL ? 2 : 1);
+    info5[3] = (int)P.smem;
+    const bool a = d->algorithm == CCVM_ALG_ADAM;
+    int r = -1;
+    if (d->solver == SOLVER_DL) r = a ? regs_tc<SOLVER_DL, true>() : regs_tc<SOLVER_DL, false>();
+    if (d->solver == SOLVER_MF) r = a ? regs_tc<SOLVER_MF, true>() : regs_tc<SOLVER_MF, false>();
+    if (d->solver == SOLVER_LV) r = a ? regs_tc<SOLVER_LV, true>() : regs_tc<SOLVER_LV, false>();
+    if (d->solver == SOLVER_PLV) r = a ? regs_tc<SOLVER_PLV, true>() : regs_tc<SOLVER_PLV, false>();
+    info5[4] = r;
+    return CCVM_OK;
+  }
   if (path != PATH_LEGACY) {
     TmemPlan P;
     if ((rc = plan_tmem(*d, di, path, P))) return rc;
@@ -458,11 +600,13 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
   const int path = choose_path(*d);
-  const bool use_tmem = path != PATH_LEGACY;  // tiled kernel (TMEM or streamed Q)
+  const bool use_tmem = path == PATH_TMEM || path == PATH_GMEM;  // tiled SIMT kernel (TMEM or streamed Q)
   LaunchPlan L;
   TmemPlan TP;
   memset(&L, 0, sizeof(L));
-  if (use_tmem) {
+  if (path == PATH_TC) {
+    // planned inside solve_tc
+  } else if (use_tmem) {
     if ((rc = plan_tmem(*d, di, path, TP))) return rc;
     L.cg = TP.cg;
   } else if ((rc = plan_launch(*d, di, L))) {
@@ -482,6 +626,11 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   p.rg = L.rg;
   p.xs = L.xs;
   p.use_tma = L.use_tma;
+  if (path == PATH_TC) {
+    rc = solve_tc(d, p, st);
+    cudaFreeAsync(sched, st);
+    return rc;
+  }
 
   float* qs_scratch = nullptr;
   if (use_tmem && TP.qsrc == QSRC_GMEM) {

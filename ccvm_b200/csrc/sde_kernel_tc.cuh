@@ -1,0 +1,552 @@
+// Persistent Euler-Maruyama kernel, tensor-core variant (n >= 256, >= 1024 contraction rows):
+// the drift  G = X . Qs  is a genuine dense GEMM there (BASELINE config 4: n = 1024, batch 8192),
+// so it runs on the 5th-generation tensor cores as a 3xTF32 product
+//
+//        X . Qs  ~=  Xlo . Qhi  +  Xhi . Qlo  +  Xhi . Qhi        (hi = tf32(x), lo = x - hi)
+//
+// with FP32 accumulation in TMEM (tcgen05.mma kind::tf32, cta_group::1, M = 128, N = 256, K = 8).
+// Reference loops: dl_solver.py:468-769, mf_solver.py:493-764, langevin_solver.py:368-561,
+// pumped_langevin_solver.py:232-449 (the einsum "bi,ij->bj" + the elementwise SDE step).
+//
+// Decomposition.  The contraction rows are (trajectory, quadrature) pairs: DL interleaves them as
+// row 2b = c_b, row 2b+1 = s_b (neighbouring lanes of one warp, so c^2 + s^2 is one shuffle); the
+// other solvers have one row per trajectory.  A CTA owns 128 rows for ALL iterations -- rows are
+// independent, there is no inter-CTA exchange.  Per iteration and 256-column output chunk:
+//
+//   warp 8 (one lane)  TMA producer: streams 16-wide k-blocks of the CTA's state rows (hi and lo,
+//                      128 x 16) and of Qs^T (hi and lo, 256 x 16) into a 4-stage shared-memory ring
+//                      (SWIZZLE_64B, K-major), 48 KB per stage;
+//   warp 9 (one lane)  MMA issuer: 2 k-steps x 3 split terms per stage into one of two 128 x 256
+//                      FP32 accumulators in TMEM; tcgen05.commit releases the stage / publishes
+//                      the accumulator;
+//   warps 0-7          epilogue: tcgen05.ld the accumulator (row = lane, 16 columns at a time),
+//                      add the affine drift term, draw the Philox / replayed noise, apply the
+//                      solver's SDE step in FP32 and write the new state as (hi, lo) into the
+//                      OTHER ping-pong buffer -- overlapped with the MMAs of the next chunk.
+//
+// The state does not fit on chip at these sizes (DL, n = 1024: 8 KB per trajectory), so it lives
+// in global memory (L2 / HBM) as two exact FP32 summands hi + lo, which are at the same time the
+// two tensor-core operands; Qs^T hi / lo (8 MB at n = 1024) stays L2 resident.  A k-block of
+// iteration t+1 only depends on the epilogue of the output chunk that covers its columns, so the
+// producer waits per chunk (state_ready[c]) and the pipeline never drains between iterations.
+#pragma once
+#include <cuda.h>
+
+#include "ccvm_common.cuh"
+#include "sde_kernel.cuh"
+#include "sde_kernel_tmem.cuh"
+
+namespace ccvm {
+
+constexpr int TC_BM = 128;       // rows per CTA (= UMMA M)
+constexpr int TC_BN = 256;       // output columns per accumulator (= UMMA N)
+constexpr int TC_BK = 16;        // k-block: 16 floats = 64 B = one SWIZZLE_64B row
+constexpr int TC_STAGES = 4;
+constexpr int TC_EPI_WARPS = 8;  // warps 0-7; warp 8 = TMA producer, warp 9 = MMA issuer
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 8 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 16 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
+constexpr int TC_MAX_CHUNKS = 8;  // n <= 2048
+
+struct TcParams {
+  float* xh;        // [2][rows_p][np]  hi part of the contraction input (ping-pong)
+  float* xl;        // [2][rows_p][np]  lo part
+  float* aux;       // [n_aux][rows_p][np] FP32 in-place state: MF mu, sigma; Adam m, v
+  const float* hvec;    // [np] affine drift term h_j (0 in the padding)
+  const float* svec;    // [np] clamp bound S_j (0 in the padding)
+  int np;           // n rounded up to a multiple of TC_BN
+  int rows;         // valid rows = K * batch
+  int rows_p;       // rows rounded up to a multiple of TC_BM
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded spin: a protocol bug must trap (a reported launch failure) rather than hang the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long start = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (spins & 0xfff) == 0xfff) {
+      const long long now = clock64();
+      if (start == 0) start = now;
+      else if (now - start > 4000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_64B, rows of 64 B, 8-row atoms of 512 B
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);        // start address  [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;                    // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                             // layout type: SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// ---------------------------------------------------------------- one-off preparation
+// Qs^T split:  qt_hi[j][k] + qt_lo[j][k] = Qs[k][j] = -alpha_k alpha_j Q[k][j]  (zero padded), and the
+// per-column vectors h_j = -alpha_j ((u+l)/2 colsum_j(Q) + V_j), S_j.
+__global__ void tc_prepare_q_kernel(const float* __restrict__ q, const float* __restrict__ v,
+                                    const float* __restrict__ drift_s_vec, float drift_s,
+                                    const float* __restrict__ clamp_s_vec, float clamp_s, float a_half, float b_half,
+                                    int n, int np, float* __restrict__ qt_hi, float* __restrict__ qt_lo,
+                                    float* __restrict__ hvec, float* __restrict__ svec) {
+  const int j = blockIdx.x;  // output column
+  const float aj = j < n ? a_half / (drift_s_vec ? drift_s_vec[j] : drift_s) : 0.f;
+  float cs = 0.f;
+  for (int k = threadIdx.x; k < np; k += blockDim.x) {
+    float val = 0.f;
+    if (k < n && j < n) {
+      const float qkj = q[(size_t)k * n + j];
+      cs += qkj;
+      const float ak = a_half / (drift_s_vec ? drift_s_vec[k] : drift_s);
+      val = -ak * aj * qkj;
+    }
+    const float hi = tf32_rna(val);
+    qt_hi[(size_t)j * np + k] = hi;
+    qt_lo[(size_t)j * np + k] = val - hi;
+  }
+  __shared__ float red[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    hvec[j] = j < n ? -aj * (b_half * tot + v[j]) : 0.f;
+    svec[j] = j < n ? (clamp_s_vec ? clamp_s_vec[j] : clamp_s) : 0.f;
+  }
+}
+
+// Philox normals of (trajectory gb, iteration t, column group cg, quadrature qi): the SAME stream
+// the SIMT kernels draw (sde_kernel_tmem.cuh `draw`), so both paths see identical noise.
+__device__ __forceinline__ void tc_philox4(const SdeParams& p, unsigned long long gb, int t, int cg, uint32_t qi,
+                                           float (&n)[4]) {
+  const uint4 r = philox4x32_10(
+      make_uint4((uint32_t)gb, (uint32_t)t, (uint32_t)cg | (qi << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
+      make_uint2(p.seed_lo, p.seed_hi ^ p.off_hi));
+  box_muller(r.x, r.y, n[0], n[1]);
+  box_muller(r.z, r.w, n[2], n[3]);
+}
+
+// noise of 4 consecutive columns j0..j0+3 of one row at iteration t (0 beyond column n)
+__device__ __forceinline__ void tc_noise4(const SdeParams& p, int K, long long b, uint32_t qi, int t, int j0,
+                                          float (&w)[4]) {
+  if (p.noise == nullptr) {
+    tc_philox4(p, (unsigned long long)(p.traj_base + b), t, j0 >> 2, qi, w);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = j0 + i;
+      w[i] = (j < p.n && b < p.batch)
+                 ? p.noise[(((size_t)t * K + qi) * p.n + j) * (size_t)p.noise_batch + (size_t)(p.traj_base + b)]
+                 : 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (j0 + i >= p.n) w[i] = 0.f;
+}
+
+// initial contraction input and in-place state (both ping-pong halves are cleared)
+template <int SOLVER>
+__global__ void tc_init_state_kernel(const SdeParams p, const TcParams tc, int n_aux) {
+  constexpr int K = SolverTraits<SOLVER>::K;
+  const size_t plane = (size_t)tc.rows_p * tc.np;
+  const size_t idx4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (idx4 >= plane) return;
+  const int row = (int)(idx4 / tc.np), j0 = (int)(idx4 - (size_t)row * tc.np);
+  float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+  if constexpr (SOLVER == SOLVER_MF) {
+    // measurement of iteration 0: clamp(mu + sqrt(1/(4 j_1)) W_0 / sqrt(dt)) with mu = 0 (mf_solver.py:551-554)
+    float w[4];
+    tc_noise4(p, K, row, 0u, 0, j0, w);
+    const float sa = p.sched[SC_A];
+    float m[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float s = tc.svec[j0 + i];
+      m[i] = clampf(sa * w[i], -s, s);
+    }
+    hi = make_float4(tf32_rna(m[0]), tf32_rna(m[1]), tf32_rna(m[2]), tf32_rna(m[3]));
+    lo = make_float4(m[0] - hi.x, m[1] - hi.y, m[2] - hi.z, m[3] - hi.w);
+  }
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  *reinterpret_cast<float4*>(tc.xh + idx4) = hi;
+  *reinterpret_cast<float4*>(tc.xl + idx4) = lo;
+  *reinterpret_cast<float4*>(tc.xh + plane + idx4) = z;
+  *reinterpret_cast<float4*>(tc.xl + plane + idx4) = z;
+  for (int a = 0; a < n_aux; ++a) {
+    const float init = (SOLVER == SOLVER_MF && a == 1) ? 0.5f : 0.f;  // sigma starts at 1/2
+    *reinterpret_cast<float4*>(tc.aux + (size_t)a * plane + idx4) = make_float4(init, init, init, init);
+  }
+}
+
+// Adam transform of one gradient element (dl_solver.py:699-727 and siblings), scalar form of adam_tile4
+__device__ __forceinline__ float tc_adam(float g, float& m, float& v, const SdeParams& p, float ib1, float ib2) {
+  m = fmaf(m, p.beta1, g * p.omb1);
+  const float mh = m * ib1;
+  float upd;
+  if (!p.beta2_is_one) {
+    v = fmaf(v, p.beta2, (g * g) * p.omb2);
+    const float den = fast_sqrt(v * ib2) + 1e-8f;
+    upd = p.adam_alpha * __fdividef(mh, den);
+  } else {
+    upd = p.adam_alpha * mh;
+  }
+  return p.add_assign ? g + upd : upd;
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int SOLVER, bool ADAM>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    sde_tc_kernel(const SdeParams p, const TcParams tc, const __grid_constant__ CUtensorMap map_xh,
+                  const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_qh,
+                  const __grid_constant__ CUtensorMap map_ql) {
+  constexpr int K = SolverTraits<SOLVER>::K;
+  constexpr int AUX_ADAM = SOLVER == SOLVER_MF ? 2 : 0;  // first Adam array (after mu, sigma)
+
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 4 + TC_MAX_CHUNKS];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NP = tc.np, T = p.iterations;
+  const int NC = NP / TC_BN;          // output chunks per iteration
+  const int KB = NP / TC_BK;          // k-blocks per chunk
+  const int KB_PER_CHUNK = TC_BN / TC_BK;
+  const int row0 = blockIdx.x * TC_BM;
+  const size_t plane = (size_t)tc.rows_p * NP;
+
+  // 1024-byte aligned stage ring, then the per-column vectors
+  const uint32_t smem_base = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  float* vecs = reinterpret_cast<float*>(tc_smem + (smem_base - smem_u32(tc_smem)) + TC_STAGES * TC_STAGE_BYTES);
+  float* hs = vecs;        // [NP]
+  float* ss = vecs + NP;   // [NP]
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+  auto accf_bar = [&](int a) { return bar0 + 8u * (2 * TC_STAGES + a); };
+  auto acce_bar = [&](int a) { return bar0 + 8u * (2 * TC_STAGES + 2 + a); };
+  auto ready_bar = [&](int c) { return bar0 + 8u * (2 * TC_STAGES + 4 + c); };
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(accf_bar(a), 1);
+      mbar_init(acce_bar(a), TC_EPI_WARPS * 32);
+    }
+    for (int c = 0; c < TC_MAX_CHUNKS; ++c) mbar_init(ready_bar(c), TC_EPI_WARPS * 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(&tmem_slot, 512);
+  for (int j = tid; j < NP; j += TC_THREADS) {
+    hs[j] = tc.hvec[j];
+    ss[j] = tc.svec[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 8) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < T; ++t) {
+        const int arow = (t & 1) * tc.rows_p + row0;  // iteration t contracts ping-pong half t&1
+        for (int nc = 0; nc < NC; ++nc) {
+          for (int kb = 0; kb < KB; ++kb) {
+            if (t > 0 && nc == 0 && (kb % KB_PER_CHUNK) == 0)
+              mbar_wait(ready_bar(kb / KB_PER_CHUNK), (uint32_t)((t - 1) & 1));  // columns written by epilogue(t-1)
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+            mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+            tma_load_2d(sa, &map_xh, kb * TC_BK, arow, full_bar(stage));
+            tma_load_2d(sa + TC_A_BYTES, &map_xl, kb * TC_BK, arow, full_bar(stage));
+            tma_load_2d(sa + 2 * TC_A_BYTES, &map_qh, kb * TC_BK, nc * TC_BN, full_bar(stage));
+            tma_load_2d(sa + 2 * TC_A_BYTES + TC_B_BYTES, &map_ql, kb * TC_BK, nc * TC_BN, full_bar(stage));
+            if (++stage == TC_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                 ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;  // global chunk counter
+      for (int t = 0; t < T; ++t) {
+        for (int nc = 0; nc < NC; ++nc, ++it) {
+          const uint32_t ab = it & 1u;
+          mbar_wait(acce_bar(ab), ((it >> 1) & 1u) ^ 1u);  // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ab * TC_BN;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              const uint64_t a_hi = umma_desc_sw64(sa + ks * 32);
+              const uint64_t a_lo = umma_desc_sw64(sa + TC_A_BYTES + ks * 32);
+              const uint64_t b_hi = umma_desc_sw64(sa + 2 * TC_A_BYTES + ks * 32);
+              const uint64_t b_lo = umma_desc_sw64(sa + 2 * TC_A_BYTES + TC_B_BYTES + ks * 32);
+              umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first
+              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+            umma_commit(empty_bar(stage));  // frees the stage once these MMAs have read it
+            if (++stage == TC_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit(accf_bar(ab));  // accumulator complete
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue (warps 0-7)
+    const int r = (warp & 3) * 32 + lane;        // accumulator row == TMEM lane
+    const int colhalf = warp >> 2;               // which 128 columns of the 256-column chunk
+    const int row = row0 + r;
+    const long long b = K == 2 ? (row >> 1) : row;  // trajectory of this row
+    const uint32_t qi = K == 2 ? (uint32_t)(row & 1) : 0u;
+    const bool row_ok = row < tc.rows;
+    const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float4* sched4 = reinterpret_cast<const float4*>(p.sched);
+    uint32_t it = 0;
+    for (int t = 0; t < T; ++t) {
+      const float4 ca = __ldg(sched4 + 2 * t), cb = __ldg(sched4 + 2 * t + 1);
+      const float next_a = (t + 1 < T) ? __ldg(p.sched + (size_t)(t + 1) * SCHED_W + SC_A) : 0.f;
+      const bool last = t + 1 == T;
+      const float* xh_cur = tc.xh + (size_t)(t & 1) * plane + (size_t)row * NP;
+      const float* xl_cur = tc.xl + (size_t)(t & 1) * plane + (size_t)row * NP;
+      float* xh_nxt = tc.xh + (size_t)((t + 1) & 1) * plane + (size_t)row * NP;
+      float* xl_nxt = tc.xl + (size_t)((t + 1) & 1) * plane + (size_t)row * NP;
+      for (int nc = 0; nc < NC; ++nc, ++it) {
+        const uint32_t ab = it & 1u;
+        mbar_wait(accf_bar(ab), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tcol = tlane + ab * TC_BN + colhalf * (TC_BN / 2);
+#pragma unroll 1
+        for (int piece = 0; piece < TC_BN / 2 / 16; ++piece) {
+          const int j0 = nc * TC_BN + colhalf * (TC_BN / 2) + piece * 16;
+          float G[16];
+          tmem_ld16(tcol + piece * 16, G);
+          // old contraction input of this row (exact FP32 value = hi + lo)
+          float x[16];
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const float4 h4 = *reinterpret_cast<const float4*>(xh_cur + j0 + 4 * v4);
+            const float4 l4 = *reinterpret_cast<const float4*>(xl_cur + j0 + 4 * v4);
+            x[4 * v4 + 0] = h4.x + l4.x;
+            x[4 * v4 + 1] = h4.y + l4.y;
+            x[4 * v4 + 2] = h4.z + l4.z;
+            x[4 * v4 + 3] = h4.w + l4.w;
+          }
+          float W[16];
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            float w4[4];
+            tc_noise4(p, K, b, qi, t, j0 + 4 * v4, w4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) W[4 * v4 + i] = w4[i];
+          }
+          tmem_wait_ld();
+          if (piece == TC_BN / 2 / 16 - 1) {
+            // last read of this accumulator: hand it back to the MMA issuer
+            tc_fence_before();
+            mbar_arrive(acce_bar(ab));
+          }
+          float xn[16];  // next contraction input
+          if constexpr (SOLVER == SOLVER_DL) {
+            float* am = tc.aux + (size_t)row * NP + j0;
+            float* av = tc.aux + plane + (size_t)row * NP + j0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float g = G[i] + hs[j0 + i];
+              if constexpr (ADAM) {
+                float m = am[i], v = av[i];
+                g = tc_adam(g, m, v, p, cb.y, cb.z);
+                am[i] = m;
+                av[i] = v;
+              }
+              const float other = __shfl_xor_sync(0xffffffffu, x[i], 1);
+              const float c = qi ? other : x[i], s = qi ? x[i] : other;
+              const float r2 = fmaf(c, c, s * s);
+              const float rt = fast_sqrt(r2 + 0.5f);
+              const float u = fmaf(r2, -p.dt, qi ? ca.z : ca.y);
+              const float nz = (rt * (qi ? cb.x : ca.w)) * W[i];
+              xn[i] = x[i] + fmaf(x[i], u, fmaf(ca.x, g, nz));
+            }
+            if (last && row_ok) {
+              float* dst = (qi ? p.out1 : p.out0) + (size_t)b * p.n;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (j0 + i < p.n) dst[j0 + i] = qi ? xn[i] : clampf(xn[i], -ss[j0 + i], ss[j0 + i]);
+            }
+          } else if constexpr (SOLVER == SOLVER_MF) {
+            float* mu_p = tc.aux + (size_t)row * NP + j0;
+            float* sg_p = tc.aux + plane + (size_t)row * NP + j0;
+            float* am = tc.aux + (size_t)AUX_ADAM * plane + (size_t)row * NP + j0;
+            float* av = tc.aux + (size_t)(AUX_ADAM + 1) * plane + (size_t)row * NP + j0;
+            float mun[16], sgn[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float g = p.fs * (G[i] + hs[j0 + i]);
+              if constexpr (ADAM) {
+                float m = am[i], v = av[i];
+                g = tc_adam(g, m, v, p, cb.y, cb.z);
+                am[i] = m;
+                av[i] = v;
+              }
+              const float mu = mu_p[i], sg = sg_p[i];
+              const float g2m2 = (mu * mu) * p.g2;
+              const float a1 = fmaf(g2m2, -1.f, ca.y);
+              const float sh = sg + (-0.5f);
+              const float dmu = fmaf(a1, mu, g);
+              const float diff = (sh * ca.w) * W[i];
+              mun[i] = fmaf(p.dt, dmu + diff, mu);
+              const float a3 = fmaf(g2m2, -3.f, ca.y);
+              const float t1 = (a3 * sg) * 2.f;
+              const float t2 = (sh * sh) * (-2.f * ca.z);
+              const float t3 = fmaf(g2m2, 2.f, cb.x);
+              sgn[i] = fmaf(p.dt, (t1 + t2) + t3, sg);
+              mu_p[i] = mun[i];
+              sg_p[i] = sgn[i];
+            }
+            if (!last) {
+              // measurement of iteration t+1 (mf_solver.py:551-554) is the next contraction input
+#pragma unroll
+              for (int v4 = 0; v4 < 4; ++v4) {
+                float w4[4];
+                tc_noise4(p, K, b, 0u, t + 1, j0 + 4 * v4, w4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int jj = 4 * v4 + i;
+                  xn[jj] = clampf(fmaf(next_a, w4[i], mun[jj]), -ss[j0 + jj], ss[j0 + jj]);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xn[i] = x[i];
+              if (row_ok) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (j0 + i < p.n) {
+                    const size_t o = (size_t)b * p.n + j0 + i;
+                    p.out0[o] = mun[i];
+                    p.out1[o] = x[i];  // the clamped measurement of the LAST iteration (mf_solver.py:591)
+                    p.out2[o] = sgn[i];
+                  }
+              }
+            }
+          } else {
+            float* am = tc.aux + (size_t)row * NP + j0;
+            float* av = tc.aux + plane + (size_t)row * NP + j0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float g = G[i] + hs[j0 + i];
+              if constexpr (ADAM) {
+                float m = am[i], v = av[i];
+                g = tc_adam(g, m, v, p, cb.y, cb.z);
+                am[i] = m;
+                av[i] = v;
+              }
+              const float c = x[i];
+              float inc = fmaf(p.dtfs, g, p.sig * W[i]);
+              if constexpr (SOLVER == SOLVER_PLV) inc = fmaf(c, fmaf(c * c, -p.dt, ca.y), inc);
+              xn[i] = clampf(c + inc, -ss[j0 + i], ss[j0 + i]);
+            }
+            if (last && row_ok) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (j0 + i < p.n) p.out0[(size_t)b * p.n + j0 + i] = xn[i];
+            }
+          }
+          // publish the next contraction input as exact (hi, lo) summands
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            float4 h4, l4;
+            h4.x = tf32_rna(xn[4 * v4 + 0]);
+            h4.y = tf32_rna(xn[4 * v4 + 1]);
+            h4.z = tf32_rna(xn[4 * v4 + 2]);
+            h4.w = tf32_rna(xn[4 * v4 + 3]);
+            l4.x = xn[4 * v4 + 0] - h4.x;
+            l4.y = xn[4 * v4 + 1] - h4.y;
+            l4.z = xn[4 * v4 + 2] - h4.z;
+            l4.w = xn[4 * v4 + 3] - h4.w;
+            *reinterpret_cast<float4*>(xh_nxt + j0 + 4 * v4) = h4;
+            *reinterpret_cast<float4*>(xl_nxt + j0 + 4 * v4) = l4;
+          }
+        }
+        // the chunk's columns of the next state are written: make them visible to the TMA
+        // engine (async proxy) and let the producer fetch them for iteration t+1
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+        mbar_arrive(ready_bar(nc));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_free(tmem_base, 512);
+}
+
+}  // namespace ccvm

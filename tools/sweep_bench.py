@@ -56,7 +56,7 @@ def main():
         for i in range(len(specs)):      # build this rank's instances outside the timed region
             if i % world == rank:
                 get(i)
-        sweep.solve_sweep(solver, (min(len(specs), 2 * world), get), post_processor=pp, chunk=args.chunk)  # warm-up
+        sweep.solve_sweep(solver, (len(specs), get), post_processor=pp, chunk=args.chunk)  # warm-up (also sizes the allocator caches)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
