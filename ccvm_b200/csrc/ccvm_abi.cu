@@ -205,7 +205,10 @@ enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2, PATH_TC = 3 };
 static bool tc_eligible(const ccvm_solve_desc& d) {
   if (d.n > TC_MAX_CHUNKS * TC_BN || d.evolution_step > 0) return false;
   const long long rows = (long long)d.batch * (d.solver == CCVM_SOLVER_DL ? 2 : 1);
-  if (const char* e = getenv("CCVM_TC")) return atoi(e) != 0;
+  if (const char* e = getenv("CCVM_TC")) {
+    if (e[0] == 'a') return d.n >= 256 && rows >= 1024;  // "auto"
+    return atoi(e) != 0;  // 0: never, 1 / 2: always (1 = single-CTA kernel, 2 = CTA-pair kernel)
+  }
   return d.n >= 256 && rows >= 1024;
 }
 
@@ -335,46 +338,69 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// fp32 [rows][cols] row-major, box = box_rows x 16 floats (one SWIZZLE_64B row)
-static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// fp32 [rows][cols] row-major; box = box_rows x box_cols with box_cols * 4 bytes == the swizzle span
+static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                       uint32_t box_cols) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(CCVM_E_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CCVM_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return CCVM_OK;
 }
 
 struct TcPlan {
+  int version;  // 1: single-CTA kernel (sde_tc_kernel), 2: CTA-pair kernel (sde_tc2_kernel)
   int np, rows, rows_p, n_aux, ctas;
   size_t smem;
 };
 
+static int tc_version() {
+  if (const char* e = getenv("CCVM_TC")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2) return v;
+  }
+  return 2;
+}
+
 static void plan_tc(const ccvm_solve_desc& d, TcPlan& P) {
   const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1;
+  P.version = tc_version();
+  const int row_block = P.version == 2 ? 2 * TC_BM : TC_BM;
   P.np = ((d.n + TC_BN - 1) / TC_BN) * TC_BN;
   P.rows = K * d.batch;
-  P.rows_p = ((P.rows + TC_BM - 1) / TC_BM) * TC_BM;
+  P.rows_p = ((P.rows + row_block - 1) / row_block) * row_block;
   const bool adam = d.algorithm == CCVM_ALG_ADAM;
   P.n_aux = (d.solver == CCVM_SOLVER_MF ? 2 : 0) + (adam ? 2 : 0);
   P.ctas = P.rows_p / TC_BM;
-  P.smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)2 * P.np * sizeof(float);
+  P.smem = P.version == 2 ? (size_t)T2_SMEM_BYTES
+                          : 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)2 * P.np * sizeof(float);
 }
 
+struct TcMaps {
+  CUtensorMap xh, xl, qh, ql, oh, ol;
+};
+
 template <int SOLVER, bool ADAM>
-static int launch_tc(const SdeParams& p, const TcParams& tc, const TcPlan& P, const CUtensorMap& mxh,
-                     const CUtensorMap& mxl, const CUtensorMap& mqh, const CUtensorMap& mql, cudaStream_t st) {
+static int launch_tc(const SdeParams& p, const TcParams& tc, const TcPlan& P, const TcMaps& M, cudaStream_t st) {
   const size_t plane = (size_t)tc.rows_p * tc.np;
   tc_init_state_kernel<SOLVER><<<(unsigned)((plane / 4 + 255) / 256), 256, 0, st>>>(p, tc, P.n_aux);
   CUDA_TRY(cudaGetLastError());
-  auto kern = sde_tc_kernel<SOLVER, ADAM>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-  kern<<<P.ctas, TC_THREADS, P.smem, st>>>(p, tc, mxh, mxl, mqh, mql);
+  if (P.version == 2) {
+    auto kern = sde_tc2_kernel<SOLVER, ADAM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    kern<<<P.ctas, TC_THREADS, P.smem, st>>>(p, tc, M.xh, M.xl, M.qh, M.ql, M.oh, M.ol);
+  } else {
+    auto kern = sde_tc_kernel<SOLVER, ADAM>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    kern<<<P.ctas, TC_THREADS, P.smem, st>>>(p, tc, M.xh, M.xl, M.qh, M.ql);
+  }
   CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
 }
@@ -382,7 +408,9 @@ static int launch_tc(const SdeParams& p, const TcParams& tc, const TcPlan& P, co
 template <int SOLVER, bool ADAM>
 static int regs_tc() {
   cudaFuncAttributes fa;
-  return cudaFuncGetAttributes(&fa, sde_tc_kernel<SOLVER, ADAM>) == cudaSuccess ? fa.numRegs : -1;
+  const cudaError_t e = tc_version() == 2 ? cudaFuncGetAttributes(&fa, sde_tc2_kernel<SOLVER, ADAM>)
+                                          : cudaFuncGetAttributes(&fa, sde_tc_kernel<SOLVER, ADAM>);
+  return e == cudaSuccess ? fa.numRegs : -1;
 }
 
 // `p` carries everything but the launch geometry; sched is already being built on `st`
@@ -410,22 +438,31 @@ static int solve_tc(const ccvm_solve_desc* d, SdeParams& p, cudaStream_t st) {
                                             p.b_half, p.n, P.np, qt_hi, qt_lo, hvec, svec);
   int rc = CCVM_OK;
   if (cudaGetLastError() != cudaSuccess) rc = fail(CCVM_E_CUDA, "tc_prepare_q_kernel launch failed");
-  CUtensorMap mxh, mxl, mqh, mql;
-  if (!rc) rc = make_map_2d(&mxh, tc.xh, 2ull * P.rows_p, P.np, TC_BM);
-  if (!rc) rc = make_map_2d(&mxl, tc.xl, 2ull * P.rows_p, P.np, TC_BM);
-  if (!rc) rc = make_map_2d(&mqh, qt_hi, P.np, P.np, TC_BN);
-  if (!rc) rc = make_map_2d(&mql, qt_lo, P.np, P.np, TC_BN);
+  TcMaps M;
+  if (P.version == 2) {
+    if (!rc) rc = make_map_2d(&M.xh, tc.xh, 2ull * P.rows_p, P.np, TC_BM, T2_BK);
+    if (!rc) rc = make_map_2d(&M.xl, tc.xl, 2ull * P.rows_p, P.np, TC_BM, T2_BK);
+    if (!rc) rc = make_map_2d(&M.qh, qt_hi, P.np, P.np, TC_BM, T2_BK);
+    if (!rc) rc = make_map_2d(&M.ql, qt_lo, P.np, P.np, TC_BM, T2_BK);
+    if (!rc) rc = make_map_2d(&M.oh, tc.xh, 2ull * P.rows_p, P.np, TC_BM, 16);
+    if (!rc) rc = make_map_2d(&M.ol, tc.xl, 2ull * P.rows_p, P.np, TC_BM, 16);
+  } else {
+    if (!rc) rc = make_map_2d(&M.xh, tc.xh, 2ull * P.rows_p, P.np, TC_BM, TC_BK);
+    if (!rc) rc = make_map_2d(&M.xl, tc.xl, 2ull * P.rows_p, P.np, TC_BM, TC_BK);
+    if (!rc) rc = make_map_2d(&M.qh, qt_hi, P.np, P.np, TC_BN, TC_BK);
+    if (!rc) rc = make_map_2d(&M.ql, qt_lo, P.np, P.np, TC_BN, TC_BK);
+  }
   if (!rc) {
     const bool adam = d->algorithm == CCVM_ALG_ADAM;
     switch (d->solver * 2 + (adam ? 1 : 0)) {
-      case 0: rc = launch_tc<SOLVER_DL, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
-      case 1: rc = launch_tc<SOLVER_DL, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
-      case 2: rc = launch_tc<SOLVER_MF, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
-      case 3: rc = launch_tc<SOLVER_MF, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
-      case 4: rc = launch_tc<SOLVER_LV, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
-      case 5: rc = launch_tc<SOLVER_LV, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
-      case 6: rc = launch_tc<SOLVER_PLV, false>(p, tc, P, mxh, mxl, mqh, mql, st); break;
-      default: rc = launch_tc<SOLVER_PLV, true>(p, tc, P, mxh, mxl, mqh, mql, st); break;
+      case 0: rc = launch_tc<SOLVER_DL, false>(p, tc, P, M, st); break;
+      case 1: rc = launch_tc<SOLVER_DL, true>(p, tc, P, M, st); break;
+      case 2: rc = launch_tc<SOLVER_MF, false>(p, tc, P, M, st); break;
+      case 3: rc = launch_tc<SOLVER_MF, true>(p, tc, P, M, st); break;
+      case 4: rc = launch_tc<SOLVER_LV, false>(p, tc, P, M, st); break;
+      case 5: rc = launch_tc<SOLVER_LV, true>(p, tc, P, M, st); break;
+      case 6: rc = launch_tc<SOLVER_PLV, false>(p, tc, P, M, st); break;
+      default: rc = launch_tc<SOLVER_PLV, true>(p, tc, P, M, st); break;
     }
   }
   cudaFreeAsync(scratch, st);

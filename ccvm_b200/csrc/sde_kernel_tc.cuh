@@ -223,6 +223,23 @@ __global__ void tc_init_state_kernel(const SdeParams p, const TcParams tc, int n
   }
 }
 
+// 16 consecutive floats of a row-private array, as four 128-bit accesses
+__device__ __forceinline__ void tc_ld16(const float* src, float (&r)[16]) {
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4) {
+    const float4 t = *reinterpret_cast<const float4*>(src + 4 * v4);
+    r[4 * v4 + 0] = t.x;
+    r[4 * v4 + 1] = t.y;
+    r[4 * v4 + 2] = t.z;
+    r[4 * v4 + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void tc_st16(float* dst, const float (&r)[16]) {
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4)
+    *reinterpret_cast<float4*>(dst + 4 * v4) = make_float4(r[4 * v4], r[4 * v4 + 1], r[4 * v4 + 2], r[4 * v4 + 3]);
+}
+
 // Adam transform of one gradient element (dl_solver.py:699-727 and siblings), scalar form of adam_tile4
 __device__ __forceinline__ float tc_adam(float g, float& m, float& v, const SdeParams& p, float ib1, float ib2) {
   m = fmaf(m, p.beta1, g * p.omb1);
@@ -238,6 +255,139 @@ __device__ __forceinline__ float tc_adam(float g, float& m, float& v, const SdeP
   return p.add_assign ? g + upd : upd;
 }
 
+// The solver's SDE step on 16 consecutive columns j0..j0+15 of one contraction row: G is the raw
+// contraction x.Qs, x the old contraction input, W the noise of iteration t; xn receives the next
+// contraction input.  In-place FP32 state (MF mu / sigma, Adam moments) lives in tc.aux and is only
+// ever touched by the thread that owns the row.  Writes the solver outputs on the last iteration.
+template <int SOLVER, bool ADAM>
+__device__ __forceinline__ void tc_update16(const SdeParams& p, const TcParams& tc, size_t plane, int row, long long b,
+                                            uint32_t qi, bool row_ok, int t, bool last, const float4 ca,
+                                            const float4 cb, float next_a, int j0, const float (&G)[16],
+                                            const float (&x)[16], const float (&W)[16], const float* hs,
+                                            const float* ss, float (&xn)[16]) {
+  constexpr int K = SolverTraits<SOLVER>::K;
+  constexpr int AUX_ADAM = SOLVER == SOLVER_MF ? 2 : 0;  // first Adam array (after mu, sigma)
+  const int NP = tc.np;
+  if constexpr (SOLVER == SOLVER_DL) {
+    float* am = tc.aux + (size_t)row * NP + j0;
+    float* av = tc.aux + plane + (size_t)row * NP + j0;
+    float m16[16], v16[16];
+    if constexpr (ADAM) {
+      tc_ld16(am, m16);
+      tc_ld16(av, v16);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float g = G[i] + hs[j0 + i];
+      if constexpr (ADAM) g = tc_adam(g, m16[i], v16[i], p, cb.y, cb.z);
+      const float other = __shfl_xor_sync(0xffffffffu, x[i], 1);
+      const float c = qi ? other : x[i], s = qi ? x[i] : other;
+      const float r2 = fmaf(c, c, s * s);
+      const float rt = fast_sqrt(r2 + 0.5f);
+      const float u = fmaf(r2, -p.dt, qi ? ca.z : ca.y);
+      const float nz = (rt * (qi ? cb.x : ca.w)) * W[i];
+      xn[i] = x[i] + fmaf(x[i], u, fmaf(ca.x, g, nz));
+    }
+    if constexpr (ADAM) {
+      tc_st16(am, m16);
+      tc_st16(av, v16);
+    }
+    if (last && row_ok) {
+      float* dst = (qi ? p.out1 : p.out0) + (size_t)b * p.n;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (j0 + i < p.n) dst[j0 + i] = qi ? xn[i] : clampf(xn[i], -ss[j0 + i], ss[j0 + i]);
+    }
+  } else if constexpr (SOLVER == SOLVER_MF) {
+    float* mu_p = tc.aux + (size_t)row * NP + j0;
+    float* sg_p = tc.aux + plane + (size_t)row * NP + j0;
+    float* am = tc.aux + (size_t)AUX_ADAM * plane + (size_t)row * NP + j0;
+    float* av = tc.aux + (size_t)(AUX_ADAM + 1) * plane + (size_t)row * NP + j0;
+    float mun[16], sgn[16], m16[16], v16[16];
+    tc_ld16(mu_p, mun);
+    tc_ld16(sg_p, sgn);
+    if constexpr (ADAM) {
+      tc_ld16(am, m16);
+      tc_ld16(av, v16);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float g = p.fs * (G[i] + hs[j0 + i]);
+      if constexpr (ADAM) g = tc_adam(g, m16[i], v16[i], p, cb.y, cb.z);
+      const float mu = mun[i], sg = sgn[i];
+      const float g2m2 = (mu * mu) * p.g2;
+      const float a1 = fmaf(g2m2, -1.f, ca.y);
+      const float sh = sg + (-0.5f);
+      const float dmu = fmaf(a1, mu, g);
+      const float diff = (sh * ca.w) * W[i];
+      mun[i] = fmaf(p.dt, dmu + diff, mu);
+      const float a3 = fmaf(g2m2, -3.f, ca.y);
+      const float t1 = (a3 * sg) * 2.f;
+      const float t2 = (sh * sh) * (-2.f * ca.z);
+      const float t3 = fmaf(g2m2, 2.f, cb.x);
+      sgn[i] = fmaf(p.dt, (t1 + t2) + t3, sg);
+    }
+    tc_st16(mu_p, mun);
+    tc_st16(sg_p, sgn);
+    if constexpr (ADAM) {
+      tc_st16(am, m16);
+      tc_st16(av, v16);
+    }
+    if (!last) {
+      // measurement of iteration t+1 (mf_solver.py:551-554) is the next contraction input
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        float w4[4];
+        tc_noise4(p, K, b, 0u, t + 1, j0 + 4 * v4, w4);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int jj = 4 * v4 + i;
+          xn[jj] = clampf(fmaf(next_a, w4[i], mun[jj]), -ss[j0 + jj], ss[j0 + jj]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) xn[i] = x[i];
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (j0 + i < p.n) {
+            const size_t o = (size_t)b * p.n + j0 + i;
+            p.out0[o] = mun[i];
+            p.out1[o] = x[i];  // the clamped measurement of the LAST iteration (mf_solver.py:591)
+            p.out2[o] = sgn[i];
+          }
+      }
+    }
+  } else {
+    float* am = tc.aux + (size_t)row * NP + j0;
+    float* av = tc.aux + plane + (size_t)row * NP + j0;
+    float m16[16], v16[16];
+    if constexpr (ADAM) {
+      tc_ld16(am, m16);
+      tc_ld16(av, v16);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float g = G[i] + hs[j0 + i];
+      if constexpr (ADAM) g = tc_adam(g, m16[i], v16[i], p, cb.y, cb.z);
+      const float c = x[i];
+      float inc = fmaf(p.dtfs, g, p.sig * W[i]);
+      if constexpr (SOLVER == SOLVER_PLV) inc = fmaf(c, fmaf(c * c, -p.dt, ca.y), inc);
+      xn[i] = clampf(c + inc, -ss[j0 + i], ss[j0 + i]);
+    }
+    if constexpr (ADAM) {
+      tc_st16(am, m16);
+      tc_st16(av, v16);
+    }
+    if (last && row_ok) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (j0 + i < p.n) p.out0[(size_t)b * p.n + j0 + i] = xn[i];
+    }
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int SOLVER, bool ADAM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -245,7 +395,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                   const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_qh,
                   const __grid_constant__ CUtensorMap map_ql) {
   constexpr int K = SolverTraits<SOLVER>::K;
-  constexpr int AUX_ADAM = SOLVER == SOLVER_MF ? 2 : 0;  // first Adam array (after mu, sigma)
 
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   __shared__ __align__(8) unsigned long long bars[2 * TC_STAGES + 4 + TC_MAX_CHUNKS];
@@ -414,111 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             mbar_arrive(acce_bar(ab));
           }
           float xn[16];  // next contraction input
-          if constexpr (SOLVER == SOLVER_DL) {
-            float* am = tc.aux + (size_t)row * NP + j0;
-            float* av = tc.aux + plane + (size_t)row * NP + j0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float g = G[i] + hs[j0 + i];
-              if constexpr (ADAM) {
-                float m = am[i], v = av[i];
-                g = tc_adam(g, m, v, p, cb.y, cb.z);
-                am[i] = m;
-                av[i] = v;
-              }
-              const float other = __shfl_xor_sync(0xffffffffu, x[i], 1);
-              const float c = qi ? other : x[i], s = qi ? x[i] : other;
-              const float r2 = fmaf(c, c, s * s);
-              const float rt = fast_sqrt(r2 + 0.5f);
-              const float u = fmaf(r2, -p.dt, qi ? ca.z : ca.y);
-              const float nz = (rt * (qi ? cb.x : ca.w)) * W[i];
-              xn[i] = x[i] + fmaf(x[i], u, fmaf(ca.x, g, nz));
-            }
-            if (last && row_ok) {
-              float* dst = (qi ? p.out1 : p.out0) + (size_t)b * p.n;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (j0 + i < p.n) dst[j0 + i] = qi ? xn[i] : clampf(xn[i], -ss[j0 + i], ss[j0 + i]);
-            }
-          } else if constexpr (SOLVER == SOLVER_MF) {
-            float* mu_p = tc.aux + (size_t)row * NP + j0;
-            float* sg_p = tc.aux + plane + (size_t)row * NP + j0;
-            float* am = tc.aux + (size_t)AUX_ADAM * plane + (size_t)row * NP + j0;
-            float* av = tc.aux + (size_t)(AUX_ADAM + 1) * plane + (size_t)row * NP + j0;
-            float mun[16], sgn[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float g = p.fs * (G[i] + hs[j0 + i]);
-              if constexpr (ADAM) {
-                float m = am[i], v = av[i];
-                g = tc_adam(g, m, v, p, cb.y, cb.z);
-                am[i] = m;
-                av[i] = v;
-              }
-              const float mu = mu_p[i], sg = sg_p[i];
-              const float g2m2 = (mu * mu) * p.g2;
-              const float a1 = fmaf(g2m2, -1.f, ca.y);
-              const float sh = sg + (-0.5f);
-              const float dmu = fmaf(a1, mu, g);
-              const float diff = (sh * ca.w) * W[i];
-              mun[i] = fmaf(p.dt, dmu + diff, mu);
-              const float a3 = fmaf(g2m2, -3.f, ca.y);
-              const float t1 = (a3 * sg) * 2.f;
-              const float t2 = (sh * sh) * (-2.f * ca.z);
-              const float t3 = fmaf(g2m2, 2.f, cb.x);
-              sgn[i] = fmaf(p.dt, (t1 + t2) + t3, sg);
-              mu_p[i] = mun[i];
-              sg_p[i] = sgn[i];
-            }
-            if (!last) {
-              // measurement of iteration t+1 (mf_solver.py:551-554) is the next contraction input
-#pragma unroll
-              for (int v4 = 0; v4 < 4; ++v4) {
-                float w4[4];
-                tc_noise4(p, K, b, 0u, t + 1, j0 + 4 * v4, w4);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int jj = 4 * v4 + i;
-                  xn[jj] = clampf(fmaf(next_a, w4[i], mun[jj]), -ss[j0 + jj], ss[j0 + jj]);
-                }
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) xn[i] = x[i];
-              if (row_ok) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (j0 + i < p.n) {
-                    const size_t o = (size_t)b * p.n + j0 + i;
-                    p.out0[o] = mun[i];
-                    p.out1[o] = x[i];  // the clamped measurement of the LAST iteration (mf_solver.py:591)
-                    p.out2[o] = sgn[i];
-                  }
-              }
-            }
-          } else {
-            float* am = tc.aux + (size_t)row * NP + j0;
-            float* av = tc.aux + plane + (size_t)row * NP + j0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float g = G[i] + hs[j0 + i];
-              if constexpr (ADAM) {
-                float m = am[i], v = av[i];
-                g = tc_adam(g, m, v, p, cb.y, cb.z);
-                am[i] = m;
-                av[i] = v;
-              }
-              const float c = x[i];
-              float inc = fmaf(p.dtfs, g, p.sig * W[i]);
-              if constexpr (SOLVER == SOLVER_PLV) inc = fmaf(c, fmaf(c * c, -p.dt, ca.y), inc);
-              xn[i] = clampf(c + inc, -ss[j0 + i], ss[j0 + i]);
-            }
-            if (last && row_ok) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (j0 + i < p.n) p.out0[(size_t)b * p.n + j0 + i] = xn[i];
-            }
-          }
+          tc_update16<SOLVER, ADAM>(p, tc, plane, row, b, qi, row_ok, t, last, ca, cb, next_a, j0, G, x, W, hs, ss, xn);
           // publish the next contraction input as exact (hi, lo) summands
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) {
@@ -547,6 +592,304 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   tc_fence_before();
   __syncthreads();
   if (warp == 9) tmem_free(tmem_base, 512);
+}
+
+// =====================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster share every MMA.  Per pair and stage the
+// accumulator tile is 256 rows x 256 columns: each CTA stages ITS 128 state rows (hi, lo) and ITS
+// 128-row half of the Qs^T tile, the leader issues one tcgen05.mma.cta_group::2 (M = 256) that reads
+// both halves, and each CTA's TMEM receives its own 128 accumulator rows.  Compared with the
+// single-CTA kernel above (profiles/r1_ncu_sde_tc_v1.txt: L1->XBAR request port 76-89 % busy, tensor
+// pipe 41 %) this
+//   * halves the Qs^T bytes every SM pulls from L2 and the shared-memory bandwidth the MMAs need;
+//   * moves 32-wide k-blocks (128 B rows, SWIZZLE_128B): half the TMA requests per byte;
+//   * stores the new state through a swizzled shared-memory tile and TMA (full 64 B rows instead
+//     of 16 B pieces of 32 B sectors) and reads the old state with 256-bit L1-bypassing loads.
+constexpr int T2_BK = 32;                                // floats per k-block (128 B)
+constexpr int T2_STAGES = 3;
+constexpr int T2_TILE_BYTES = TC_BM * T2_BK * 4;          // 16 KB: 128 rows x 32 floats
+constexpr int T2_STAGE_BYTES = 4 * T2_TILE_BYTES;         // A hi, A lo, B-half hi, B-half lo
+constexpr int T2_OUT_TILE_BYTES = TC_BM * 16 * 4;         // 8 KB: 128 rows x 16 floats (SWIZZLE_64B)
+constexpr int T2_SMEM_BYTES = 1024 + T2_STAGES * T2_STAGE_BYTES + 4 * T2_OUT_TILE_BYTES;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier of the pair's LEADER CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                                 uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// K-major, SWIZZLE_128B, rows of 128 B, 8-row atoms of 1024 B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void ld_cg_256(const float* src, float* r) {
+  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(src)
+               : "memory");
+}
+
+template <int SOLVER, bool ADAM>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    sde_tc2_kernel(const SdeParams p, const TcParams tc, const __grid_constant__ CUtensorMap map_xh,
+                   const __grid_constant__ CUtensorMap map_xl, const __grid_constant__ CUtensorMap map_qh,
+                   const __grid_constant__ CUtensorMap map_ql, const __grid_constant__ CUtensorMap map_oh,
+                   const __grid_constant__ CUtensorMap map_ol) {
+  constexpr int K = SolverTraits<SOLVER>::K;
+  constexpr int PIECES = TC_BN / 2 / 16;  // 16-column pieces per epilogue warpgroup and chunk
+
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  __shared__ __align__(8) unsigned long long bars[2 * T2_STAGES + 4 + TC_MAX_CHUNKS];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int NP = tc.np, T = p.iterations;
+  const int NC = NP / TC_BN;
+  const int KB = NP / T2_BK;
+  constexpr int KB_PER_CHUNK = TC_BN / T2_BK;
+  const int row0 = blockIdx.x * TC_BM;
+  const size_t plane = (size_t)tc.rows_p * NP;
+
+  const uint32_t smem_base = (smem_u32(tc_smem) + 1023u) & ~1023u;
+  const uint32_t out_base = smem_base + T2_STAGES * T2_STAGE_BYTES;  // [warpgroup][hi | lo] staging tiles
+
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (T2_STAGES + s); };
+  auto accf_bar = [&](int a) { return bar0 + 8u * (2 * T2_STAGES + a); };
+  auto acce_bar = [&](int a) { return bar0 + 8u * (2 * T2_STAGES + 2 + a); };
+  auto ready_bar = [&](int c) { return bar0 + 8u * (2 * T2_STAGES + 4 + c); };
+
+  if (tid == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);    // used in the leader: its producer's expect_tx + both CTAs' bytes
+      mbar_init(empty_bar(s), 1);   // multicast commit of the leader's MMA thread
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(accf_bar(a), 1);                      // multicast commit
+      mbar_init(acce_bar(a), 2 * TC_EPI_WARPS * 32);  // used in the leader: both CTAs' epilogue threads
+    }
+    for (int c = 0; c < TC_MAX_CHUNKS; ++c) mbar_init(ready_bar(c), 2);  // one elected thread per warpgroup
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 8) {
+    // ============================================================ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < T; ++t) {
+        const int arow = (t & 1) * tc.rows_p + row0;
+        for (int nc = 0; nc < NC; ++nc) {
+          const int brow = nc * TC_BN + (int)rank * TC_BM;  // this CTA's half of the Qs^T tile
+          for (int kb = 0; kb < KB; ++kb) {
+            if (t > 0 && nc == 0 && (kb % KB_PER_CHUNK) == 0)
+              mbar_wait(ready_bar(kb / KB_PER_CHUNK), (uint32_t)((t - 1) & 1));
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
+            const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * T2_STAGE_BYTES);
+            tma_load_2d_pair(sa, &map_xh, kb * T2_BK, arow, lbar);
+            tma_load_2d_pair(sa + T2_TILE_BYTES, &map_xl, kb * T2_BK, arow, lbar);
+            tma_load_2d_pair(sa + 2 * T2_TILE_BYTES, &map_qh, kb * T2_BK, brow, lbar);
+            tma_load_2d_pair(sa + 3 * T2_TILE_BYTES, &map_ql, kb * T2_BK, brow, lbar);
+            if (++stage == T2_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ============================================================ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      // D = F32, A = B = TF32, K-major, N = 256, M = 256 (128 rows per CTA)
+      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                 ((uint32_t)((2 * TC_BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t it = 0;
+      for (int t = 0; t < T; ++t) {
+        for (int nc = 0; nc < NC; ++nc, ++it) {
+          const uint32_t ab = it & 1u;
+          mbar_wait(acce_bar(ab), ((it >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ab * TC_BN;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < T2_BK / 8; ++ks) {
+              const uint64_t a_hi = umma_desc_sw128(sa + ks * 32);
+              const uint64_t a_lo = umma_desc_sw128(sa + T2_TILE_BYTES + ks * 32);
+              const uint64_t b_hi = umma_desc_sw128(sa + 2 * T2_TILE_BYTES + ks * 32);
+              const uint64_t b_lo = umma_desc_sw128(sa + 3 * T2_TILE_BYTES + ks * 32);
+              umma_tf32_pair(d_tmem, a_lo, b_hi, idesc, (kb | ks) != 0);
+              umma_tf32_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32_pair(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+            umma_commit_pair(empty_bar(stage));
+            if (++stage == T2_STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          umma_commit_pair(accf_bar(ab));
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue (warps 0-7, both CTAs)
+    const int wg = warp >> 2;                    // warpgroup = 128-column half of the chunk
+    const int r = (warp & 3) * 32 + lane;        // accumulator row == TMEM lane
+    const int row = row0 + r;
+    const long long b = K == 2 ? (row >> 1) : row;
+    const uint32_t qi = K == 2 ? (uint32_t)(row & 1) : 0u;
+    const bool row_ok = row < tc.rows;
+    const bool elected = (tid & 127) == 0;
+    const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t out_hi = out_base + wg * 2 * T2_OUT_TILE_BYTES, out_lo = out_hi + T2_OUT_TILE_BYTES;
+    const uint32_t my_row = (uint32_t)r * 64u;
+    const uint32_t swz = ((uint32_t)r >> 1) & 3u;  // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+    const uint32_t acce_leader0 = mapa_cluster(acce_bar(0), 0), acce_leader1 = mapa_cluster(acce_bar(1), 0);
+    const float4* sched4 = reinterpret_cast<const float4*>(p.sched);
+    uint32_t it = 0;
+    for (int t = 0; t < T; ++t) {
+      const float4 ca = __ldg(sched4 + 2 * t), cb = __ldg(sched4 + 2 * t + 1);
+      const float next_a = (t + 1 < T) ? __ldg(p.sched + (size_t)(t + 1) * SCHED_W + SC_A) : 0.f;
+      const bool last = t + 1 == T;
+      const float* xh_cur = tc.xh + (size_t)(t & 1) * plane + (size_t)row * NP;
+      const float* xl_cur = tc.xl + (size_t)(t & 1) * plane + (size_t)row * NP;
+      const int nrow0 = ((t + 1) & 1) * tc.rows_p + row0;  // first row of this CTA in the next state half
+      for (int nc = 0; nc < NC; ++nc, ++it) {
+        const uint32_t ab = it & 1u;
+        mbar_wait(accf_bar(ab), (it >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tcol = tlane + ab * TC_BN + wg * (TC_BN / 2);
+#pragma unroll 1
+        for (int piece = 0; piece < PIECES; ++piece) {
+          const int j0 = nc * TC_BN + wg * (TC_BN / 2) + piece * 16;
+          float G[16];
+          tmem_ld16(tcol + piece * 16, G);
+          // old contraction input: written by TMA (async proxy, L2), so it must not be served
+          // from this SM's L1 -- 256-bit .cg loads fetch whole 32 B sectors straight from L2
+          float x[16], xl[16];
+          ld_cg_256(xh_cur + j0, x);
+          ld_cg_256(xh_cur + j0 + 8, x + 8);
+          ld_cg_256(xl_cur + j0, xl);
+          ld_cg_256(xl_cur + j0 + 8, xl + 8);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] += xl[i];
+          float W[16];
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            float w4[4];
+            tc_noise4(p, K, b, qi, t, j0 + 4 * v4, w4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) W[4 * v4 + i] = w4[i];
+          }
+          tmem_wait_ld();
+          if (piece == PIECES - 1) {
+            tc_fence_before();
+            mbar_arrive_cluster(ab ? acce_leader1 : acce_leader0);  // accumulator drained (leader's barrier)
+          }
+          float xn[16];
+          tc_update16<SOLVER, ADAM>(p, tc, plane, row, b, qi, row_ok, t, last, ca, cb, next_a, j0, G, x, W, tc.hvec,
+                                    tc.svec, xn);
+          // stage the new (hi, lo) rows in the swizzled tile and hand them to the TMA engine
+          if (elected) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous store left the tile
+          group_barrier(1 + wg, 128);
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const float h0 = tf32_rna(xn[4 * v4 + 0]), h1 = tf32_rna(xn[4 * v4 + 1]);
+            const float h2 = tf32_rna(xn[4 * v4 + 2]), h3 = tf32_rna(xn[4 * v4 + 3]);
+            const uint32_t off = my_row + (((uint32_t)v4 ^ swz) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_hi + off), "f"(h0), "f"(h1), "f"(h2),
+                         "f"(h3)
+                         : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_lo + off), "f"(xn[4 * v4 + 0] - h0),
+                         "f"(xn[4 * v4 + 1] - h1), "f"(xn[4 * v4 + 2] - h2), "f"(xn[4 * v4 + 3] - h3)
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          group_barrier(1 + wg, 128);
+          if (elected) {
+            tma_store_2d(&map_oh, j0, nrow0, out_hi);
+            tma_store_2d(&map_ol, j0, nrow0, out_lo);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (elected) {
+          // this warpgroup's half of the chunk is in global memory: the producer may fetch it
+          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+          mbar_arrive(ready_bar(nc));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 9)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
 }  // namespace ccvm
