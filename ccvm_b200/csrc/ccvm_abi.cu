@@ -298,26 +298,37 @@ __global__ void scale_q_kernel(const float* __restrict__ q, const float* __restr
   qs[idx] = val;
 }
 
-template <int SOLVER, bool ADAM>
-static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  if (P.qsrc == QSRC_TMEM) {
-    auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-    kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
-  } else {
-    auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-    kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
-  }
+// In-loop noise generation (sde_kernel_tmem.cuh, PIPE): Philox mode with enough Q chunks to hide it in.
+template <int SOLVER>
+static bool use_pipe(const SdeParams& p) {
+  if (getenv("CCVM_NO_PIPE")) return false;
+  return pipe_ok<SOLVER>(p.cg, p.noise == nullptr);
+}
+
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE>
+static int launch_tmem_variant(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
+  auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC, PIPE>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+  kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
   CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
 }
 
 template <int SOLVER, bool ADAM>
+static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
+  const bool pipe = use_pipe<SOLVER>(p);
+  if (P.qsrc == QSRC_TMEM)
+    return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true>(p, P, st)
+                : launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, false>(p, P, st);
+  return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_GMEM, true>(p, P, st)
+              : launch_tmem_variant<SOLVER, ADAM, QSRC_GMEM, false>(p, P, st);
+}
+
+template <int SOLVER, bool ADAM>
 static int regs_tmem(int qsrc) {
   cudaFuncAttributes fa;
-  cudaError_t e = qsrc == QSRC_TMEM ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM>)
-                                    : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM>);
+  cudaError_t e = qsrc == QSRC_TMEM ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM, true>)
+                                    : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM, true>);
   return e == cudaSuccess ? fa.numRegs : -1;
 }
 

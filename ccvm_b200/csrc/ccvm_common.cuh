@@ -114,6 +114,7 @@ struct SdeParams {
   float beta1, beta2, omb1, omb2, adam_alpha;  // omb = 1 - beta, rounded from fp64
   int add_assign, beta2_is_one;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
+  uint32_t pin_mask;       // always 0 (a run-time zero the compiler cannot fold; see sde_kernel_tmem.cuh, PIPE)
 };
 
 }  // namespace ccvm

@@ -101,7 +101,15 @@ __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4]
 // The body is shared by the single-problem kernel and the batched (many instances per launch)
 // kernel: `cta` is the CTA's index inside ITS problem; threads beyond ng*gt (batched launches use
 // one block size for a whole bucket of problems) only take part in the CTA-wide barriers.
-template <int SOLVER, bool ADAM, int QSRC>
+//
+// PIPE (Philox mode, CG > 4*K): the noise of an iteration does not depend on the state, so its
+// Philox rounds and Box-Muller transforms are issued INSIDE the drift contraction, one Philox call
+// (four normals) per pair of Q chunks, instead of as a separate phase after it.  The contraction
+// is a pure FFMA2 stream (every FFMA2 holds the FMA pipe for two cycles and leaves every other
+// issue slot free); the ALU / MUFU work and the dependent IMAD.WIDE chain of the generator fill
+// those slots, and the latency-bound phase between contraction and barrier shrinks to the SDE
+// update itself (profiles/r1_ncu_sde_dl_tmem_v3.txt: FMA pipe 73 % busy, 27 % bubbles, before).
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE>
 __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaunch& L, const int cta, float* smem,
                                               uint32_t* tmem_slot_p) {
   constexpr int K = SolverTraits<SOLVER>::K;
@@ -182,6 +190,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   pf2 st[2][4];             // st[0] = c | mu, st[1] = s | sigma  (x: trajectory gb0, y: gb0+1)
   pf2 am[KT][4], avv[KT][4];  // Adam moments of the tracked arrays
   pf2 W[KT][4];               // noise of the current iteration
+  pf2 Wn[KT][4];              // PIPE + MF: noise of the NEXT iteration (its measurement), drawn during the drift
   pf2 meas[4];              // MF: clamped measurement
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
@@ -193,33 +202,36 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       am[q][jj] = dup(0.f);
       avv[q][jj] = dup(0.f);
       W[q][jj] = dup(0.f);
+      Wn[q][jj] = dup(0.f);
     }
   }
 
   const uint2 key = make_uint2(p.seed_lo, p.seed_hi ^ p.off_hi);
 
+  // one Philox call: the four columns of (quadrature q, trajectory i) at iteration t
+  auto quantum = [&](pf2 (&Wd)[KT][4], int q, int i, int t) {
+    const unsigned long long gb = (unsigned long long)(p.traj_base + gb0 + i);
+    const uint32_t qi = (uint32_t)(q + half);  // which quadrature's stream
+    const uint4 r = philox4x32_10(
+        make_uint4((uint32_t)gb, (uint32_t)t, (uint32_t)cgc | (qi << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
+        key);
+    float n0, n1, n2, n3;
+    box_muller(r.x, r.y, n0, n1);
+    box_muller(r.z, r.w, n2, n3);
+    const float nn[4] = {n0, n1, n2, n3};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float w = colok[jj] ? nn[jj] : 0.f;
+      if (i) Wd[q][jj].y = w; else Wd[q][jj].x = w;
+    }
+  };
+
   auto draw = [&](int t) {
-    if (p.noise == nullptr) {
+    if (PIPE || p.noise == nullptr) {
 #pragma unroll
       for (int q = 0; q < KT; ++q)
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const unsigned long long gb = (unsigned long long)(p.traj_base + gb0 + i);
-          const uint32_t qi = (uint32_t)(q + half);  // which quadrature's stream
-          const uint4 r = philox4x32_10(
-              make_uint4((uint32_t)gb, (uint32_t)t,
-                         (uint32_t)cgc | (qi << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
-              key);
-          float n0, n1, n2, n3;
-          box_muller(r.x, r.y, n0, n1);
-          box_muller(r.z, r.w, n2, n3);
-          const float nn[4] = {n0, n1, n2, n3};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const float w = colok[jj] ? nn[jj] : 0.f;
-            if (i) W[q][jj].y = w; else W[q][jj].x = w;
-          }
-        }
+        for (int i = 0; i < 2; ++i) quantum(W, q, i, t);
     } else {
 #pragma unroll
       for (int q = 0; q < KT; ++q)
@@ -284,8 +296,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       // tcgen05.ld is in flight while the current chunk is consumed (no register copies)
       const float* xrow = X + (size_t)buf * NP * XS + RW * rg + 2 * half;
       int off = 0;
-      auto contract4 = [&](const float (&qq)[16]) {
+      // returns the bits of the last state value it loaded (scheduling pin of the PIPE variant)
+      auto contract4 = [&](const float (&qq)[16]) -> uint32_t {
         const float* xr = xrow + off;
+        uint32_t last = 0;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           pf2 xv[KT];
@@ -297,6 +311,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
             const float2 x2 = *reinterpret_cast<const float2*>(xr + kk * XS);
             xv[0] = pk(x2.x, x2.y);
           }
+          last = __float_as_uint(xv[0].x);
 #pragma unroll
           for (int q = 0; q < KT; ++q)
 #pragma unroll
@@ -304,6 +319,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         }
         xrow += 4 * XS;
         off = (off + RW * RG) & L.xmask;
+        return last;
       };
       float qa[16], qb[16];
       // chunk c = rows 4c..4c+3 of the thread's 4 columns
@@ -324,6 +340,26 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       };
       load_chunk(0, qa);
       int kc = 0;
+      if constexpr (PIPE) {
+        // CG > 2*NQ (checked by the host): chunks 0 .. 2*NQ exist, no guards in the unrolled part
+        constexpr int NQ = 2 * KT;
+        const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
+#pragma unroll
+        for (int u = 0; u < NQ; ++u) {
+          wait_chunk();
+          load_chunk(2 * u + 1, qb);
+          // p.pin_mask is 0 at run time: the generator's counter formally depends on a state value
+          // loaded in THIS pair of chunks, which keeps ptxas from hoisting all of the noise work
+          // to the top of the iteration (it did) and spreads it over the contraction instead.
+          const uint32_t pin = contract4(qa) & p.pin_mask;
+          wait_chunk();
+          load_chunk(2 * u + 2, qa);
+          contract4(qb);
+          if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
+          else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
+        }
+        kc = 2 * NQ;
+      }
       for (; kc + 2 <= CG; kc += 2) {
         wait_chunk();
         load_chunk(kc + 1, qb);
@@ -340,7 +376,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
 
     // ---- elementwise SDE step (same arithmetic as sde_kernel.cuh)
     if constexpr (SOLVER == SOLVER_DL) {
-      draw(t);
+      if constexpr (!PIPE) draw(t);
       if constexpr (ADAM) {
         adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
         adam_tile4(acc[1], am[1], avv[1], p, cb.y, cb.z);
@@ -382,14 +418,19 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         st[1][jj] = fma2(dtp, add2(add2(t1, t2), t3), sg);
       }
       if (t + 1 < T) {
-        draw(t + 1);
+        if constexpr (PIPE) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) W[0][jj] = Wn[0][jj];
+        } else {
+          draw(t + 1);
+        }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
           meas[jj] = clamp2(fma2(dup(sa.x), W[0][jj], st[0][jj]), -sclamp[jj], sclamp[jj]);
         stage(buf ^ 1, meas, meas);
       }
     } else {
-      draw(t);
+      if constexpr (!PIPE) draw(t);
       if constexpr (ADAM) adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
       const pf2 dtfs = dup(p.dtfs), sig = dup(p.sig), mdt = dup(-p.dt), d1 = dup(ca.y);
 #pragma unroll
@@ -458,12 +499,18 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   }
 }
 
-template <int SOLVER, bool ADAM, int QSRC>
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE>
 __global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
     sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
   extern __shared__ __align__(16) float smem[];
   __shared__ uint32_t tmem_slot;
-  sde_tile_body<SOLVER, ADAM, QSRC>(p, L, blockIdx.x, smem, &tmem_slot);
+  sde_tile_body<SOLVER, ADAM, QSRC, PIPE>(p, L, blockIdx.x, smem, &tmem_slot);
+}
+
+// PIPE needs Philox noise and more than 4*K chunks of four Q rows (DL: n >= 33, others: n >= 17).
+template <int SOLVER>
+__host__ __device__ __forceinline__ bool pipe_ok(int cg, bool philox) {
+  return philox && cg > 4 * SolverTraits<SOLVER>::K;
 }
 
 // One launch over MANY problem instances (grid = sum of the instances' CTAs): the reference's user
@@ -489,7 +536,10 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   const SdeParams p = s_item.p;
   const TmemLaunch L = s_item.L;
-  sde_tile_body<SOLVER, ADAM, QSRC_TMEM>(p, L, m.y, smem, &tmem_slot);
+  if (pipe_ok<SOLVER>(p.cg, p.noise == nullptr))
+    sde_tile_body<SOLVER, ADAM, QSRC_TMEM, true>(p, L, m.y, smem, &tmem_slot);
+  else
+    sde_tile_body<SOLVER, ADAM, QSRC_TMEM, false>(p, L, m.y, smem, &tmem_slot);
 }
 
 }  // namespace ccvm
