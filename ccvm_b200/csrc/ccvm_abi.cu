@@ -252,9 +252,16 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   if (rg > rg_max) rg = rg_max;
   if (rg < 1) rg = 1;
   if (ng == 2 && path != PATH_TMEM && 2 * round32(rg * cg) > max_threads) ng = 1;
+  // in-loop noise generation (sde_kernel_tmem.cuh, PIPE): Philox mode with enough Q chunks to hide it in
+  const bool pipe = getenv("CCVM_NO_PIPE") == nullptr &&
+                    (d.solver == CCVM_SOLVER_DL ? pipe_ok<SOLVER_DL>(cg, d.rng_mode == CCVM_RNG_PHILOX)
+                                                : pipe_ok<SOLVER_LV>(cg, d.rng_mode == CCVM_RNG_PHILOX));
   int xs = 0, xmask = 31;
   auto smem_of = [&](int xs_) { return ((size_t)2 * np + (size_t)ng * 2 * np * xs_) * sizeof(float); };
-  for (;;) {
+  const bool fixed_xs = pipe && path == PATH_TMEM;  // compile-time panel stride, no row rotation
+  if (fixed_xs && (RW * rg > TMEM_PIPE_XS || smem_of(TMEM_PIPE_XS) > (size_t)di.max_smem))
+    return fail(CCVM_E_INVALID, "internal: the fixed state-panel stride does not fit (n=%d rg=%d)", d.n, rg);
+  for (; !fixed_xs;) {
     xmask = 31;
     xs = ((RW * rg + 32 + 3) / 4) * 4;
     if (smem_of(xs) <= (size_t)di.max_smem) break;
@@ -271,8 +278,13 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   P.L.rg = rg;
   P.L.ng = ng;
   P.L.gt = path == PATH_TMEM ? (ng > 1 ? 128 : round32(rg * cg)) : round32(rg * cg);
+  if (fixed_xs) {
+    xs = TMEM_PIPE_XS;
+    xmask = 0;
+  }
   P.L.xs = xs;
   P.L.xmask = xmask;
+  P.L.pipe = pipe ? 1 : 0;
   P.L.tcols = tcols;
   P.L.phase_ns = 0;
   if (const char* e = getenv("CCVM_PHASE_NS")) P.L.phase_ns = atoi(e);
@@ -298,13 +310,6 @@ __global__ void scale_q_kernel(const float* __restrict__ q, const float* __restr
   qs[idx] = val;
 }
 
-// In-loop noise generation (sde_kernel_tmem.cuh, PIPE): Philox mode with enough Q chunks to hide it in.
-template <int SOLVER>
-static bool use_pipe(const SdeParams& p) {
-  if (getenv("CCVM_NO_PIPE")) return false;
-  return pipe_ok<SOLVER>(p.cg, p.noise == nullptr);
-}
-
 template <int SOLVER, bool ADAM, int QSRC, bool PIPE>
 static int launch_tmem_variant(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
   auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC, PIPE>;
@@ -316,7 +321,7 @@ static int launch_tmem_variant(const SdeParams& p, const TmemPlan& P, cudaStream
 
 template <int SOLVER, bool ADAM>
 static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  const bool pipe = use_pipe<SOLVER>(p);
+  const bool pipe = P.L.pipe != 0;
   if (P.qsrc == QSRC_TMEM)
     return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true>(p, P, st)
                 : launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, false>(p, P, st);

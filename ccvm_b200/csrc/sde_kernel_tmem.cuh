@@ -19,6 +19,8 @@
 //     one group's FMA/LSU-bound contraction overlaps the other's ALU/MUFU-bound noise + update.
 //     Threads t and t+128 share a TMEM lane and therefore the same column group.
 #pragma once
+#include <type_traits>
+
 #include "ccvm_common.cuh"
 #include "sde_kernel.cuh"
 
@@ -32,6 +34,7 @@ struct TmemLaunch {
   int tcols;   // TMEM columns to allocate (power of two >= 4*NP, >= 32); unused for QSRC_GMEM
   int phase_ns;  // start delay of odd groups (experiment knob; 0 in production)
   int xmask;        // 31: per-column-group bank offsets inside an X row (needs 32 floats of slack); 0: none
+  int pipe;         // 1: in-loop noise generation (PIPE kernels); decided once by the host plan
   const float* qs;  // QSRC_GMEM: the scaled matrix Qs[NP][NP] (zero padded) in global memory
 };
 
@@ -41,6 +44,12 @@ struct TmemLaunch {
 //                         is too large for on-chip replication, so it stays L2-resident (4 MB at
 //                         n = 1024) and every CTA re-reads it once per iteration.
 enum : int { QSRC_TMEM = 0, QSRC_GMEM = 1 };
+
+// Row stride (floats) of the state panel in the TMEM + PIPE kernels: a compile-time constant so
+// that every LDS of the contraction is [base + immediate] (the run-time stride cost one IMAD on the
+// FMA pipe per load).  68 = 64 + 4: rows 4 apart land 16 banks apart, which keeps the (rare) STS
+// of the panel at <= 3-way conflicts without the per-row rotation of the generic layout.
+constexpr int TMEM_PIPE_XS = 68;
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
@@ -119,7 +128,8 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
 
   uint32_t& tmem_slot = *tmem_slot_p;
   const int tid = threadIdx.x;
-  const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = L.xs, T = p.iterations;
+  constexpr int XSC = (PIPE && QSRC == QSRC_TMEM) ? TMEM_PIPE_XS : 0;  // compile-time panel stride (0: run time)
+  const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = XSC ? XSC : L.xs, T = p.iterations;
   const bool idle = tid >= L.ng * L.gt;
   const int grp = idle ? 0 : tid / L.gt, lg = tid - grp * L.gt;
   const int half = SPLIT ? (lg >> 7) : 0;   // SPLIT: 0 = c thread, 1 = s thread
@@ -291,7 +301,77 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     for (int q = 0; q < KT; ++q)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) acc[q][jj] = dup(hreg[jj]);
-    {
+    if constexpr (XSC != 0) {
+      // TMEM + PIPE: the Q chunk AND the four state rows it meets are both fetched one chunk ahead
+      // into ping-pong registers (tcgen05.ld / LDS in flight under the previous chunk's FFMA2s);
+      // all shared-memory addresses are xp + immediate, xp advances once per chunk pair.
+      typedef typename std::conditional<KT == 2, float4, float2>::type XV;
+      constexpr int ROWB = XSC * 4;  // bytes per panel row
+      const char* xp = reinterpret_cast<const char*>(X + (size_t)buf * NP * XSC + RW * rg);
+      float qa[16], qb[16];
+      XV xa[4], xb[4];
+      auto load_x = [&](int row, XV (&dst)[4]) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dst[kk] = *reinterpret_cast<const XV*>(xp + (row + kk) * ROWB);
+      };
+      auto contract = [&](const float (&qq)[16], const XV (&xx)[4]) -> uint32_t {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          pf2 xv[KT];
+          if constexpr (KT == 2) {
+            xv[0] = pk(xx[kk].x, xx[kk].y);
+            xv[1] = pk(xx[kk].z, xx[kk].w);
+          } else {
+            xv[0] = pk(xx[kk].x, xx[kk].y);
+          }
+#pragma unroll
+          for (int q = 0; q < KT; ++q)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qq[4 * kk + jj]), acc[q][jj]);
+        }
+        return __float_as_uint(xx[3].x);
+      };
+      constexpr int NQ = 2 * KT;
+      const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
+      tmem_ld16(tlane, qa);
+      load_x(0, xa);
+      int kc = 0;
+#pragma unroll
+      for (int u = 0; u < NQ; ++u) {  // CG > 2*NQ: chunks 0 .. 2*NQ exist
+        tmem_wait_ld();
+        tmem_ld16(tlane + 16 * (2 * u + 1), qb);
+        load_x(4, xb);
+        // p.pin_mask is 0 at run time: the generator's counter formally depends on a state value
+        // consumed in THIS pair of chunks, which keeps ptxas from hoisting all of the noise work
+        // to the top of the iteration (it did) and spreads it over the contraction instead.
+        const uint32_t pin = contract(qa, xa) & p.pin_mask;
+        tmem_wait_ld();
+        tmem_ld16(tlane + 16 * (2 * u + 2), qa);
+        load_x(8, xa);
+        contract(qb, xb);
+        xp += 8 * ROWB;
+        if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
+        else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
+      }
+      kc = 2 * NQ;
+      for (; kc + 2 <= CG; kc += 2) {
+        tmem_wait_ld();
+        tmem_ld16(tlane + 16 * (kc + 1), qb);
+        load_x(4, xb);
+        contract(qa, xa);
+        tmem_wait_ld();
+        if (kc + 2 < CG) {
+          tmem_ld16(tlane + 16 * (kc + 2), qa);
+          load_x(8, xa);
+        }
+        contract(qb, xb);
+        xp += 8 * ROWB;
+      }
+      if (kc < CG) {
+        tmem_wait_ld();
+        contract(qa, xa);
+      }
+    } else {
       // four k's against one 16-column TMEM chunk; two chunk buffers ping-pong so that the next
       // tcgen05.ld is in flight while the current chunk is consumed (no register copies)
       const float* xrow = X + (size_t)buf * NP * XS + RW * rg + 2 * half;
@@ -536,7 +616,7 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   const SdeParams p = s_item.p;
   const TmemLaunch L = s_item.L;
-  if (pipe_ok<SOLVER>(p.cg, p.noise == nullptr))
+  if (L.pipe)
     sde_tile_body<SOLVER, ADAM, QSRC_TMEM, true>(p, L, m.y, smem, &tmem_slot);
   else
     sde_tile_body<SOLVER, ADAM, QSRC_TMEM, false>(p, L, m.y, smem, &tmem_slot);
