@@ -197,7 +197,7 @@ struct TmemPlan {
   size_t smem;
 };
 
-enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2, PATH_TC = 3 };
+enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2, PATH_TC = 3, PATH_HYB = 4 };
 
 // tcgen05 3xTF32 drift (sde_kernel_tc.cuh) where batch x N x N is a genuine dense GEMM:
 // n >= 256 and at least 1024 contraction rows (8 CTAs of 128 rows); CCVM_TC=0 / 1 overrides the
@@ -216,6 +216,8 @@ static int choose_path(const ccvm_solve_desc& d) {
   if (getenv("CCVM_LEGACY")) return PATH_LEGACY;  // first-generation shared-memory kernel (n <~ 160)
   if (tc_eligible(d)) return PATH_TC;
   if (d.n <= 128 && getenv("CCVM_NO_TMEM") == nullptr) return PATH_TMEM;
+  // 128 < n <= 256: first 128 rows of every Q slice in TMEM, the rest in shared memory
+  if (d.n <= 4 * 64 && getenv("CCVM_NO_TMEM") == nullptr && getenv("CCVM_NO_HYB") == nullptr) return PATH_HYB;
   return PATH_GMEM;
 }
 
@@ -224,8 +226,9 @@ static int choose_path(const ccvm_solve_desc& d) {
 static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, TmemPlan& P, int share_hint = 0) {
   const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1, RW = 2 * K;
   const int cg = (d.n + 3) / 4, np = 4 * cg;
-  const int max_threads = path == PATH_TMEM ? 256 : 512;
-  const int lanes = path == PATH_TMEM ? 128 : max_threads;   // threads one group may span
+  const bool tm = path == PATH_TMEM || path == PATH_HYB;    // Q slices (partly) TMEM resident
+  const int max_threads = tm ? 256 : 512;
+  const int lanes = tm ? 128 : max_threads;   // threads one group may span
   if (cg > lanes) return fail(CCVM_E_TOO_LARGE, "n=%d exceeds the tiled SIMT path (n <= %d)", d.n, 4 * lanes);
   const int rg_max = lanes / cg;
   const int share = share_hint > 0 ? share_hint : (d.batch + di.sms - 1) / di.sms;
@@ -235,7 +238,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   if (pairs > rg_max) {
     // a second, independently synchronised group if the CTA has room for it
     const int rg2 = (pairs + 1) / 2 < rg_max ? (pairs + 1) / 2 : rg_max;
-    const int gt2 = path == PATH_TMEM ? 128 : round32(rg2 * cg);
+    const int gt2 = tm ? 128 : round32(rg2 * cg);
     if (2 * gt2 <= max_threads) {
       ng = 2;
       rg = rg2;
@@ -251,15 +254,17 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   }
   if (rg > rg_max) rg = rg_max;
   if (rg < 1) rg = 1;
-  if (ng == 2 && path != PATH_TMEM && 2 * round32(rg * cg) > max_threads) ng = 1;
+  if (ng == 2 && !tm && 2 * round32(rg * cg) > max_threads) ng = 1;
   // in-loop noise generation (sde_kernel_tmem.cuh, PIPE): Philox mode with enough Q chunks to hide it in
   const bool pipe = getenv("CCVM_NO_PIPE") == nullptr &&
                     (d.solver == CCVM_SOLVER_DL ? pipe_ok<SOLVER_DL>(cg, d.rng_mode == CCVM_RNG_PHILOX)
                                                 : pipe_ok<SOLVER_LV>(cg, d.rng_mode == CCVM_RNG_PHILOX));
   int xs = 0, xmask = 31;
-  auto smem_of = [&](int xs_) { return ((size_t)2 * np + (size_t)ng * 2 * np * xs_) * sizeof(float); };
-  const bool fixed_xs = pipe && path == PATH_TMEM;  // compile-time panel stride, no row rotation
-  if (fixed_xs && (RW * rg > TMEM_PIPE_XS || smem_of(TMEM_PIPE_XS) > (size_t)di.max_smem))
+  const size_t tail = path == PATH_HYB ? (size_t)(np - 4 * HYB_TMEM_CHUNKS) * HYB_LD : 0;  // floats
+  auto smem_of = [&](int xs_) { return ((size_t)2 * np + (size_t)ng * 2 * np * xs_ + tail) * sizeof(float); };
+  const bool fixed_xs = pipe && tm;  // compile-time panel stride, no row rotation
+  const int pipe_xs = path == PATH_HYB ? HYB_PIPE_XS : TMEM_PIPE_XS;
+  if (fixed_xs && (RW * rg > pipe_xs || smem_of(pipe_xs) > (size_t)di.max_smem))
     return fail(CCVM_E_INVALID, "internal: the fixed state-panel stride does not fit (n=%d rg=%d)", d.n, rg);
   for (; !fixed_xs;) {
     xmask = 31;
@@ -277,9 +282,11 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   memset(&P.L, 0, sizeof(P.L));
   P.L.rg = rg;
   P.L.ng = ng;
-  P.L.gt = path == PATH_TMEM ? (ng > 1 ? 128 : round32(rg * cg)) : round32(rg * cg);
+  P.L.gt = tm ? (ng > 1 ? 128 : round32(rg * cg)) : round32(rg * cg);
+  if (path == PATH_HYB) tcols = 512;
+  P.L.tcols = tcols;
   if (fixed_xs) {
-    xs = TMEM_PIPE_XS;
+    xs = pipe_xs;
     xmask = 0;
   }
   P.L.xs = xs;
@@ -288,7 +295,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   P.L.tcols = tcols;
   P.L.phase_ns = 0;
   if (const char* e = getenv("CCVM_PHASE_NS")) P.L.phase_ns = atoi(e);
-  P.qsrc = path == PATH_TMEM ? QSRC_TMEM : QSRC_GMEM;
+  P.qsrc = path == PATH_TMEM ? QSRC_TMEM : path == PATH_HYB ? QSRC_HYB : QSRC_GMEM;
   P.cg = cg;
   P.threads = ng * P.L.gt;
   P.ctas = (d.batch + ng * 2 * rg - 1) / (ng * 2 * rg);
@@ -325,6 +332,9 @@ static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
   if (P.qsrc == QSRC_TMEM)
     return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true>(p, P, st)
                 : launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, false>(p, P, st);
+  if (P.qsrc == QSRC_HYB)
+    return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_HYB, true>(p, P, st)
+                : launch_tmem_variant<SOLVER, ADAM, QSRC_HYB, false>(p, P, st);
   return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_GMEM, true>(p, P, st)
               : launch_tmem_variant<SOLVER, ADAM, QSRC_GMEM, false>(p, P, st);
 }
@@ -332,8 +342,9 @@ static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
 template <int SOLVER, bool ADAM>
 static int regs_tmem(int qsrc) {
   cudaFuncAttributes fa;
-  cudaError_t e = qsrc == QSRC_TMEM ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM, true>)
-                                    : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM, true>);
+  cudaError_t e = qsrc == QSRC_TMEM  ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM, true>)
+                  : qsrc == QSRC_HYB ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_HYB, true>)
+                                     : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM, true>);
   return e == cudaSuccess ? fa.numRegs : -1;
 }
 
@@ -653,7 +664,7 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
   const int path = choose_path(*d);
-  const bool use_tmem = path == PATH_TMEM || path == PATH_GMEM;  // tiled SIMT kernel (TMEM or streamed Q)
+  const bool use_tmem = path == PATH_TMEM || path == PATH_GMEM || path == PATH_HYB;  // tiled SIMT kernel
   LaunchPlan L;
   TmemPlan TP;
   memset(&L, 0, sizeof(L));
@@ -745,7 +756,8 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
       return fail(CCVM_E_INVALID, "all descriptors of a batch must share solver and algorithm");
     if (descs[i].rng_mode != CCVM_RNG_PHILOX || descs[i].evolution_step > 0)
       return fail(CCVM_E_INVALID, "batched solves use Philox noise and no evolution sampling");
-    (choose_path(descs[i]) == PATH_TMEM ? batched : single).push_back(i);
+    const int path = choose_path(descs[i]);
+    (path == PATH_TMEM || path == PATH_HYB ? batched : single).push_back(i);
   }
   for (int i : single)
     if ((rc = ccvm_solve(&descs[i], stream))) return rc;
@@ -760,7 +772,7 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
   const int share = (int)((total_traj + di.sms - 1) / di.sms);
   for (size_t b = 0; b < batched.size(); ++b) {
     const ccvm_solve_desc& d = descs[batched[b]];
-    if ((rc = plan_tmem(d, di, PATH_TMEM, plans[b], share))) return rc;
+    if ((rc = plan_tmem(d, di, choose_path(d), plans[b], share))) return rc;
     jobs[b].a = sched_args(&d);
     jobs[b].offset = rows;
     rows += d.iterations;
@@ -776,38 +788,42 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
   build_schedule_batch_kernel<<<dim3((max_t + 127) / 128, (unsigned)jobs.size()), 128, 0, st>>>(d_jobs, sched);
   CUDA_TRY(cudaGetLastError());
 
-  // items + CTA maps, bucketed by block size so small instances do not pay for big blocks
+  // items + CTA maps, bucketed by Q source and block size so small instances do not pay for big blocks
   std::vector<BatchItem> items(batched.size());
   const int bucket_threads[4] = {32, 64, 128, 256};
-  std::vector<int2> maps[4];
-  size_t bucket_smem[4] = {0, 0, 0, 0};
+  constexpr int NB = 8;  // buckets 0-3: QSRC_TMEM, 4-7: QSRC_HYB
+  std::vector<int2> maps[NB];
+  size_t bucket_smem[NB] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (size_t b = 0; b < batched.size(); ++b) {
     const ccvm_solve_desc& d = descs[batched[b]];
     fill_params(&d, sched + jobs[b].offset * SCHED_W, plans[b].cg, items[b].p);
     items[b].L = plans[b].L;
     int k = 0;
     while (bucket_threads[k] < plans[b].threads) ++k;
+    if (plans[b].qsrc == QSRC_HYB) k += 4;
     for (int c = 0; c < plans[b].ctas; ++c) maps[k].push_back(make_int2((int)b, c));
     if (plans[b].smem > bucket_smem[k]) bucket_smem[k] = plans[b].smem;
   }
   size_t total_ctas = 0;
-  for (int k = 0; k < 4; ++k) total_ctas += maps[k].size();
+  for (int k = 0; k < NB; ++k) total_ctas += maps[k].size();
   CUDA_TRY(cudaMallocAsync((void**)&d_items, items.size() * sizeof(BatchItem), st));
   CUDA_TRY(cudaMallocAsync((void**)&d_map, total_ctas * sizeof(int2), st));
   CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(BatchItem), cudaMemcpyHostToDevice, st));
   size_t off = 0;
   const bool adam = alg == CCVM_ALG_ADAM;
-  for (int k = 0; k < 4 && !rc; ++k) {
+  for (int k = 0; k < NB && !rc; ++k) {
     if (maps[k].empty()) continue;
     const size_t n = maps[k].size();
     CUDA_TRY(cudaMemcpyAsync(d_map + off, maps[k].data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
-#define BATCH_LAUNCH(S, A)                                                                                 \
+#define BATCH_LAUNCH_Q(S, A, Q)                                                                            \
   {                                                                                                        \
-    auto kern = sde_tmem_batch_kernel<S, A>;                                                               \
+    auto kern = sde_tmem_batch_kernel<S, A, Q>;                                                            \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem[k]); \
     if (e != cudaSuccess) rc = fail(CCVM_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));      \
-    else kern<<<(unsigned)n, bucket_threads[k], bucket_smem[k], st>>>(d_items, d_map + off);               \
+    else kern<<<(unsigned)n, bucket_threads[k & 3], bucket_smem[k], st>>>(d_items, d_map + off);           \
   }
+#define BATCH_LAUNCH(S, A)                                \
+  if (k < 4) BATCH_LAUNCH_Q(S, A, QSRC_TMEM) else BATCH_LAUNCH_Q(S, A, QSRC_HYB)
     switch (solver * 2 + (adam ? 1 : 0)) {
       case 0: BATCH_LAUNCH(SOLVER_DL, false) break;
       case 1: BATCH_LAUNCH(SOLVER_DL, true) break;
@@ -819,6 +835,7 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
       default: BATCH_LAUNCH(SOLVER_PLV, true) break;
     }
 #undef BATCH_LAUNCH
+#undef BATCH_LAUNCH_Q
     if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(CCVM_E_CUDA, "batched launch failed");
     off += n;
   }

@@ -76,13 +76,25 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// two uniforms in (0,1] -> two standard normals (Box-Muller on the MUFU pipe)
+// two uniforms in (0,1] -> two standard normals (Box-Muller on the MUFU pipe).  u1 >= 2^-33 is never
+// denormal, so the flush-to-zero lg2 needs none of the range fix-up __log2f carries (3 instructions
+// per pair); the angle comes out of its conversion FFMA already in radians.
+__device__ __forceinline__ float fast_lg2(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
   const float u1 = fmaf(__uint2float_rn(a), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float u2 = fmaf(__uint2float_rn(b), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-  const float r = fast_sqrt(-1.3862943611198906f * __log2f(u1));  // sqrt(-2 ln u1)
+  const float th = fmaf(__uint2float_rn(b), 1.4629180792671596e-09f, 7.314590396335798e-10f);  // 2 pi u2
+  const float r = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));  // sqrt(-2 ln u1)
   float sn, cs;
-  __sincosf(6.2831853071795865f * u2, &sn, &cs);
+  __sincosf(th, &sn, &cs);
   n0 = r * cs;
   n1 = r * sn;
 }

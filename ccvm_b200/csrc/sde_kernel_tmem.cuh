@@ -43,13 +43,22 @@ struct TmemLaunch {
 //   QSRC_GMEM (any n):    streamed from global memory / L2 with read-only 128-bit loads; the matrix
 //                         is too large for on-chip replication, so it stays L2-resident (4 MB at
 //                         n = 1024) and every CTA re-reads it once per iteration.
-enum : int { QSRC_TMEM = 0, QSRC_GMEM = 1 };
+//   QSRC_HYB (128 < n <= 256): rows k < 128 of the slice in the thread's TMEM lane (all 512 columns),
+//                         rows k >= 128 in shared memory, zero padded to HYB_LD columns per row so
+//                         that every address of the tail is base + immediate (4 LDS.128 per chunk;
+//                         lanes of one column group broadcast, neighbouring groups are contiguous).
+enum : int { QSRC_TMEM = 0, QSRC_GMEM = 1, QSRC_HYB = 2 };
+constexpr int HYB_TMEM_CHUNKS = 32;  // chunks of 4 rows held in TMEM (128 rows x 4 columns = 512 TMEM columns)
+constexpr int HYB_LD = 256;          // floats per row of the shared-memory tail
 
 // Row stride (floats) of the state panel in the TMEM + PIPE kernels: a compile-time constant so
 // that every LDS of the contraction is [base + immediate] (the run-time stride cost one IMAD on the
 // FMA pipe per load).  68 = 64 + 4: rows 4 apart land 16 banks apart, which keeps the (rare) STS
 // of the panel at <= 3-way conflicts without the per-row rotation of the generic layout.
 constexpr int TMEM_PIPE_XS = 68;
+// Same for the hybrid kernel: n > 128 leaves at most 3 trajectory pairs per 128-lane group
+// (RW * RG <= 12 floats per row), and the panel has to share the SM with the 128 KB tail of Qs.
+constexpr int HYB_PIPE_XS = 20;
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols)
@@ -83,24 +92,27 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 }
 
 // Adam transform on a 4-variable tile of trajectory pairs (dl_solver.py:699-727 and siblings).
+// The moments are kept pre-divided by (1 - beta):  ms = m / (1 - beta1),  vs = v / (1 - beta2), so
+//   m_hat = ms (1 - beta1) ib1,   sqrt(v_hat) = sqrt(vs) sqrt((1 - beta2) ib2)
+// and the per-iteration scalars fold into two constants: 6 packed operations + 4 MUFU per pair of
+// elements instead of 11 + 4 (the update phase is latency-bound, every instruction off the chain
+// counts).  Same quantities as the reference up to FP32 rounding of the refactored products.
 __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4], const SdeParams& p, float ib1,
                                            float ib2) {
-  const pf2 b1 = dup(p.beta1), b2 = dup(p.beta2), o1 = dup(p.omb1), o2 = dup(p.omb2);
-  const pf2 i1 = dup(ib1), i2 = dup(ib2), al = dup(p.adam_alpha), eps = dup(1e-8f);
+  const pf2 b1 = dup(p.beta1), b2 = dup(p.beta2), eps = dup(1e-8f);
+  const pf2 ca = dup(p.adam_alpha * p.omb1 * ib1);
+  const pf2 sa = dup(fast_sqrt(p.omb2 * ib2));
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     const pf2 gr = g[jj];
-    m[jj] = fma2(m[jj], b1, mul2(gr, o1));
-    const pf2 mh = mul2(m[jj], i1);
-    pf2 upd;
+    m[jj] = fma2(m[jj], b1, gr);
+    pf2 u = m[jj];
     if (!p.beta2_is_one) {
-      v[jj] = fma2(v[jj], b2, mul2(mul2(gr, gr), o2));
-      const pf2 den = add2(sqrt2(mul2(v[jj], i2)), eps);
-      upd = mul2(al, div2(mh, den));
-    } else {
-      upd = mul2(al, mh);
+      v[jj] = fma2(v[jj], b2, mul2(gr, gr));
+      const pf2 den = fma2(sqrt2(v[jj]), sa, eps);
+      u = mul2(u, pk(fast_rcp(den.x), fast_rcp(den.y)));
     }
-    g[jj] = p.add_assign ? add2(gr, upd) : upd;
+    g[jj] = p.add_assign ? fma2(u, ca, gr) : mul2(u, ca);
   }
 }
 
@@ -128,7 +140,9 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
 
   uint32_t& tmem_slot = *tmem_slot_p;
   const int tid = threadIdx.x;
-  constexpr int XSC = (PIPE && QSRC == QSRC_TMEM) ? TMEM_PIPE_XS : 0;  // compile-time panel stride (0: run time)
+  constexpr bool HAS_TMEM = QSRC != QSRC_GMEM;
+  // compile-time panel stride (0: run time)
+  constexpr int XSC = !PIPE ? 0 : QSRC == QSRC_TMEM ? TMEM_PIPE_XS : QSRC == QSRC_HYB ? HYB_PIPE_XS : 0;
   const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = XSC ? XSC : L.xs, T = p.iterations;
   const bool idle = tid >= L.ng * L.gt;
   const int grp = idle ? 0 : tid / L.gt, lg = tid - grp * L.gt;
@@ -139,9 +153,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   float* hv = smem;                                   // [NP]
   float* av = hv + NP;                                // [NP]
   float* X = av + NP + (size_t)grp * 2 * NP * XS;     // this group's [2][NP][XS] panel
+  float* qtail = av + NP + (size_t)L.ng * 2 * NP * XS;  // QSRC_HYB: Qs rows 128 .. NP-1, [NP - 128][HYB_LD]
 
   // ------------------------------------------------------------------ prologue
-  if (QSRC == QSRC_TMEM && warp == 0) tmem_alloc(&tmem_slot, L.tcols);
+  if (HAS_TMEM && warp == 0) tmem_alloc(&tmem_slot, L.tcols);
   for (int j = tid; j < NP; j += blockDim.x) {
     float a = 0.f;
     if (j < N) a = p.a_half / (p.drift_s_vec ? p.drift_s_vec[j] : p.drift_s);
@@ -150,7 +165,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tbase = QSRC == QSRC_TMEM ? tmem_slot : 0u;
+  const uint32_t tbase = HAS_TMEM ? tmem_slot : 0u;
   for (int j = tid; j < NP; j += blockDim.x) {
     float h = 0.f;
     if (j < N) {
@@ -168,9 +183,16 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   const int cgc = active ? cg : 0;
   const int j0 = 4 * cgc;
   const uint32_t tlane = tbase + ((uint32_t)((l >> 5) * 32) << 16);  // this warp's TMEM lane quadrant
-  if (QSRC == QSRC_TMEM && !idle && grp == 0 && half == 0) {
+  if constexpr (QSRC == QSRC_HYB) {
+    for (int idx = tid; idx < (NP - 4 * HYB_TMEM_CHUNKS) * HYB_LD; idx += blockDim.x) {
+      const int k = 4 * HYB_TMEM_CHUNKS + idx / HYB_LD, j = idx % HYB_LD;
+      qtail[idx] = (k < N && j < N) ? -av[k] * av[j] * p.q[k * N + j] : 0.f;
+    }
+  }
+  if (HAS_TMEM && !idle && grp == 0 && half == 0) {
     // every lane stores its own copy of the 4 columns it contracts against
-    for (int k = 0; k < NP; ++k) {
+    const int ktm = QSRC == QSRC_HYB ? 4 * HYB_TMEM_CHUNKS : NP;
+    for (int k = 0; k < ktm; ++k) {
       float qv[4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
@@ -354,22 +376,71 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
       }
       kc = 2 * NQ;
-      for (; kc + 2 <= CG; kc += 2) {
-        tmem_wait_ld();
-        tmem_ld16(tlane + 16 * (kc + 1), qb);
-        load_x(4, xb);
-        contract(qa, xa);
-        tmem_wait_ld();
-        if (kc + 2 < CG) {
+      if constexpr (QSRC == QSRC_HYB) {
+        // chunks 2*NQ .. 31 from TMEM; the last prefetch of this part already comes from the tail
+        const char* qp = reinterpret_cast<const char*>(qtail + j0);
+        auto lds_q = [&](int row, float (&dst)[16]) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const float4 v = *reinterpret_cast<const float4*>(qp + (row + kk) * (HYB_LD * 4));
+            dst[4 * kk] = v.x; dst[4 * kk + 1] = v.y; dst[4 * kk + 2] = v.z; dst[4 * kk + 3] = v.w;
+          }
+        };
+#pragma unroll 1
+        for (; kc + 2 < HYB_TMEM_CHUNKS; kc += 2) {
+          tmem_wait_ld();
+          tmem_ld16(tlane + 16 * (kc + 1), qb);
+          load_x(4, xb);
+          contract(qa, xa);
+          tmem_wait_ld();
           tmem_ld16(tlane + 16 * (kc + 2), qa);
           load_x(8, xa);
+          contract(qb, xb);
+          xp += 8 * ROWB;
         }
-        contract(qb, xb);
-        xp += 8 * ROWB;
-      }
-      if (kc < CG) {
-        tmem_wait_ld();
-        contract(qa, xa);
+        {  // kc == 30: chunk 31 is the last one in TMEM, chunk 32 the first of the tail (CG > 32)
+          tmem_wait_ld();
+          tmem_ld16(tlane + 16 * (kc + 1), qb);
+          load_x(4, xb);
+          contract(qa, xa);
+          tmem_wait_ld();
+          lds_q(0, qa);
+          load_x(8, xa);
+          contract(qb, xb);
+          xp += 8 * ROWB;
+          kc += 2;
+        }
+        for (; kc + 2 <= CG; kc += 2) {
+          lds_q(4, qb);
+          load_x(4, xb);
+          contract(qa, xa);
+          if (kc + 2 < CG) {
+            lds_q(8, qa);
+            load_x(8, xa);
+          }
+          contract(qb, xb);
+          xp += 8 * ROWB;
+          qp += 8 * (HYB_LD * 4);
+        }
+        if (kc < CG) contract(qa, xa);
+      } else {
+        for (; kc + 2 <= CG; kc += 2) {
+          tmem_wait_ld();
+          tmem_ld16(tlane + 16 * (kc + 1), qb);
+          load_x(4, xb);
+          contract(qa, xa);
+          tmem_wait_ld();
+          if (kc + 2 < CG) {
+            tmem_ld16(tlane + 16 * (kc + 2), qa);
+            load_x(8, xa);
+          }
+          contract(qb, xb);
+          xp += 8 * ROWB;
+        }
+        if (kc < CG) {
+          tmem_wait_ld();
+          contract(qa, xa);
+        }
       }
     } else {
       // four k's against one 16-column TMEM chunk; two chunk buffers ping-pong so that the next
@@ -407,6 +478,17 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       auto load_chunk = [&](int c, float (&dst)[16]) {
         if constexpr (QSRC == QSRC_TMEM) {
           tmem_ld16(tlane + 16 * c, dst);
+        } else if constexpr (QSRC == QSRC_HYB) {
+          if (c < HYB_TMEM_CHUNKS) {
+            tmem_ld16(tlane + 16 * c, dst);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const float4 v = *reinterpret_cast<const float4*>(
+                  qtail + (size_t)(4 * (c - HYB_TMEM_CHUNKS) + kk) * HYB_LD + j0);
+              dst[4 * kk] = v.x; dst[4 * kk + 1] = v.y; dst[4 * kk + 2] = v.z; dst[4 * kk + 3] = v.w;
+            }
+          }
         } else {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
@@ -416,7 +498,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         }
       };
       auto wait_chunk = [&]() {
-        if constexpr (QSRC == QSRC_TMEM) tmem_wait_ld();
+        if constexpr (HAS_TMEM) tmem_wait_ld();
       };
       load_chunk(0, qa);
       int kc = 0;
@@ -572,7 +654,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     }
   }
   }  // !idle
-  if constexpr (QSRC == QSRC_TMEM) {
+  if constexpr (HAS_TMEM) {
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_free(tbase, L.tcols);
@@ -601,7 +683,7 @@ struct BatchItem {
   TmemLaunch L;
 };
 
-template <int SOLVER, bool ADAM>
+template <int SOLVER, bool ADAM, int QSRC>
 __global__ void __launch_bounds__(256, 1)
     sde_tmem_batch_kernel(const BatchItem* __restrict__ items, const int2* __restrict__ cta_map) {
   extern __shared__ __align__(16) float smem[];
@@ -617,9 +699,9 @@ __global__ void __launch_bounds__(256, 1)
   const SdeParams p = s_item.p;
   const TmemLaunch L = s_item.L;
   if (L.pipe)
-    sde_tile_body<SOLVER, ADAM, QSRC_TMEM, true>(p, L, m.y, smem, &tmem_slot);
+    sde_tile_body<SOLVER, ADAM, QSRC, true>(p, L, m.y, smem, &tmem_slot);
   else
-    sde_tile_body<SOLVER, ADAM, QSRC_TMEM, false>(p, L, m.y, smem, &tmem_slot);
+    sde_tile_body<SOLVER, ADAM, QSRC, false>(p, L, m.y, smem, &tmem_slot);
 }
 
 }  // namespace ccvm

@@ -16,8 +16,9 @@ KEYS = {
     "lv": (LangevinSolver, dict(dt=0.002, S=0.5, sigma=0.5, feedback_scale=1.0), "adam"),
     "plv": (PumpedLangevinSolver, dict(pump=2.0, dt=0.002, S=0.5, sigma=0.5, feedback_scale=1.0), "grad-descent"),
 }
-# sizes straddle every CTA-size bucket and include one instance beyond the TMEM path (n > 128)
-SIZES = (5, 20, 33, 70, 128, 140, 64, 20)
+# sizes straddle every CTA-size bucket of both batched kernels (TMEM: n <= 128, hybrid: n <= 256) and
+# include one instance beyond them (streamed Q, solved by its own launch)
+SIZES = (5, 20, 33, 70, 128, 140, 64, 250, 20, 300)
 
 
 def _solver(name, batch, iters):

@@ -36,8 +36,11 @@ CASES = [
     ("plv", False, 70, 300, 400, 1e-3), ("plv", True, 70, 300, 400, 1e-3),
     ("dl", False, 20, 1000, 1500, 1e-3), ("mf", False, 33, 129, 300, 1e-3),   # ragged: n % 4 != 0, odd batch
     ("lv", False, 128, 64, 100, 1e-3), ("dl", False, 1, 3, 50, 1e-3), ("plv", True, 5, 1, 50, 1e-3),
-    # n > 128: the Q slice no longer fits a TMEM lane -> streamed from L2 (QSRC_GMEM)
+    # 128 < n <= 256: the Q slice no longer fits a TMEM lane -> rows >= 128 in shared memory (QSRC_HYB)
     ("dl", False, 200, 40, 120, 1e-3), ("dl", True, 131, 33, 100, 2e-3), ("mf", True, 250, 64, 150, 1e-3),
+    ("mf", False, 129, 50, 100, 1e-3), ("lv", False, 256, 40, 80, 1e-3), ("plv", True, 160, 70, 100, 1e-3),
+    ("lv", True, 253, 9, 60, 1e-3), ("dl", False, 256, 24, 60, 1e-3),
+    # n > 256 with too few rows for the tensor-core path: streamed from L2 (QSRC_GMEM)
     ("lv", False, 300, 16, 80, 1e-3), ("plv", False, 513, 6, 40, 1e-3),
 ]
 
@@ -196,6 +199,49 @@ def test_alternate_kernel_paths(monkeypatch, env, solver, adam):
     size the TMEM kernel normally takes (selected through the library's environment switches)."""
     monkeypatch.setenv(env, "1")
     test_replay_parity_vs_oracle(solver, adam, 70, 100, 200, 2e-3 if (solver == "dl" and adam) else 1e-3)
+
+
+def test_streamed_q_path_below_256(monkeypatch):
+    """CCVM_NO_HYB sends 128 < n <= 256 through the streamed-Q kernel (the path n > 256 takes)."""
+    monkeypatch.setenv("CCVM_NO_HYB", "1")
+    test_replay_parity_vs_oracle("dl", True, 131, 33, 100, 2e-3)
+    test_replay_parity_vs_oracle("mf", False, 200, 40, 100, 1e-3)
+
+
+@pytest.mark.parametrize("solver,adam", [("dl", False), ("dl", True), ("mf", False), ("mf", True), ("lv", False),
+                                         ("lv", True), ("plv", False), ("plv", True)])
+@pytest.mark.parametrize("n,b", [(129, 300), (170, 1000), (256, 333)])
+def test_hybrid_philox_matches_streamed_q(monkeypatch, solver, adam, n, b):
+    """Production (Philox, in-loop noise) variant of the hybrid TMEM + shared-memory kernel against
+    the streamed-Q kernel under the same Philox stream: same noise, same arithmetic up to the
+    order of the prefetch, so the states must agree closely after a short run; the hybrid path must
+    also be bit-reproducible and independent of how the batch is split."""
+    t = 40
+    q, v, _ = instance(n, 11, 0.2 if solver == "dl" else 0.05)
+    sid = {"dl": nat.SOLVER_DL, "mf": nat.SOLVER_MF, "lv": nat.SOLVER_LANGEVIN, "plv": nat.SOLVER_PUMPED_LANGEVIN}[solver]
+    kw = {"dl": dict(s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0, g=0.05),
+          "mf": dict(s=20.0, pump=0.0, dt=0.0025, j=5.0, feedback_scale=4000.0, g=0.01),
+          "lv": dict(s=0.5, dt=0.002, sigma=0.5, feedback_scale=1.0),
+          "plv": dict(s=0.5, pump=2.0, dt=0.002, sigma=0.5, feedback_scale=1.0)}[solver]
+    if solver == "dl" and not adam:
+        kw["feedback_scale"] = 100.0
+    if adam:
+        kw["hyperparameters"] = HP
+    alg = nat.ALG_ADAM if adam else nat.ALG_ORIGINAL
+    qg, vg = q.cuda(), v.cuda()
+    hyb, _ = E.solve(sid, alg, qg, vg, b, t, seed=3, offset=4, **kw)
+    hyb = [o.clone() for o in hyb]
+    again, _ = E.solve(sid, alg, qg, vg, b, t, seed=3, offset=4, **kw)
+    assert all(torch.equal(a, c) for a, c in zip(hyb, again))
+    cut = b // 3 + 1
+    lo, _ = E.solve(sid, alg, qg, vg, cut, t, seed=3, offset=4, traj_base=0, **kw)
+    hi, _ = E.solve(sid, alg, qg, vg, b - cut, t, seed=3, offset=4, traj_base=cut, **kw)
+    assert all(torch.equal(torch.cat([a, c]), f) for a, c, f in zip(lo, hi, hyb))
+    monkeypatch.setenv("CCVM_NO_HYB", "1")
+    ref, _ = E.solve(sid, alg, qg, vg, b, t, seed=3, offset=4, **kw)
+    for a, c in zip(ref, hyb):
+        assert torch.isfinite(c).all()
+        assert (a - c).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1.0)
 
 
 def test_large_n_limits():

@@ -1,0 +1,149 @@
+"""Statistical-equivalence gate of the production (Philox) path on the 300 bundled BoxQP instances
+(BASELINE.json configs[1]): every solver, B = 1000, T = 1500, the parameter keys of
+the reference's examples, against success fractions recorded from the UNMODIFIED reference on the
+CPU (tests/golden/equivalence_ref.json, written by tests/golden/make_equivalence.py).
+
+    python tools/equivalence_gpu.py [--seed 0] [--out profiles/r1_equivalence.json]
+
+Gate (per solver):
+  * per (instance, threshold): two-proportion z-test at 95 % between the engine's and the
+    reference's success fraction; at most `max_reject` (5 % + the reference's own seed-to-seed
+    rejection rate) of the 300 x 7 cells may reject;
+  * per size and threshold: the pooled success fraction (50 instances x B) must lie within the
+    two-sample 95 % interval of the pooled reference fraction (Bonferroni over the 42 cells);
+  * where both hit the `optimal` bucket, best objective values agree within 1e-4 relative.
+The reference's seed 0 vs seed 1 results go through the same tests: that is the calibration.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SIZES = (20, 30, 40, 50, 60, 70)
+THRESH = ("optimal", "one_percent", "two_percent", "three_percent", "four_percent", "five_percent", "ten_percent")
+Z95 = 1.959964
+Z_BONF42 = 3.04   # two-sided 95 % over 42 (size, threshold) cells
+
+
+def load_bundled(device="cuda"):
+    """The 300 bundled instances as ProblemInstance objects (unscaled), from the packed fixture."""
+    from ccvm_b200.problem_classes.boxqp import ProblemInstance
+    z = np.load(os.path.join(GOLDEN, "bundled_instances.npz"))
+    out = {}
+    for n in SIZES:
+        insts = []
+        for k in range(z[f"q{n}"].shape[0]):
+            inst = ProblemInstance(device=device, instance_type="tuning", name=str(z[f"name{n}"][k])[:-3])
+            inst.problem_size = n
+            inst.q_matrix = torch.from_numpy(z[f"q{n}"][k]).to(device)
+            inst.v_vector = torch.from_numpy(z[f"v{n}"][k]).to(device)
+            inst.optimal_sol = inst.best_sol = float(z[f"opt{n}"][k])
+            inst.num_frac_values, inst.solution_vector, inst.optimality = 0, [], True
+            insts.append(inst)
+        out[n] = insts
+    return out
+
+
+def run_engine(name, key, post, seed, batch, chunk=50):
+    """rows[n] = per instance [7 success fractions..., best objective] from the CUDA engine."""
+    from ccvm_b200.solvers import DLSolver, MFSolver, LangevinSolver, PumpedLangevinSolver
+    cls = {"mf": MFSolver, "langevin": LangevinSolver, "pumped_langevin": PumpedLangevinSolver, "dl": DLSolver}[name]
+    torch.manual_seed(seed)
+    bundled = load_bundled()
+    rows = {}
+    for n in SIZES:
+        solver = cls(device="cuda", batch_size=batch)
+        solver.parameter_key = {n: dict(key)}
+        insts = bundled[n]
+        for inst in insts:
+            inst.scale_coefs(solver.get_scaling_factor(inst.q_matrix))
+        sols = []
+        for lo in range(0, len(insts), chunk):
+            sols += solver.solve_many(insts[lo:lo + chunk], post_processor=post)
+        rows[n] = [[s.solution_performance[t] for t in THRESH] + [float(s.best_objective_value)] for s in sols]
+    return rows
+
+
+def compare(a, b, batch):
+    """Gate statistics between two result sets {n: rows}; returns a dict (see module docstring)."""
+    cells = rejects = 0
+    pooled = []
+    best_bad = best_cmp = 0
+    worst_pool = 0.0
+    for n in SIZES:
+        ra, rb = np.asarray(a[n], dtype=np.float64), np.asarray(b[n], dtype=np.float64)
+        pa, pb = ra[:, :7], rb[:, :7]
+        pm = (pa + pb) / 2
+        se = np.sqrt(np.maximum(pm * (1 - pm), 0.0) * 2 / batch)
+        # +0.5/batch: both fractions are rounded to 4 dp by the reference (solution.py:118)
+        rej = np.abs(pa - pb) > Z95 * se + 0.5 / batch
+        cells += rej.size
+        rejects += int(rej.sum())
+        # pooled over the 50 instances of this size (variance = sum of the per-instance binomials)
+        var = (pa * (1 - pa) + pb * (1 - pb)).sum(axis=0) / batch / pa.shape[0] ** 2
+        diff = pa.mean(axis=0) - pb.mean(axis=0)
+        zs = np.abs(diff) / np.sqrt(np.maximum(var, 1e-12))
+        worst_pool = max(worst_pool, float(zs.max()))
+        pooled.append({"n": n, "a": pa.mean(axis=0).round(4).tolist(), "b": pb.mean(axis=0).round(4).tolist(),
+                       "z": zs.round(2).tolist()})
+        both = (pa[:, 0] > 0) & (pb[:, 0] > 0)
+        best_cmp += int(both.sum())
+        rel = np.abs(ra[both, 7] - rb[both, 7]) / np.abs(rb[both, 7])
+        best_bad += int((rel > 1e-4).sum())
+    return {"cells": cells, "rejects": rejects, "reject_rate": rejects / cells, "pooled": pooled,
+            "pooled_worst_z": worst_pool, "pooled_ok": worst_pool <= Z_BONF42,
+            "best_compared": best_cmp, "best_mismatch": best_bad}
+
+
+def gate(ref, name, engine_rows, batch):
+    ref0 = {n: ref[f"{name}/seed0/{n}"] for n in SIZES}
+    out = {"engine_vs_ref": compare(engine_rows, ref0, batch)}
+    if f"{name}/seed1/{SIZES[-1]}" in ref:
+        ref1 = {n: ref[f"{name}/seed1/{n}"] for n in SIZES}
+        out["ref_seed0_vs_seed1"] = compare(ref1, ref0, batch)
+        out["engine_vs_ref_seed1"] = compare(engine_rows, ref1, batch)
+    cal = out.get("ref_seed0_vs_seed1", {}).get("reject_rate", 0.0)
+    e = out["engine_vs_ref"]
+    out["max_reject"] = 0.05 + cal
+    out["pass"] = bool(e["reject_rate"] <= out["max_reject"] and e["pooled_ok"] and e["best_mismatch"] == 0)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--solvers", default="mf,langevin,pumped_langevin,dl")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    ref = json.load(open(os.path.join(GOLDEN, "equivalence_ref.json")))
+    meta = ref["_meta"]
+    report = {"batch": meta["batch"], "iterations": meta["iterations"], "engine_seed": args.seed,
+              "reference": {"torch": meta["torch"], "device": meta["device"]}}
+    ok = True
+    for name in args.solvers.split(","):
+        if f"{name}/seed0/{SIZES[-1]}" not in ref:
+            print(f"{name}: no reference record, skipped")
+            continue
+        rows = run_engine(name, meta["keys"][name], meta["post_processor"][name], args.seed, meta["batch"])
+        g = gate(ref, name, rows, meta["batch"])
+        report[name] = g
+        e, c = g["engine_vs_ref"], g.get("ref_seed0_vs_seed1")
+        print(f"{name}: pass={g['pass']} cell rejections {e['rejects']}/{e['cells']} ({100 * e['reject_rate']:.2f} %)"
+              f" pooled worst z {e['pooled_worst_z']:.2f}; best mismatches {e['best_mismatch']}/{e['best_compared']}"
+              + (f" | reference seed0 vs seed1: {100 * c['reject_rate']:.2f} %, worst z {c['pooled_worst_z']:.2f}" if c else ""))
+        ok = ok and g["pass"]
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        json.dump(report, open(args.out, "w"), indent=1)
+    print("EQUIVALENCE", "PASS" if ok else "FAIL")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
