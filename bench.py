@@ -191,6 +191,11 @@ def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version
+    # banner there) are diverted to stderr until the line is printed
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ccvm_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -296,6 +301,12 @@ def run_gpu_arm(args):
         e2e_s = t[0].item()
 
     # ---- roofline of the dominant kernel (the persistent SDE kernel): FP32 SIMT FMA
+    traffic = None   # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "bench_kernel_traffic.json")) as fh:
+            traffic = json.load(fh)["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     peak_tf = None
     cpu_baseline = None
     if rank == 0:
@@ -327,7 +338,7 @@ def run_gpu_arm(args):
                     "api": "ccvm_solve_host (C ABI, pinned host buffers)"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "frac": achieved_tf / peak_tf, "traffic": traffic,
                          "kernel": "ccvm::sde_tmem_kernel<DL, adam>", "kernel_ms": solve_avg_ms,
                          "peak_source": "measured in-process: register-only FFMA2 probe (ccvm_microbench_fp32); "
                                         "MEASURED_PEAKS.json has no FP32 SIMT figure (HBM/bf16 only)",
@@ -335,7 +346,10 @@ def run_gpu_arm(args):
             "cpu_baseline": cpu_baseline,
             "wall_s_timed_region": wall,
         }
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if distributed:
         dist.barrier()
         dist.destroy_process_group()
