@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libccvm_b200.so")
+# CCVM_B200_LIB: alternative build of the same library (kernel experiments); default is the in-tree one
+LIB_PATH = os.environ.get("CCVM_B200_LIB") or os.path.join(_HERE, "libccvm_b200.so")
 
 SOLVER_DL, SOLVER_MF, SOLVER_LANGEVIN, SOLVER_PUMPED_LANGEVIN = 0, 1, 2, 3
 ALG_ORIGINAL, ALG_ADAM = 0, 1

@@ -32,6 +32,10 @@ def main():
     ap.add_argument("--iters", type=int, default=1500)
     ap.add_argument("--solvers", default="mf,langevin,pumped_langevin,dl")
     ap.add_argument("--chunk", type=int, default=1, help="instances per batched launch (solve_many)")
+    ap.add_argument("--count", type=int, default=0,
+                    help="BASELINE configs[4]: this many instances with N drawn uniformly from --sizes "
+                         "(numpy RandomState(0)), instance k seeded with k; overrides --per-size")
+    ap.add_argument("--warm", type=int, default=0, help="instances in the untimed warm-up pass (0: all)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -39,7 +43,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
     sizes = [int(x) for x in args.sizes.split(",")]
-    specs = [(n, k) for n in sizes for k in range(args.per_size)]
+    if args.count > 0:
+        import numpy as np
+        draw = np.random.RandomState(0).choice(len(sizes), args.count)
+        specs = [(sizes[int(i)], k) for k, i in enumerate(draw)]
+    else:
+        specs = [(n, k) for n in sizes for k in range(args.per_size)]
     all_md = {}
     for name in args.solvers.split(","):
         cls, key, pp = KEYS[name]
@@ -53,10 +62,14 @@ def main():
                 cache[i] = sweep.synthetic_instance(n, k, solver._scaling_multiplier)
             return cache[i]
 
+        t_gen = time.perf_counter()
         for i in range(len(specs)):      # build this rank's instances outside the timed region
             if i % world == rank:
                 get(i)
-        sweep.solve_sweep(solver, (len(specs), get), post_processor=pp, chunk=args.chunk)  # warm-up (also sizes the allocator caches)
+        torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t_gen
+        n_warm = min(args.warm, len(specs)) if args.warm > 0 else len(specs)
+        sweep.solve_sweep(solver, (n_warm, get), post_processor=pp, chunk=args.chunk)  # warm-up (also sizes the allocator caches)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -69,6 +82,8 @@ def main():
             steps = len(specs) * args.batch * args.iters
             print(json.dumps({"solver": name, "post_processor": pp, "instances": len(specs), "sizes": sizes,
                               "batch": args.batch, "iterations": args.iters, "n_gpus": world, "chunk": args.chunk, "wall_s": wall,
+                              "instance_build_s_rank0": t_gen,
+                              "drift_tflops": sum(2.0 * (2 if name == "dl" else 1) * n * n for n, _ in specs) * args.batch * args.iters / wall / 1e12,
                               "ms_per_instance": wall / len(specs) * 1e3, "traj_steps_per_s": steps / wall,
                               "sum_kernel_solve_time_s": sum(r["solve_time"] * r["batch_size"] for r in md)}), flush=True)
     if rank == 0:
