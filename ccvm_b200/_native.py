@@ -24,7 +24,7 @@ EXPORTS = (
     "ccvm_postprocess_adam", "ccvm_solution_stats", "ccvm_scaling_factor", "ccvm_solve_host",
     "ccvm_microbench_fp32", "ccvm_query_launch", "ccvm_abi_version", "ccvm_last_error",
     "ccvm_eval_hook", "ccvm_change_variables", "ccvm_fit_to_constraints", "ccvm_scale_coefs",
-    "ccvm_solve_batch", "ccvm_solution_stats_batch",
+    "ccvm_solve_batch", "ccvm_solution_stats_batch", "ccvm_generate_boxqp",
 )
 
 _fp = C.c_void_p  # device / host pointers travel as plain addresses
@@ -112,6 +112,7 @@ def load():
     lib.ccvm_fit_to_constraints.argtypes = [_fp, _fp, C.c_int32, C.c_int32, C.c_double, C.c_double, _fp, _fp,
                                             C.c_int64, _fp]
     lib.ccvm_scale_coefs.argtypes = [_fp, _fp, C.c_int32, _fp, C.c_int64, _fp, _fp, _fp]
+    lib.ccvm_generate_boxqp.argtypes = [_fp, _fp, C.c_int32, C.c_uint64, C.c_double, C.c_double, _fp]
     for name in EXPORTS:
         if name not in ("ccvm_last_error",):
             getattr(lib, name).restype = C.c_int if name != "ccvm_last_error" else C.c_char_p

@@ -1187,6 +1187,49 @@ extern "C" int ccvm_scaling_factor(const float* q, int32_t n, double multiplier,
   return CCVM_OK;
 }
 
+// ------------------------------------------------------------ synthetic instance generator
+// Dense symmetric BoxQP coefficients with the statistics of the reference's bundled instances
+// (off-diagonal std 28.5/sqrt(N), diagonal std sqrt(2) x that -- the law of
+// (A + A^T)/sqrt(2) for i.i.d. normal A -- and V std 20), drawn on the device with Philox keyed by
+// (seed, unordered index pair): element (i, j) and (j, i) evaluate the same counter, so no transpose
+// pass is needed.  Stored in the reference's in-memory convention (negated, problem_instance.py:183-188).
+__global__ void generate_boxqp_kernel(float* __restrict__ q, float* __restrict__ v, int n, uint32_t seed_lo,
+                                      uint32_t seed_hi, float q_std, float v_std) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n + n) return;
+  int i, j;
+  uint32_t plane;
+  if (idx < n * n) {
+    i = idx / n;
+    j = idx - i * n;
+    if (i > j) {
+      const int t = i;
+      i = j;
+      j = t;
+    }
+    plane = 0u;
+  } else {
+    i = idx - n * n;
+    j = 0;
+    plane = 1u;
+  }
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)j, plane, 0x51424f58u), make_uint2(seed_lo, seed_hi));
+  float z0, z1;
+  box_muller(r.x, r.y, z0, z1);
+  if (plane == 0u) q[idx] = -(i == j ? 1.41421356237f : 1.f) * q_std * z0;
+  else v[i] = -v_std * z0;
+}
+
+extern "C" int ccvm_generate_boxqp(float* q, float* v, int32_t n, uint64_t seed, double q_offdiag_std, double v_std,
+                                   void* stream) {
+  if (!q || !v || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_generate_boxqp");
+  const int total = n * n + n;
+  generate_boxqp_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      q, v, n, (uint32_t)seed, (uint32_t)(seed >> 32), (float)q_offdiag_std, (float)v_std);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
 // ------------------------------------------------------------------ host-buffer entry
 extern "C" int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue_desc* epi, const float* h_q,
                                const float* h_v, double optimal_value, float* h_energy, void* h_stats,

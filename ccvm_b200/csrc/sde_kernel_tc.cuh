@@ -242,16 +242,14 @@ __device__ __forceinline__ void tc_st16(float* dst, const float (&r)[16]) {
 
 // Adam transform of one gradient element (dl_solver.py:699-727 and siblings), scalar form of adam_tile4
 __device__ __forceinline__ float tc_adam(float g, float& m, float& v, const SdeParams& p, float ib1, float ib2) {
+  // branch-free (the per-element branch on beta2 == 1 fenced the 16 unrolled chains from each other):
+  // beta2 == 1 -> update = alpha m_hat, the v / den chain is evaluated on harmless values and dropped
+  const bool b2one = p.beta2_is_one != 0;
   m = fmaf(m, p.beta1, g * p.omb1);
   const float mh = m * ib1;
-  float upd;
-  if (!p.beta2_is_one) {
-    v = fmaf(v, p.beta2, (g * g) * p.omb2);
-    const float den = fast_sqrt(v * ib2) + 1e-8f;
-    upd = p.adam_alpha * __fdividef(mh, den);
-  } else {
-    upd = p.adam_alpha * mh;
-  }
+  v = b2one ? v : fmaf(v, p.beta2, (g * g) * p.omb2);
+  const float den = fast_sqrt(v * ib2) + 1e-8f;
+  const float upd = p.adam_alpha * (b2one ? mh : __fdividef(mh, den));
   return p.add_assign ? g + upd : upd;
 }
 

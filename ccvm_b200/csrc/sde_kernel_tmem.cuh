@@ -99,20 +99,23 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
 // counts).  Same quantities as the reference up to FP32 rounding of the refactored products.
 __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4], const SdeParams& p, float ib1,
                                            float ib2) {
-  const pf2 b1 = dup(p.beta1), b2 = dup(p.beta2), eps = dup(1e-8f);
+  // The run-time options are folded into scalars so that the tile is ONE straight-line block (a
+  // branch per element kept ptxas from interleaving the eight dependent MUFU chains):
+  //   beta2 == 1 (dl_solver.py:707-713: update = alpha m_hat): v <- g^2, den = 0 sqrt(v) + 1 = 1;
+  //   add_assign False: the gradient enters with weight 0.
+  const bool b2one = p.beta2_is_one != 0;
+  const pf2 b1 = dup(p.beta1), b2 = dup(b2one ? 0.f : p.beta2), eps = dup(b2one ? 1.f : 1e-8f);
   const pf2 ca = dup(p.adam_alpha * p.omb1 * ib1);
-  const pf2 sa = dup(fast_sqrt(p.omb2 * ib2));
+  const pf2 sa = dup(b2one ? 0.f : fast_sqrt(p.omb2 * ib2));
+  const pf2 aa = dup(p.add_assign ? 1.f : 0.f);
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     const pf2 gr = g[jj];
     m[jj] = fma2(m[jj], b1, gr);
-    pf2 u = m[jj];
-    if (!p.beta2_is_one) {
-      v[jj] = fma2(v[jj], b2, mul2(gr, gr));
-      const pf2 den = fma2(sqrt2(v[jj]), sa, eps);
-      u = mul2(u, pk(fast_rcp(den.x), fast_rcp(den.y)));
-    }
-    g[jj] = p.add_assign ? fma2(u, ca, gr) : mul2(u, ca);
+    v[jj] = fma2(v[jj], b2, mul2(gr, gr));
+    const pf2 den = fma2(sqrt2(v[jj]), sa, eps);
+    const pf2 u = mul2(m[jj], pk(fast_rcp(den.x), fast_rcp(den.y)));
+    g[jj] = fma2(u, ca, mul2(gr, aa));
   }
 }
 

@@ -263,6 +263,21 @@ def scaling_factor(q, multiplier):
     return out.to(home)
 
 
+def generate_boxqp(n, seed, device=None, q_offdiag_std=None, v_std=20.0):
+    """(Q, V) of a synthetic dense symmetric BoxQP instance drawn on the device (``ccvm_generate_boxqp``):
+    coefficient statistics of the bundled benchmarking instances (off-diagonal std
+    28.5/sqrt(N), V std 20), reference sign convention, deterministic in (n, seed)."""
+    nat.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    q = torch.empty((n, n), dtype=torch.float32, device=dev)
+    v = torch.empty((n,), dtype=torch.float32, device=dev)
+    std = 28.5 / n ** 0.5 if q_offdiag_std is None else float(q_offdiag_std)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_generate_boxqp(nat.ptr(q), nat.ptr(v), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, std,
+                                                 float(v_std), nat.current_stream_ptr(dev)))
+    return q, v
+
+
 def microbench_fp32(mode=1):
     """Measured register-only FP32 FMA throughput in TFLOP/s (0 = FFMA, 1 = packed FFMA2)."""
     nat.require_cuda()

@@ -10,20 +10,27 @@ import torch.distributed as dist
 from . import parallel
 
 
-def synthetic_instance(n, seed, scaling_multiplier, device="cuda", name=None):
+def synthetic_instance(n, seed, scaling_multiplier, device="cuda", name=None, on_device=False):
     """Synthetic dense BoxQP fitted to the bundled instances: symmetric Gaussian Q with
     off-diagonal std 28.5/sqrt(N), V std 20, reference sign convention, scaled like
     ``instance.scale_coefs(solver.get_scaling_factor(Q))``.  No Gurobi optimum exists, so
-    ``optimal_sol`` is left at 0 and must be filled from the best value found."""
+    ``optimal_sol`` is left at 0 and must be filled from the best value found.
+
+    ``on_device=False`` draws with the host generator SURVEY.md 8d specifies (seed 1000 + k, the
+    instances ``bench.py`` and the tests use); ``on_device=True`` draws the same distribution with the
+    engine's Philox generator directly in HBM (no host randn, no H2D copy) -- a different stream."""
     from .problem_classes.boxqp import ProblemInstance
     from . import engine
-    g = torch.Generator().manual_seed(1000 + seed)
-    a = torch.randn(n, n, generator=g)
-    q = -((a + a.T) / 2 ** 0.5 * (28.5 / n ** 0.5)).float()
-    v = -(20.0 * torch.randn(n, generator=g)).float()
     inst = ProblemInstance(device=device, instance_type="test", name=name or f"synthetic{n:03d}-{seed}")
     inst.problem_size = n
-    inst.q_matrix, inst.v_vector = q.to(device), v.to(device)
+    if on_device:
+        inst.q_matrix, inst.v_vector = engine.generate_boxqp(n, 1000 + seed, device=device)
+    else:
+        g = torch.Generator().manual_seed(1000 + seed)
+        a = torch.randn(n, n, generator=g)
+        q = -((a + a.T) / 2 ** 0.5 * (28.5 / n ** 0.5)).float()
+        v = -(20.0 * torch.randn(n, generator=g)).float()
+        inst.q_matrix, inst.v_vector = q.to(device), v.to(device)
     inst.optimal_sol = inst.best_sol = 0.0
     inst.num_frac_values, inst.solution_vector, inst.optimality = 0, [], False
     inst.scale_coefs(engine.scaling_factor(inst.q_matrix, scaling_multiplier))

@@ -251,6 +251,14 @@ int ccvm_fit_to_constraints(const float* x, float* out, int32_t batch, int32_t n
 int ccvm_scale_coefs(const float* q, const float* v, int32_t n, const float* factor,
                      int64_t factor_len, float* q_out, float* v_out, void* stream);
 
+/* Replaces the instance source of a synthetic sweep (no reference function: its instances are files,
+ * problem_classes/boxqp/problem_instance.py:116-224): fills q[n*n] and v[n]
+ * (device) with a dense symmetric BoxQP instance whose coefficient statistics match the bundled
+ * benchmarking instances (off-diagonal std q_offdiag_std, diagonal std sqrt(2) x that, V std v_std),
+ * in the reference's in-memory sign convention.  Deterministic in (n, seed). */
+int ccvm_generate_boxqp(float* q, float* v, int32_t n, uint64_t seed, double q_offdiag_std,
+                        double v_std, void* stream);
+
 /*
  * Host-buffer convenience used for end-to-end timing: copies Q and V from HOST memory,
  * runs ccvm_solve + ccvm_epilogue + ccvm_solution_stats on `stream`, copies energy[batch] and the

@@ -280,3 +280,34 @@ def test_errors_on_gpu_path():
     s.fit_to_constraints = lambda *a: None
     with pytest.raises(RuntimeError, match="was replaced"):
         s(instance=inst)
+
+
+def test_device_instance_generator():
+    """ccvm_generate_boxqp: dense symmetric, the coefficient statistics of the bundled instances
+    (SURVEY.md 8d), deterministic in (n, seed), usable as a ProblemInstance source."""
+    from ccvm_b200 import sweep
+    n = 250
+    q, v = E.generate_boxqp(n, 17)
+    q2, v2 = E.generate_boxqp(n, 17)
+    q3, _ = E.generate_boxqp(n, 18)
+    assert torch.equal(q, q2) and torch.equal(v, v2) and not torch.equal(q, q3)
+    assert torch.equal(q, q.T)
+    off = q[~torch.eye(n, dtype=torch.bool, device=q.device)]
+    sigma = 28.5 / n ** 0.5
+    m = off.numel() / 2          # independent entries
+    assert abs(off.mean().item()) < 5 * sigma / m ** 0.5
+    assert abs(off.std().item() / sigma - 1) < 5 / (2 * m) ** 0.5
+    assert abs(q.diagonal().std().item() / (2 ** 0.5 * sigma) - 1) < 5 / (2 * n) ** 0.5
+    big_v = torch.cat([E.generate_boxqp(200, s)[1] for s in range(50)])
+    assert abs(big_v.std().item() / 20.0 - 1) < 0.05 and abs(big_v.mean().item()) < 1.0
+    # statistics of a bundled instance of the same size, for reference
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bundled_instances.npz"))
+    q70 = torch.from_numpy(z["q70"][0])
+    g70, _ = E.generate_boxqp(70, 3)
+    mask = ~torch.eye(70, dtype=torch.bool)
+    assert abs(g70.cpu()[mask].std().item() / q70[mask].std().item() - 1) < 0.1
+    inst = sweep.synthetic_instance(40, 5, 0.05, on_device=True)
+    solver = LangevinSolver(device="cuda", batch_size=64)
+    solver.parameter_key = {40: dict(dt=0.002, S=0.5, sigma=0.5, feedback_scale=1.0, iterations=50)}
+    sol = solver(instance=inst, post_processor="grad-descent")
+    assert torch.isfinite(sol.objective_values).all()

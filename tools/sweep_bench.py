@@ -36,6 +36,7 @@ def main():
                     help="BASELINE configs[4]: this many instances with N drawn uniformly from --sizes "
                          "(numpy RandomState(0)), instance k seeded with k; overrides --per-size")
     ap.add_argument("--warm", type=int, default=0, help="instances in the untimed warm-up pass (0: all)")
+    ap.add_argument("--on-device", action="store_true", help="draw the instances with the device generator")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
@@ -59,7 +60,7 @@ def main():
         def get(i, solver=solver, cache=cache):
             if i not in cache:
                 n, k = specs[i]
-                cache[i] = sweep.synthetic_instance(n, k, solver._scaling_multiplier)
+                cache[i] = sweep.synthetic_instance(n, k, solver._scaling_multiplier, on_device=args.on_device)
             return cache[i]
 
         t_gen = time.perf_counter()
