@@ -230,6 +230,11 @@ def run_gpu_arm(args):
             return P.merge_results(rec)
         return res
 
+    # context pre-warm (not a step): module loading and the SM clock ramp of a fresh process take
+    # tens of milliseconds, more than W short steps cover -- spin the FP32 probe for ~0.2 s first
+    t_pre = time.perf_counter()
+    while time.perf_counter() - t_pre < 0.2:
+        E.microbench_fp32(1)
     for w in range(args.warmup):
         device_step(w)
     torch.cuda.synchronize(dev)
