@@ -261,10 +261,15 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
                                                 : pipe_ok<SOLVER_LV>(cg, d.rng_mode == CCVM_RNG_PHILOX));
   int xs = 0, xmask = 31;
   const size_t tail = path == PATH_HYB ? (size_t)(np - 4 * HYB_TMEM_CHUNKS) * HYB_LD : 0;  // floats
-  auto smem_of = [&](int xs_) { return ((size_t)2 * np + (size_t)ng * 2 * np * xs_ + tail) * sizeof(float); };
   const bool fixed_xs = pipe && tm;  // compile-time panel stride, no row rotation
+  // fixed-stride panels of the K = 1 solvers in the hybrid kernel hold two k rows per panel row
+  // (sde_kernel_tmem.cuh, KP)
+  const int kp = (fixed_xs && K == 1 && path == PATH_HYB) ? 2 : 1;
+  auto smem_of = [&](int xs_) {
+    return ((size_t)2 * np + (size_t)ng * 2 * (np / kp) * xs_ + tail) * sizeof(float);
+  };
   const int pipe_xs = path == PATH_HYB ? HYB_PIPE_XS : TMEM_PIPE_XS;
-  if (fixed_xs && (RW * rg > pipe_xs || smem_of(pipe_xs) > (size_t)di.max_smem))
+  if (fixed_xs && (RW * kp * rg > pipe_xs || smem_of(pipe_xs) > (size_t)di.max_smem))
     return fail(CCVM_E_INVALID, "internal: the fixed state-panel stride does not fit (n=%d rg=%d)", d.n, rg);
   for (; !fixed_xs;) {
     xmask = 31;

@@ -58,6 +58,10 @@ constexpr int HYB_LD = 256;          // floats per row of the shared-memory tail
 constexpr int TMEM_PIPE_XS = 68;
 // Same for the hybrid kernel: n > 128 leaves at most 3 trajectory pairs per 128-lane group
 // (RW * RG <= 12 floats per row), and the panel has to share the SM with the 128 KB tail of Qs.
+// There the K = 1 solvers pack TWO k rows into one panel row ((k even: b0,b1), (k odd: b0,b1)): one
+// LDS.128 then feeds 8 FFMA2 exactly like a DL row (c0,c1,s0,s1) does, instead of one LDS.64 per
+// 4 FFMA2 (n = 250: Langevin 46 -> 52 %, MF 44 -> 47 % of FP32 peak).  Measured neutral-to-worse for
+// n <= 128, where up to 25 pairs share a row and the wide load costs up to 4 wavefronts: not used there.
 constexpr int HYB_PIPE_XS = 20;
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
@@ -145,8 +149,12 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   const int tid = threadIdx.x;
   constexpr bool HAS_TMEM = QSRC != QSRC_GMEM;
   // compile-time panel stride (0: run time)
-  constexpr int XSC = !PIPE ? 0 : QSRC == QSRC_TMEM ? TMEM_PIPE_XS : QSRC == QSRC_HYB ? HYB_PIPE_XS : 0;
+  constexpr int XSC = !PIPE ? 0
+                      : QSRC == QSRC_TMEM ? TMEM_PIPE_XS
+                      : QSRC == QSRC_HYB ? HYB_PIPE_XS : 0;
+  constexpr int KP = (XSC != 0 && KT == 1 && QSRC == QSRC_HYB) ? 2 : 1;  // k rows per panel row (see HYB_PIPE_XS)
   const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = XSC ? XSC : L.xs, T = p.iterations;
+  const int PR = NP / KP;                            // panel rows per buffer
   const bool idle = tid >= L.ng * L.gt;
   const int grp = idle ? 0 : tid / L.gt, lg = tid - grp * L.gt;
   const int half = SPLIT ? (lg >> 7) : 0;   // SPLIT: 0 = c thread, 1 = s thread
@@ -155,8 +163,8 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
 
   float* hv = smem;                                   // [NP]
   float* av = hv + NP;                                // [NP]
-  float* X = av + NP + (size_t)grp * 2 * NP * XS;     // this group's [2][NP][XS] panel
-  float* qtail = av + NP + (size_t)L.ng * 2 * NP * XS;  // QSRC_HYB: Qs rows 128 .. NP-1, [NP - 128][HYB_LD]
+  float* X = av + NP + (size_t)grp * 2 * PR * XS;     // this group's [2][PR][XS] panel
+  float* qtail = av + NP + (size_t)L.ng * 2 * PR * XS;  // QSRC_HYB: Qs rows 128 .. NP-1, [NP - 128][HYB_LD]
 
   // ------------------------------------------------------------------ prologue
   if (HAS_TMEM && warp == 0) tmem_alloc(&tmem_slot, L.tcols);
@@ -179,7 +187,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     hv[j] = h;
   }
   if (!idle)
-    for (int i = lg; i < 2 * NP * XS; i += L.gt) X[i] = 0.f;
+    for (int i = lg; i < 2 * PR * XS; i += L.gt) X[i] = 0.f;
 
   const int rg = l % RG, cg = l / RG;
   const bool active = cg < CG;
@@ -288,6 +296,15 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   const int xoff = (cgc * RW * RG) & L.xmask;
   auto stage = [&](int buf, const pf2 (&a)[4], const pf2 (&b)[4]) {
     if (!active) return;
+    if constexpr (KP == 2) {
+      // the tile's rows j0 .. j0+3 are two k pairs: two STS.128
+#pragma unroll
+      for (int jp = 0; jp < 2; ++jp) {
+        float* dst = X + ((size_t)buf * PR + (j0 >> 1) + jp) * XS + 4 * rg;
+        *reinterpret_cast<float4*>(dst) = make_float4(a[2 * jp].x, a[2 * jp].y, a[2 * jp + 1].x, a[2 * jp + 1].y);
+      }
+      return;
+    }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       float* dst = X + ((size_t)buf * NP + (j0 + jj)) * XS + xoff + RW * rg + 2 * half;
@@ -330,16 +347,19 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       // TMEM + PIPE: the Q chunk AND the four state rows it meets are both fetched one chunk ahead
       // into ping-pong registers (tcgen05.ld / LDS in flight under the previous chunk's FFMA2s);
       // all shared-memory addresses are xp + immediate, xp advances once per chunk pair.
-      typedef typename std::conditional<KT == 2, float4, float2>::type XV;
+      // one panel row of a pair: (c0,c1,s0,s1), (k even b0,b1, k odd b0,b1), or (b0,b1)
+      typedef typename std::conditional<KT * KP == 2, float4, float2>::type XV;
+      constexpr int XR = 4 / KP;     // panel rows per chunk of four k
       constexpr int ROWB = XSC * 4;  // bytes per panel row
-      const char* xp = reinterpret_cast<const char*>(X + (size_t)buf * NP * XSC + RW * rg);
+      const char* xp = reinterpret_cast<const char*>(X + (size_t)buf * PR * XSC + RW * KP * rg);
       float qa[16], qb[16];
-      XV xa[4], xb[4];
-      auto load_x = [&](int row, XV (&dst)[4]) {
+      XV xa[XR], xb[XR];
+      // `row` counts k rows (0, 4, 8) relative to xp
+      auto load_x = [&](int row, XV (&dst)[XR]) {
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) dst[kk] = *reinterpret_cast<const XV*>(xp + (row + kk) * ROWB);
+        for (int kk = 0; kk < XR; ++kk) dst[kk] = *reinterpret_cast<const XV*>(xp + (row / KP + kk) * ROWB);
       };
-      auto contract = [&](const float (&qq)[16], const XV (&xx)[4]) -> uint32_t {
+      auto contract = [&](const float (&qq)[16], const XV (&xx)[XR]) -> uint32_t {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           pf2 xv[KT];
@@ -347,14 +367,15 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
             xv[0] = pk(xx[kk].x, xx[kk].y);
             xv[1] = pk(xx[kk].z, xx[kk].w);
           } else {
-            xv[0] = pk(xx[kk].x, xx[kk].y);
+            if constexpr (KP == 2) xv[0] = (kk & 1) ? pk(xx[kk / 2].z, xx[kk / 2].w) : pk(xx[kk / 2].x, xx[kk / 2].y);
+            else xv[0] = pk(xx[kk].x, xx[kk].y);
           }
 #pragma unroll
           for (int q = 0; q < KT; ++q)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qq[4 * kk + jj]), acc[q][jj]);
         }
-        return __float_as_uint(xx[3].x);
+        return __float_as_uint(xx[XR - 1].x);
       };
       constexpr int NQ = 2 * KT;
       const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
@@ -374,7 +395,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         tmem_ld16(tlane + 16 * (2 * u + 2), qa);
         load_x(8, xa);
         contract(qb, xb);
-        xp += 8 * ROWB;
+        xp += (8 / KP) * ROWB;
         if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
         else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
       }
@@ -399,7 +420,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
           tmem_ld16(tlane + 16 * (kc + 2), qa);
           load_x(8, xa);
           contract(qb, xb);
-          xp += 8 * ROWB;
+          xp += (8 / KP) * ROWB;
         }
         {  // kc == 30: chunk 31 is the last one in TMEM, chunk 32 the first of the tail (CG > 32)
           tmem_wait_ld();
@@ -410,7 +431,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
           lds_q(0, qa);
           load_x(8, xa);
           contract(qb, xb);
-          xp += 8 * ROWB;
+          xp += (8 / KP) * ROWB;
           kc += 2;
         }
         for (; kc + 2 <= CG; kc += 2) {
@@ -422,7 +443,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
             load_x(8, xa);
           }
           contract(qb, xb);
-          xp += 8 * ROWB;
+          xp += (8 / KP) * ROWB;
           qp += 8 * (HYB_LD * 4);
         }
         if (kc < CG) contract(qa, xa);
@@ -438,7 +459,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
             load_x(8, xa);
           }
           contract(qb, xb);
-          xp += 8 * ROWB;
+          xp += (8 / KP) * ROWB;
         }
         if (kc < CG) {
           tmem_wait_ld();

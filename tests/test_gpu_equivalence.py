@@ -1,0 +1,28 @@
+"""Production (Philox) mode against the UNMODIFIED reference on ALL 300 bundled BoxQP instances
+(BASELINE.json configs[1], SURVEY.md 8d "statistical-equivalence gate"): B = 1000, T = 1500, the
+parameter keys of the reference's examples.  The reference's success fractions were recorded on the
+CPU by tests/golden/make_equivalence.py (two seeds: the second calibrates the gate with the
+reference's own seed-to-seed spread); the engine runs here through solve_many."""
+import json
+import os
+
+import pytest
+
+from tools import equivalence_gpu as G
+
+pytestmark = pytest.mark.gpu
+
+REF = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "equivalence_ref.json")))
+SOLVERS = [s for s in ("mf", "langevin", "pumped_langevin", "dl") if f"{s}/seed0/70" in REF]
+
+
+@pytest.mark.parametrize("name", SOLVERS)
+def test_statistically_equivalent_on_bundled_instances(name):
+    meta = REF["_meta"]
+    rows = G.run_engine(name, meta["keys"][name], meta["post_processor"][name], seed=0, batch=meta["batch"])
+    g = G.gate(REF, name, rows, meta["batch"])
+    e = g["engine_vs_ref"]
+    assert e["reject_rate"] <= g["max_reject"], (name, e["rejects"], e["cells"], g["max_reject"])
+    assert e["pooled_ok"], (name, e["pooled_worst_z"], e["pooled"])
+    assert e["best_mismatch"] <= g["max_best_mismatch"], (name, e["best_mismatch"], g["max_best_mismatch"])
+    assert g["pass"]

@@ -11,8 +11,11 @@ Gate (per solver):
     rejection rate) of the 300 x 7 cells may reject;
   * per size and threshold: the pooled success fraction (50 instances x B) must lie within the
     two-sample 95 % interval of the pooled reference fraction (Bonferroni over the 42 cells);
-  * where both hit the `optimal` bucket, best objective values agree within 1e-4 relative.
-The reference's seed 0 vs seed 1 results go through the same tests: that is the calibration.
+  * where both hit the `optimal` bucket, best objective values agree within 1e-4 relative on all but
+    (the reference's own seed-to-seed disagreements + 3) instances -- the bucket is 0.1 % wide, so two
+    runs can legitimately end in different near-optimal vertices.
+With two reference seeds on record the reference side is their union (2 x B trajectories); seed 0
+vs seed 1 goes through the same tests: that is the calibration.
 """
 import argparse
 import json
@@ -28,7 +31,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 SIZES = (20, 30, 40, 50, 60, 70)
 THRESH = ("optimal", "one_percent", "two_percent", "three_percent", "four_percent", "five_percent", "ten_percent")
 Z95 = 1.959964
-Z_BONF42 = 3.04   # two-sided 95 % over 42 (size, threshold) cells
+Z_BONF42 = 3.24   # two-sided 95 % over 42 (size, threshold) cells: Phi^-1(1 - 0.025/42)
 
 
 def load_bundled(device="cuda"):
@@ -70,8 +73,10 @@ def run_engine(name, key, post, seed, batch, chunk=50):
     return rows
 
 
-def compare(a, b, batch):
-    """Gate statistics between two result sets {n: rows}; returns a dict (see module docstring)."""
+def compare(a, b, batch_a, batch_b=None):
+    """Gate statistics between two result sets {n: rows} drawn with `batch_a` / `batch_b` trajectories
+    per instance; returns a dict (see module docstring)."""
+    batch_b = batch_b or batch_a
     cells = rejects = 0
     pooled = []
     best_bad = best_cmp = 0
@@ -79,14 +84,14 @@ def compare(a, b, batch):
     for n in SIZES:
         ra, rb = np.asarray(a[n], dtype=np.float64), np.asarray(b[n], dtype=np.float64)
         pa, pb = ra[:, :7], rb[:, :7]
-        pm = (pa + pb) / 2
-        se = np.sqrt(np.maximum(pm * (1 - pm), 0.0) * 2 / batch)
-        # +0.5/batch: both fractions are rounded to 4 dp by the reference (solution.py:118)
-        rej = np.abs(pa - pb) > Z95 * se + 0.5 / batch
+        pm = (pa * batch_a + pb * batch_b) / (batch_a + batch_b)
+        se = np.sqrt(np.maximum(pm * (1 - pm), 0.0) * (1.0 / batch_a + 1.0 / batch_b))
+        # +0.5/batch: the fractions are rounded to 4 dp by the reference (solution.py:118)
+        rej = np.abs(pa - pb) > Z95 * se + 0.5 / batch_a
         cells += rej.size
         rejects += int(rej.sum())
         # pooled over the 50 instances of this size (variance = sum of the per-instance binomials)
-        var = (pa * (1 - pa) + pb * (1 - pb)).sum(axis=0) / batch / pa.shape[0] ** 2
+        var = (pa * (1 - pa) / batch_a + pb * (1 - pb) / batch_b).sum(axis=0) / pa.shape[0] ** 2
         diff = pa.mean(axis=0) - pb.mean(axis=0)
         zs = np.abs(diff) / np.sqrt(np.maximum(var, 1e-12))
         worst_pool = max(worst_pool, float(zs.max()))
@@ -101,17 +106,39 @@ def compare(a, b, batch):
             "best_compared": best_cmp, "best_mismatch": best_bad}
 
 
+def merge_seeds(r0, r1):
+    """Two reference runs of the same instances as one run with twice the trajectories: success
+    fractions averaged, best objective = the better of the two."""
+    out = {}
+    for n in SIZES:
+        a, b = np.asarray(r0[n], dtype=np.float64), np.asarray(r1[n], dtype=np.float64)
+        m = (a + b) / 2
+        m[:, 7] = np.maximum(a[:, 7], b[:, 7])
+        out[n] = m.tolist()
+    return out
+
+
 def gate(ref, name, engine_rows, batch):
+    """Engine (one run of `batch` trajectories per instance) against the reference.  With two
+    reference seeds on record the reference is their union (2 x batch trajectories: half the
+    sampling noise on that side) and seed 0 vs seed 1 is reported as the calibration: the
+    reference's own rejection rate, pooled z and best-objective disagreements under the same tests."""
     ref0 = {n: ref[f"{name}/seed0/{n}"] for n in SIZES}
-    out = {"engine_vs_ref": compare(engine_rows, ref0, batch)}
+    out = {}
     if f"{name}/seed1/{SIZES[-1]}" in ref:
         ref1 = {n: ref[f"{name}/seed1/{n}"] for n in SIZES}
+        out["engine_vs_ref"] = compare(engine_rows, merge_seeds(ref0, ref1), batch, 2 * batch)
         out["ref_seed0_vs_seed1"] = compare(ref1, ref0, batch)
+        out["engine_vs_ref_seed0"] = compare(engine_rows, ref0, batch)
         out["engine_vs_ref_seed1"] = compare(engine_rows, ref1, batch)
-    cal = out.get("ref_seed0_vs_seed1", {}).get("reject_rate", 0.0)
+    else:
+        out["engine_vs_ref"] = compare(engine_rows, ref0, batch)
+    cal = out.get("ref_seed0_vs_seed1", {})
     e = out["engine_vs_ref"]
-    out["max_reject"] = 0.05 + cal
-    out["pass"] = bool(e["reject_rate"] <= out["max_reject"] and e["pooled_ok"] and e["best_mismatch"] == 0)
+    out["max_reject"] = 0.05 + cal.get("reject_rate", 0.0)
+    out["max_best_mismatch"] = cal.get("best_mismatch", 0) + 3
+    out["pass"] = bool(e["reject_rate"] <= out["max_reject"] and e["pooled_ok"]
+                       and e["best_mismatch"] <= out["max_best_mismatch"])
     return out
 
 

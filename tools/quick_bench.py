@@ -53,13 +53,18 @@ def main():
             E.solve(sid, alg, q, v, args.batch, args.iters, seed=1, offset=w, **kw)
             torch.cuda.synchronize()
             w += 1
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        # per-launch events, median: a sporadic host-side stall (allocator growth, module loading)
+        # in one launch must not leak into a kernel number
+        per = []
         for r in range(args.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             outs, _ = E.solve(sid, alg, q, v, args.batch, args.iters, seed=1, offset=10 + r, **kw)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.reps
+            e1.record()
+            torch.cuda.synchronize()
+            per.append(e0.elapsed_time(e1))
+        per.sort()
+        ms = per[len(per) // 2]
         steps = args.batch * args.iters / (ms * 1e-3)
         m = 2 if sid == nat.SOLVER_DL else 1
         tflops = steps * 2 * m * args.n ** 2 / 1e12
