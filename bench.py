@@ -350,6 +350,7 @@ def run_gpu_arm(args):
                          "algorithmic_flops_per_launch": flops_per_launch},
             "cpu_baseline": cpu_baseline,
             "wall_s_timed_region": wall,
+            "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(np.max(step_ms)),
         }
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)

@@ -200,16 +200,24 @@ struct TmemPlan {
 enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2, PATH_TC = 3, PATH_HYB = 4 };
 
 // tcgen05 3xTF32 drift (sde_kernel_tc.cuh) where batch x N x N is a genuine dense GEMM:
-// n >= 256 and at least 1024 contraction rows (8 CTAs of 128 rows); CCVM_TC=0 / 1 overrides the
-// size rule (experiments and tests), evolution sampling stays on the SIMT path.
+// n > 256 and at least 1024 contraction rows (8 CTAs of 128 rows).  n = 256 itself is also served by
+// the hybrid SIMT kernel, which keeps all SMs busy at small batches: measured crossover at ~10k rows
+// (one tensor-core iteration of a 128-row CTA takes ~34 us at n = 256, latency-bound with a single
+// output chunk; one hybrid wave of 1184 trajectories 4-7 us).  CCVM_TC=0 / 1 / 2 overrides the size
+// rule (experiments and tests), evolution sampling stays on the SIMT path.
+static bool tc_size_rule(const ccvm_solve_desc& d) {
+  const long long rows = (long long)d.batch * (d.solver == CCVM_SOLVER_DL ? 2 : 1);
+  if (d.n > 256) return rows >= 1024;
+  return d.n == 256 && rows >= 10240;
+}
+
 static bool tc_eligible(const ccvm_solve_desc& d) {
   if (d.n > TC_MAX_CHUNKS * TC_BN || d.evolution_step > 0) return false;
-  const long long rows = (long long)d.batch * (d.solver == CCVM_SOLVER_DL ? 2 : 1);
   if (const char* e = getenv("CCVM_TC")) {
-    if (e[0] == 'a') return d.n >= 256 && rows >= 1024;  // "auto"
+    if (e[0] == 'a') return tc_size_rule(d);  // "auto"
     return atoi(e) != 0;  // 0: never, 1 / 2: always (1 = single-CTA kernel, 2 = CTA-pair kernel)
   }
-  return d.n >= 256 && rows >= 1024;
+  return tc_size_rule(d);
 }
 
 static int choose_path(const ccvm_solve_desc& d) {

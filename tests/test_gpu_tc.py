@@ -29,9 +29,13 @@ def test_path_selection(monkeypatch):
     monkeypatch.delenv("CCVM_TC", raising=False)
     assert _launch_info(nat.SOLVER_DL, 1024, 8192)["threads"] == TC_THREADS      # config 4
     assert _launch_info(nat.SOLVER_DL, 1024, 8192)["ctas"] == 128
-    assert _launch_info(nat.SOLVER_LANGEVIN, 256, 1024)["threads"] == TC_THREADS
-    assert _launch_info(nat.SOLVER_DL, 256, 512)["threads"] == TC_THREADS        # 1024 rows
-    assert _launch_info(nat.SOLVER_LANGEVIN, 256, 512)["threads"] != TC_THREADS  # too few rows: SIMT
+    assert _launch_info(nat.SOLVER_LANGEVIN, 320, 1024)["threads"] == TC_THREADS
+    assert _launch_info(nat.SOLVER_DL, 320, 512)["threads"] == TC_THREADS        # 1024 rows
+    assert _launch_info(nat.SOLVER_LANGEVIN, 320, 512)["threads"] != TC_THREADS  # too few rows: SIMT
+    # n = 256 is also within reach of the hybrid SIMT kernel: tensor cores only from ~10k rows
+    assert _launch_info(nat.SOLVER_DL, 256, 8192)["threads"] == TC_THREADS
+    assert _launch_info(nat.SOLVER_LANGEVIN, 256, 8192)["threads"] != TC_THREADS
+    assert _launch_info(nat.SOLVER_DL, 256, 1024)["threads"] != TC_THREADS
     assert _launch_info(nat.SOLVER_DL, 250, 8192)["threads"] != TC_THREADS       # n < 256: SIMT
     assert _launch_info(nat.SOLVER_DL, 70, 4096)["threads"] != TC_THREADS
     monkeypatch.setenv("CCVM_TC", "0")
