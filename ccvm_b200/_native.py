@@ -24,7 +24,7 @@ EXPORTS = (
     "ccvm_postprocess_adam", "ccvm_solution_stats", "ccvm_scaling_factor", "ccvm_solve_host",
     "ccvm_microbench_fp32", "ccvm_query_launch", "ccvm_abi_version", "ccvm_last_error",
     "ccvm_eval_hook", "ccvm_change_variables", "ccvm_fit_to_constraints", "ccvm_scale_coefs",
-    "ccvm_solve_batch", "ccvm_solution_stats_batch", "ccvm_generate_boxqp",
+    "ccvm_solve_batch", "ccvm_solution_stats_batch", "ccvm_generate_boxqp", "ccvm_microbench_tf32",
 )
 
 _fp = C.c_void_p  # device / host pointers travel as plain addresses
@@ -105,6 +105,7 @@ def load():
     lib.ccvm_solve_host.argtypes = [C.POINTER(SolveDesc), C.POINTER(EpilogueDesc), _fp, _fp, C.c_double,
                                     _fp, _fp, _fp]
     lib.ccvm_microbench_fp32.argtypes = [C.c_int32, C.POINTER(C.c_double), _fp]
+    lib.ccvm_microbench_tf32.argtypes = [C.c_int32, C.POINTER(C.c_double), _fp]
     lib.ccvm_query_launch.argtypes = [C.POINTER(SolveDesc), C.POINTER(C.c_int32)]
     lib.ccvm_eval_hook.argtypes = [C.POINTER(HookDesc), _fp]
     lib.ccvm_change_variables.argtypes = [_fp, _fp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,

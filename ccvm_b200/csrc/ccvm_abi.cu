@@ -1368,6 +1368,110 @@ extern "C" int ccvm_microbench_fp32(int32_t mode, double* tflops, void* stream) 
   return CCVM_OK;
 }
 
+// ------------------------------------------------------------------ tensor-pipe probe
+// Roofline denominator of the tcgen05 path ("measure dense TF32 peak on the box"):
+// every CTA (or CTA pair) issues back-to-back tcgen05.mma kind::tf32 of the shape the SDE kernel
+// uses (M = 128 per CTA, N = 256, K = 8) on operands that stay in shared memory, alternating two
+// TMEM accumulators -- no loads, no epilogue.  What it reports is the rate at which the tensor pipe
+// retires this instruction, i.e. the ceiling of sde_tc_kernel (cta_group::1) and sde_tc2_kernel
+// (cta_group::2); three MMAs make one logical 3xTF32 product.
+template <int PAIR>
+__device__ __forceinline__ void tf32_probe_body(int iters) {
+  extern __shared__ __align__(1024) uint8_t probe_smem[];
+  __shared__ __align__(8) unsigned long long done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t base = (smem_u32(probe_smem) + 1023u) & ~1023u;
+  // A: 128 rows x 32 floats (16 KB), B: 256 (single CTA) or 128 (pair: this CTA's half) rows x 32 floats
+  constexpr int B_ROWS = PAIR ? 128 : 256;
+  float* tiles = reinterpret_cast<float*>(probe_smem + (base - smem_u32(probe_smem)));
+  for (int i = tid; i < (128 + B_ROWS) * 32; i += blockDim.x) tiles[i] = 1.0f / (float)(1 + (i & 7));
+  uint32_t rank = 0;
+  if (PAIR) rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(smem_u32(&done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      tmem_alloc(&tmem_slot, 512);
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy tile writes -> tensor-core reads
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  if (tid == 32 && rank == 0) {
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) |
+                               ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
+    const uint32_t a0 = base, b0 = base + 128 * 32 * 4;
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t d = tmem_base + (uint32_t)(it & 1) * 256u;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = umma_desc_sw128(a0 + ks * 32), bd = umma_desc_sw128(b0 + ks * 32);
+        if (PAIR) umma_tf32_pair(d, ad, bd, idesc, (it > 1 || ks > 0) ? 1u : 0u);
+        else umma_tf32(d, ad, bd, idesc, (it > 1 || ks > 0) ? 1u : 0u);
+      }
+    }
+    if (PAIR) umma_commit_pair(smem_u32(&done_bar)); else umma_commit(smem_u32(&done_bar));
+  }
+  mbar_wait(smem_u32(&done_bar), 0u);
+  tc_fence_after();
+  tc_fence_before();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 0) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else tmem_free(tmem_base, 512);
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) tf32_probe_kernel(int iters) { tf32_probe_body<0>(iters); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) tf32_probe_pair_kernel(int iters) {
+  tf32_probe_body<1>(iters);
+}
+
+extern "C" int ccvm_microbench_tf32(int32_t mode, double* tflops, void* stream) {
+  if (!tflops || (mode != 1 && mode != 2)) return fail(CCVM_E_INVALID, "bad argument to ccvm_microbench_tf32");
+  DeviceInfo di;
+  int rc = device_info(di);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int iters = 2048;
+  const int grid = mode == 2 ? (di.sms / 2) * 2 : di.sms;
+  const size_t smem = 1024 + (size_t)(128 + (mode == 2 ? 128 : 256)) * 32 * 4;
+  if (mode == 1) CUDA_TRY(cudaFuncSetAttribute(tf32_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  else CUDA_TRY(cudaFuncSetAttribute(tf32_probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    if (mode == 1) tf32_probe_kernel<<<grid, 128, smem, st>>>(iters);
+    else tf32_probe_pair_kernel<<<grid, 128, smem, st>>>(iters);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    // MMAs per launch x flops per MMA (pair: M = 256 per instruction, one instruction per two CTAs)
+    const double mmas = (double)(mode == 2 ? grid / 2 : grid) * iters * 4.0;
+    const double flops = mmas * 2.0 * (mode == 2 ? 256.0 : 128.0) * 256.0 * 8.0;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return CCVM_OK;
+}
+
 // ------------------------------------------------------------------ operator hooks
 // One thread per output element, arithmetic in the reference's fp32 operation order
 // (host scalars are folded in fp64 first, exactly as Python does before they meet a tensor).

@@ -286,6 +286,15 @@ def microbench_fp32(mode=1):
     return val.value
 
 
+def microbench_tf32(mode=2):
+    """Measured dense TF32 tensor-pipe throughput in TFLOP/s of the tcgen05.mma shape the SDE kernels
+    use (1 = cta_group::1, 2 = cta_group::2): the roofline denominator of the tensor-core path."""
+    nat.require_cuda()
+    val = C.c_double(0.0)
+    nat.check(nat.load().ccvm_microbench_tf32(int(mode), C.byref(val), nat.current_stream_ptr()))
+    return val.value
+
+
 def to_engine_device(t):
     """Tensors handed to a kernel must be on a CUDA device; CPU tensors are copied to the current
     one (plumbing).  Without a GPU this raises -- there is no CPU implementation to fall back to."""

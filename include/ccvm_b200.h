@@ -275,6 +275,12 @@ int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue_desc* epi,
  * writes achieved TFLOP/s. */
 int ccvm_microbench_fp32(int32_t mode, double* tflops, void* stream);
 
+/* Roofline denominator of the tensor-core path, no reference counterpart: measured rate of
+ * back-to-back tcgen05.mma kind::tf32 (M = 128 per CTA, N = 256, K = 8, operands resident in
+ * shared memory, FP32 accumulators in TMEM) over all SMs, in dense TF32 TFLOP/s.
+ * mode 1: cta_group::1, mode 2: cta_group::2 (CTA pairs).  Synchronises the stream. */
+int ccvm_microbench_tf32(int32_t mode, double* tflops, void* stream);
+
 /* Query the launch geometry ccvm_solve would use: fills threads per CTA, CTAs, trajectories per
  * CTA, dynamic shared memory bytes, registers per thread.  For reports and tests. */
 int ccvm_query_launch(const ccvm_solve_desc* desc, int32_t* info5);

@@ -311,3 +311,13 @@ def test_device_instance_generator():
     solver.parameter_key = {40: dict(dt=0.002, S=0.5, sigma=0.5, feedback_scale=1.0, iterations=50)}
     sol = solver(instance=inst, post_processor="grad-descent")
     assert torch.isfinite(sol.objective_values).all()
+
+
+def test_roofline_probes():
+    """The two roofline denominators (bench.py, tools/tensor_peak.py) land where a B200 can be:
+    FP32 FFMA2 near 148 x 128 x 2 x f, dense TF32 tcgen05 between half and all of the nominal 1.19 PFLOP/s."""
+    assert 55.0 < E.microbench_fp32(1) < 80.0
+    assert 55.0 < E.microbench_fp32(0) < 80.0
+    for mode in (1, 2):
+        tf = E.microbench_tf32(mode)
+        assert 600.0 < tf < 1300.0, (mode, tf)
