@@ -74,3 +74,68 @@ def test_merge_without_process_group():
     best, idx, tot, vec = P.merge_results(P.pack_local_result(e, x, [1, 2, 3, 4, 5, 6, 7], 10))
     assert best.item() == 2.0 and idx.item() == 11 and tot.tolist() == [1, 2, 3, 4, 5, 6, 7]
     assert torch.equal(vec, x[1])
+
+
+class _FakeSolution:
+    def __init__(self, name, n):
+        self.best_index = n % 7
+        self._md = {"instance_name": name, "problem_size": n, "best_objective_value": float(n) * 1.5,
+                    "solve_time": 1e-6 * n, "batch_size": 10}
+
+    def get_metadata_dict(self):
+        return dict(self._md)
+
+
+class _FakeInstance:
+    def __init__(self, k):
+        self.name, self.problem_size = f"inst{k}", 10 + k
+
+
+class _FakeSolver:
+    """Stands in for a CCVMSolver on a machine without a GPU: records which instances it was given."""
+
+    def __init__(self):
+        self.seen = []
+
+    def __call__(self, instance, post_processor=None, **kw):
+        self.seen.append(instance.name)
+        return _FakeSolution(instance.name, instance.problem_size)
+
+    def solve_many(self, instances, post_processor=None, **kw):
+        return [self(instance=i, post_processor=post_processor) for i in instances]
+
+
+def _sweep_worker(rank, world, port, count, chunk, out):
+    from ccvm_b200 import sweep
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        solver = _FakeSolver()
+        built = []
+
+        def get(k):
+            built.append(k)
+            return _FakeInstance(k)
+
+        md = sweep.solve_sweep(solver, (count, get), post_processor="grad-descent", chunk=chunk)
+        out[rank] = (md, list(solver.seen), sorted(set(built)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("chunk", [1, 3])
+def test_instance_sweep_shards_round_robin_and_gathers_in_order(chunk):
+    world, count = 2, 9
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sweep_worker, args=(world, _free_port(), count, chunk, out), nprocs=world, join=True)
+    for rank in range(world):
+        md, seen, built = out[rank]
+        # every rank ends with ALL records, in instance order, each stamped with its owner
+        assert [r["index"] for r in md] == list(range(count))
+        assert [r["instance_name"] for r in md] == [f"inst{k}" for k in range(count)]
+        assert [r["rank"] for r in md] == [k % world for k in range(count)]
+        assert all(r["best_index"] == (10 + r["index"]) % 7 for r in md)
+        # ... but only built and solved its own share
+        mine = [k for k in range(count) if k % world == rank]
+        assert built == mine and seen == [f"inst{k}" for k in mine]
