@@ -148,6 +148,11 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   uint32_t& tmem_slot = *tmem_slot_p;
   const int tid = threadIdx.x;
   constexpr bool HAS_TMEM = QSRC != QSRC_GMEM;
+  // DL + Adam is the one tile at the edge of the register file (2 quadratures x (state, m, v) x 4
+  // columns: ~245 registers): ptxas schedules it measurably better (3.69 vs 3.90 ms at N = 70) with
+  // the padding-column noise masked and the contraction tail left inside the loop -- the two
+  // simplifications every other tile gains 5-13 % from.
+  constexpr bool DENSE_TILE = SOLVER == SOLVER_DL && ADAM;
   // compile-time panel stride (0: run time)
   constexpr int XSC = !PIPE ? 0
                       : QSRC == QSRC_TMEM ? TMEM_PIPE_XS
@@ -261,10 +266,13 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     float n0, n1, n2, n3;
     box_muller(r.x, r.y, n0, n1);
     box_muller(r.z, r.w, n2, n3);
+    // Padding columns (j >= n) draw noise like any other: their state stays finite (zero drift, the
+    // solver's own saturating terms / a zero clamp), it only ever meets the zero rows of Qs and is
+    // never written out -- masking it cost a SEL per normal.
     const float nn[4] = {n0, n1, n2, n3};
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      const float w = colok[jj] ? nn[jj] : 0.f;
+      const float w = (DENSE_TILE && !colok[jj]) ? 0.f : nn[jj];
       if (i) Wd[q][jj].y = w; else Wd[q][jj].x = w;
     }
   };
@@ -448,22 +456,47 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         }
         if (kc < CG) contract(qa, xa);
       } else {
-        for (; kc + 2 <= CG; kc += 2) {
+        // steady state: both prefetches unconditional; the last one or two chunks are peeled off
+        if constexpr (DENSE_TILE) {
+          for (; kc + 2 <= CG; kc += 2) {
+            tmem_wait_ld();
+            tmem_ld16(tlane + 16 * (kc + 1), qb);
+            load_x(4, xb);
+            contract(qa, xa);
+            tmem_wait_ld();
+            if (kc + 2 < CG) {
+              tmem_ld16(tlane + 16 * (kc + 2), qa);
+              load_x(8, xa);
+            }
+            contract(qb, xb);
+            xp += (8 / KP) * ROWB;
+          }
+          if (kc < CG) {
+            tmem_wait_ld();
+            contract(qa, xa);
+          }
+        } else {
+        for (; kc + 2 < CG; kc += 2) {
           tmem_wait_ld();
           tmem_ld16(tlane + 16 * (kc + 1), qb);
           load_x(4, xb);
           contract(qa, xa);
           tmem_wait_ld();
-          if (kc + 2 < CG) {
-            tmem_ld16(tlane + 16 * (kc + 2), qa);
-            load_x(8, xa);
-          }
+          tmem_ld16(tlane + 16 * (kc + 2), qa);
+          load_x(8, xa);
           contract(qb, xb);
           xp += (8 / KP) * ROWB;
         }
-        if (kc < CG) {
-          tmem_wait_ld();
+        tmem_wait_ld();
+        if (kc + 2 == CG) {
+          tmem_ld16(tlane + 16 * (kc + 1), qb);
+          load_x(4, xb);
           contract(qa, xa);
+          tmem_wait_ld();
+          contract(qb, xb);
+        } else {
+          contract(qa, xa);
+        }
         }
       }
     } else {
