@@ -442,19 +442,24 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
           xp += (8 / KP) * ROWB;
           kc += 2;
         }
-        for (; kc + 2 <= CG; kc += 2) {
+        for (; kc + 2 < CG; kc += 2) {  // steady state; the last one or two chunks are peeled off
           lds_q(4, qb);
           load_x(4, xb);
           contract(qa, xa);
-          if (kc + 2 < CG) {
-            lds_q(8, qa);
-            load_x(8, xa);
-          }
+          lds_q(8, qa);
+          load_x(8, xa);
           contract(qb, xb);
           xp += (8 / KP) * ROWB;
           qp += 8 * (HYB_LD * 4);
         }
-        if (kc < CG) contract(qa, xa);
+        if (kc + 2 == CG) {
+          lds_q(4, qb);
+          load_x(4, xb);
+          contract(qa, xa);
+          contract(qb, xb);
+        } else {
+          contract(qa, xa);
+        }
       } else {
         // steady state: both prefetches unconditional; the last one or two chunks are peeled off
         if constexpr (DENSE_TILE) {
@@ -579,17 +584,24 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         }
         kc = 2 * NQ;
       }
-      for (; kc + 2 <= CG; kc += 2) {
+      for (; kc + 2 < CG; kc += 2) {  // steady state; the last one or two chunks are peeled off
         wait_chunk();
         load_chunk(kc + 1, qb);
         contract4(qa);
         wait_chunk();
-        if (kc + 2 < CG) load_chunk(kc + 2, qa);
+        load_chunk(kc + 2, qa);
         contract4(qb);
       }
       if (kc < CG) {
         wait_chunk();
-        contract4(qa);
+        if (kc + 2 == CG) {
+          load_chunk(kc + 1, qb);
+          contract4(qa);
+          wait_chunk();
+          contract4(qb);
+        } else {
+          contract4(qa);
+        }
       }
     }
 
