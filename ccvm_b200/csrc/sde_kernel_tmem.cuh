@@ -153,6 +153,11 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   // the padding-column noise masked and the contraction tail left inside the loop -- the two
   // simplifications every other tile gains 5-13 % from.
   constexpr bool DENSE_TILE = SOLVER == SOLVER_DL && ADAM;
+  // Tiles whose drift-independent update math is evaluated inside the contraction (`precompute`):
+  // chosen by measurement at N = 70 / 128 / 250 -- DL 3.23 -> 3.15 ms, Langevin + Adam 2.12 -> 2.02,
+  // PumpedLangevin + Adam 2.17 -> 2.10; neutral or slower for the others (ptxas gives up FFMA2
+  // overlap elsewhere), which keep the whole step after the contraction.
+  constexpr bool HOIST = PIPE && ((SOLVER == SOLVER_DL && !ADAM) || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM));
   // compile-time panel stride (0: run time)
   constexpr int XSC = !PIPE ? 0
                       : QSRC == QSRC_TMEM ? TMEM_PIPE_XS
@@ -351,6 +356,53 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     for (int q = 0; q < KT; ++q)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) acc[q][jj] = dup(hreg[jj]);
+    // PIPE: everything of the SDE step that does not depend on the drift is evaluated INSIDE the
+    // contraction (called right after the unrolled noise chunks, i.e. in their straight-line block,
+    // where ptxas interleaves it with the FFMA2 stream): the state arrays then hold the step's
+    // drift-free part and what is left after the last FFMA2 is one FFMA2 per element pair (plus
+    // Adam, which needs the finished gradient) -- the latency-bound tail between contraction and
+    // barrier shrinks to almost nothing, and the noise registers die before the run-time loop.
+    auto precompute = [&]() {
+      if constexpr (SOLVER == SOLVER_DL) {
+        const pf2 d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
+        const pf2 mdt = dup(-p.dt), half = dup(0.5f);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const pf2 c = st[0][jj], s = st[1][jj];
+          const pf2 r2 = fma2(c, c, mul2(s, s));
+          const pf2 rt = sqrt2(add2(r2, half));
+          const pf2 uc = fma2(r2, mdt, d1), us = fma2(r2, mdt, d2);
+          st[0][jj] = add2(c, fma2(c, uc, mul2(mul2(rt, n1), W[0][jj])));
+          st[1][jj] = add2(s, fma2(s, us, mul2(mul2(rt, n2), W[1][jj])));
+        }
+      } else if constexpr (SOLVER == SOLVER_MF) {
+        const pf2 pr = dup(ca.y), sj = dup(ca.w), opj = dup(cb.x), m2j = dup(-2.f * ca.z);
+        const pf2 g2 = dup(p.g2), dtp = dup(p.dt), mhalf = dup(-0.5f);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const pf2 mu = st[0][jj], sg = st[1][jj];
+          const pf2 g2m2 = mul2(mul2(mu, mu), g2);
+          const pf2 a1 = fma2(g2m2, dup(-1.f), pr);
+          const pf2 sh = add2(sg, mhalf);
+          const pf2 diff = mul2(mul2(sh, sj), W[0][jj]);
+          st[0][jj] = fma2(dtp, fma2(a1, mu, diff), mu);
+          const pf2 a3 = fma2(g2m2, dup(-3.f), pr);
+          const pf2 t1 = mul2(mul2(a3, sg), dup(2.f));
+          const pf2 t2 = mul2(mul2(sh, sh), m2j);
+          const pf2 t3 = fma2(g2m2, dup(2.f), opj);
+          st[1][jj] = fma2(dtp, add2(add2(t1, t2), t3), sg);
+        }
+      } else {
+        const pf2 sig = dup(p.sig), mdt = dup(-p.dt), d1 = dup(ca.y);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const pf2 c = st[0][jj];
+          pf2 pre = fma2(sig, W[0][jj], c);
+          if constexpr (SOLVER == SOLVER_PLV) pre = fma2(c, fma2(mul2(c, c), mdt, d1), pre);
+          st[0][jj] = pre;
+        }
+      }
+    };
     if constexpr (XSC != 0) {
       // TMEM + PIPE: the Q chunk AND the four state rows it meets are both fetched one chunk ahead
       // into ping-pong registers (tcgen05.ld / LDS in flight under the previous chunk's FFMA2s);
@@ -407,6 +459,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
         else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
       }
+      if constexpr (HOIST) precompute();
       kc = 2 * NQ;
       if constexpr (QSRC == QSRC_HYB) {
         // chunks 2*NQ .. 31 from TMEM; the last prefetch of this part already comes from the tail
@@ -582,6 +635,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
           if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
           else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
         }
+        if constexpr (HOIST) precompute();
         kc = 2 * NQ;
       }
       for (; kc + 2 < CG; kc += 2) {  // steady state; the last one or two chunks are peeled off
@@ -614,6 +668,13 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       }
       const pf2 gain = dup(ca.x), d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
       const pf2 mdt = dup(-p.dt), half = dup(0.5f);
+      if constexpr (HOIST) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          st[0][jj] = fma2(gain, acc[0][jj], st[0][jj]);
+          st[1][jj] = fma2(gain, acc[1][jj], st[1][jj]);
+        }
+      } else
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const pf2 c = st[0][jj], s = st[1][jj];
@@ -633,6 +694,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       if constexpr (ADAM) adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
       const pf2 pr = dup(ca.y), sj = dup(ca.w), opj = dup(cb.x), m2j = dup(-2.f * ca.z);
       const pf2 g2 = dup(p.g2), dtp = dup(p.dt), mhalf = dup(-0.5f);
+      if constexpr (HOIST) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) st[0][jj] = fma2(dtp, acc[0][jj], st[0][jj]);
+      } else
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const pf2 mu = st[0][jj], sg = st[1][jj];
@@ -664,6 +729,11 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       if constexpr (!PIPE) draw(t);
       if constexpr (ADAM) adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
       const pf2 dtfs = dup(p.dtfs), sig = dup(p.sig), mdt = dup(-p.dt), d1 = dup(ca.y);
+      if constexpr (HOIST) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          st[0][jj] = clamp2(fma2(dtfs, acc[0][jj], st[0][jj]), -sclamp[jj], sclamp[jj]);
+      } else
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const pf2 c = st[0][jj];
