@@ -226,8 +226,8 @@ def run_gpu_arm(args):
         nat.check(lib.ccvm_solution_stats(en.data_ptr(), BATCH, 0.0, res.data_ptr(), stream.cuda_stream))
         launches["n"] += 4
         if distributed:
-            rec = P.pack_local_result(en, pv, res[2:9].to(torch.float32), traj_base)
-            return P.merge_results(rec)
+            launches["n"] += 2
+            return P.merge_results(P.pack_from_stats(res, pv, traj_base))
         return res
 
     # context pre-warm (not a step): module loading and the SM clock ramp of a fresh process take

@@ -25,6 +25,7 @@ EXPORTS = (
     "ccvm_microbench_fp32", "ccvm_query_launch", "ccvm_abi_version", "ccvm_last_error",
     "ccvm_eval_hook", "ccvm_change_variables", "ccvm_fit_to_constraints", "ccvm_scale_coefs",
     "ccvm_solve_batch", "ccvm_solution_stats_batch", "ccvm_generate_boxqp", "ccvm_microbench_tf32",
+    "ccvm_pack_record", "ccvm_merge_records",
 )
 
 _fp = C.c_void_p  # device / host pointers travel as plain addresses
@@ -106,6 +107,8 @@ def load():
                                     _fp, _fp, _fp]
     lib.ccvm_microbench_fp32.argtypes = [C.c_int32, C.POINTER(C.c_double), _fp]
     lib.ccvm_microbench_tf32.argtypes = [C.c_int32, C.POINTER(C.c_double), _fp]
+    lib.ccvm_pack_record.argtypes = [_fp, _fp, C.c_int32, C.c_int64, _fp, _fp]
+    lib.ccvm_merge_records.argtypes = [_fp, C.c_int32, C.c_int32, _fp, _fp]
     lib.ccvm_query_launch.argtypes = [C.POINTER(SolveDesc), C.POINTER(C.c_int32)]
     lib.ccvm_eval_hook.argtypes = [C.POINTER(HookDesc), _fp]
     lib.ccvm_change_variables.argtypes = [_fp, _fp, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,

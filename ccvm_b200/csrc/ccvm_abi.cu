@@ -1176,6 +1176,65 @@ extern "C" int ccvm_solution_stats(const float* energy, int32_t batch, double op
   return CCVM_OK;
 }
 
+// ------------------------------------------------------- multi-GPU result records
+// One record per rank: [min energy, global trajectory index of the winner, 7 success counters,
+// winner's solution vector (n)] -- written by ONE kernel from the statistics block of
+// ccvm_solution_stats, all-gathered by the host layer, and reduced by ONE kernel on every rank
+// (ties go to the lowest rank, a NaN objective wins like torch.max(-E) propagates it).
+__global__ void pack_record_kernel(const StatsOut* __restrict__ stats, const float* __restrict__ pv, int n,
+                                   long long traj_base, float* __restrict__ rec) {
+  const int arg = stats->arg_best;
+  if (threadIdx.x == 0) {
+    rec[0] = -stats->best;
+    rec[1] = (float)(traj_base + arg);
+  }
+  if (threadIdx.x < 7) rec[2 + threadIdx.x] = (float)stats->counts[threadIdx.x];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) rec[9 + j] = pv[(size_t)arg * n + j];
+}
+
+__global__ void merge_records_kernel(const float* __restrict__ gathered, int world, int n, float* __restrict__ out) {
+  __shared__ int s_owner;
+  const int len = 9 + n;
+  if (threadIdx.x == 0) {
+    int owner = 0;
+    float best = gathered[0];
+    for (int r = 1; r < world && !(best != best); ++r) {
+      const float e = gathered[(size_t)r * len];
+      if (e != e || e < best) {
+        best = e;
+        owner = r;
+      }
+    }
+    s_owner = owner;
+    out[0] = -best;
+    out[1] = gathered[(size_t)owner * len + 1];
+  }
+  if (threadIdx.x < 7) {
+    float tot = 0.f;
+    for (int r = 0; r < world; ++r) tot += gathered[(size_t)r * len + 2 + threadIdx.x];
+    out[2 + threadIdx.x] = tot;
+  }
+  __syncthreads();
+  const float* src = gathered + (size_t)s_owner * len + 9;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) out[9 + j] = src[j];
+}
+
+extern "C" int ccvm_pack_record(const void* stats, const float* problem_variables, int32_t n, int64_t traj_base,
+                                float* record, void* stream) {
+  if (!stats || !problem_variables || !record || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_pack_record");
+  pack_record_kernel<<<1, 128, 0, (cudaStream_t)stream>>>((const StatsOut*)stats, problem_variables, n,
+                                                          (long long)traj_base, record);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+extern "C" int ccvm_merge_records(const float* gathered, int32_t world_size, int32_t n, float* merged, void* stream) {
+  if (!gathered || !merged || world_size < 1 || n < 1) return fail(CCVM_E_INVALID, "bad argument to ccvm_merge_records");
+  merge_records_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(gathered, world_size, n, merged);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
 // -------------------------------------------------------------------- scaling factor
 __global__ void __launch_bounds__(1024) scaling_factor_kernel(const float* __restrict__ q, int nn, float mult,
                                                               float* out) {

@@ -42,6 +42,18 @@ def pack_local_result(energy, problem_variables, counts, traj_base):
     return rec
 
 
+def pack_from_stats(stats, problem_variables, traj_base):
+    """Device-side ``pack_local_result``: ONE kernel builds the record from the 9-word block that
+    ``ccvm_solution_stats`` wrote (best, argmin, 7 counters) and the local solution matrix."""
+    from . import _native as nat
+    n = problem_variables.shape[1]
+    rec = torch.empty(2 + N_COUNTS + n, dtype=torch.float32, device=problem_variables.device)
+    with torch.cuda.device(rec.device):
+        nat.check(nat.load().ccvm_pack_record(stats.data_ptr(), problem_variables.data_ptr(), int(n), int(traj_base),
+                                              rec.data_ptr(), nat.current_stream_ptr(rec.device)))
+    return rec
+
+
 def merge_results(record, group=None):
     """All-gather the per-rank records and reduce them identically on every rank.
 
@@ -54,6 +66,15 @@ def merge_results(record, group=None):
         flat = torch.empty(world * record.numel(), dtype=record.dtype, device=record.device)
         dist.all_gather_into_tensor(flat, record.contiguous(), group=group)
         gathered = flat.view(world, record.numel())
+    if gathered.is_cuda:
+        # one kernel instead of half a dozen small torch launches per step
+        from . import _native as nat
+        n = record.numel() - 2 - N_COUNTS
+        out = torch.empty_like(record)
+        with torch.cuda.device(record.device):
+            nat.check(nat.load().ccvm_merge_records(gathered.data_ptr(), int(gathered.shape[0]), int(n), out.data_ptr(),
+                                                    nat.current_stream_ptr(record.device)))
+        return out[0], out[1], out[2:2 + N_COUNTS], out[2 + N_COUNTS:]
     owner = torch.argmin(gathered[:, 0])
     best = -gathered[owner, 0]
     counts = gathered[:, 2:2 + N_COUNTS].sum(dim=0)

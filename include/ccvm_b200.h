@@ -195,6 +195,20 @@ int ccvm_solution_stats_batch(const float* energy, const int64_t* offsets,
                               const float* optimal_values, int32_t count, void* result,
                               void* stream);
 
+/*
+ * Multi-GPU result records (no reference counterpart: the reference is single-device).
+ * ccvm_pack_record: from the 9-word block written by ccvm_solution_stats and the local solution
+ *   matrix problem_variables[batch][n], writes record[9 + n] (device floats):
+ *   [min energy, traj_base + local argmin, 7 success counters, the winner's solution vector].
+ * ccvm_merge_records: reduces world_size such records (gathered[world_size][9 + n], e.g. the output
+ *   of an all-gather) to merged[9 + n] = [best objective = max(-E), global index of the winner,
+ *   summed counters, winner's vector]; ties go to the lowest rank, NaN propagates.
+ */
+int ccvm_pack_record(const void* stats, const float* problem_variables, int32_t n, int64_t traj_base,
+                     float* record, void* stream);
+int ccvm_merge_records(const float* gathered, int32_t world_size, int32_t n, float* merged,
+                       void* stream);
+
 /* Replaces CCVMSolver.get_scaling_factor (solvers/ccvm_solver.py:134-150):
  *   *out (device float) = sqrt(sum |Q_ij|) * multiplier. */
 int ccvm_scaling_factor(const float* q, int32_t n, double multiplier, float* out, void* stream);

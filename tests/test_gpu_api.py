@@ -321,3 +321,44 @@ def test_roofline_probes():
     for mode in (1, 2):
         tf = E.microbench_tf32(mode)
         assert 600.0 < tf < 1300.0, (mode, tf)
+
+
+def test_device_record_pack_and_merge_match_host_logic():
+    """ccvm_pack_record / ccvm_merge_records (one kernel each) against the torch restatement in
+    ccvm_b200/parallel.py that the gloo tests pin on CPU."""
+    from ccvm_b200 import parallel as P, _native as nat
+    torch.manual_seed(3)
+    n, b = 37, 501
+    recs_dev, recs_ref = [], []
+    for r in range(4):
+        en = torch.randn(b, device="cuda") * 5 - 100
+        if r == 2:
+            en[17] = en.min() - 1.0          # rank 2 holds the global winner ...
+        if r == 3:
+            en[5] = en[5]                    # (no tie here; ties are checked below)
+        pv = torch.rand(b, n, device="cuda")
+        res = torch.empty(9, dtype=torch.int32, device="cuda")
+        nat.check(nat.load().ccvm_solution_stats(en.data_ptr(), b, 95.0, res.data_ptr(), nat.current_stream_ptr()))
+        counts = res[2:9].to(torch.float32)
+        ref = P.pack_local_result(en, pv, counts, 1000 * r)
+        dev = P.pack_from_stats(res, pv, 1000 * r)
+        assert torch.equal(ref, dev)
+        recs_dev.append(dev)
+        recs_ref.append(ref.cpu())
+    gathered = torch.stack(recs_dev).contiguous()
+    out = torch.empty_like(recs_dev[0])
+    nat.check(nat.load().ccvm_merge_records(gathered.data_ptr(), 4, n, out.data_ptr(), nat.current_stream_ptr()))
+    g = torch.stack(recs_ref)
+    owner = int(torch.argmin(g[:, 0]))
+    assert owner == 2
+    assert out[0].item() == -g[owner, 0].item() and out[1].item() == g[owner, 1].item() == 2017.0
+    assert torch.equal(out[2:9].cpu(), g[:, 2:9].sum(dim=0))
+    assert torch.equal(out[9:].cpu(), g[owner, 9:])
+    # ties go to the lowest rank
+    gathered[3, 0] = gathered[2, 0]
+    gathered[1, 0] = gathered[2, 0]
+    nat.check(nat.load().ccvm_merge_records(gathered.data_ptr(), 4, n, out.data_ptr(), nat.current_stream_ptr()))
+    assert out[1].item() == gathered[1, 1].item()
+    # merge_results on a CUDA record without a process group = identity reduction of one record
+    best, idx, counts, vec = P.merge_results(recs_dev[0])
+    assert best.item() == -recs_dev[0][0].item() and torch.equal(vec, recs_dev[0][9:])
