@@ -273,8 +273,11 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   // fixed-stride panels of the K = 1 solvers in the hybrid kernel hold two k rows per panel row
   // (sde_kernel_tmem.cuh, KP)
   const int kp = (fixed_xs && K == 1 && path == PATH_HYB) ? 2 : 1;
+  // DL + Adam parks its second moments in shared memory (sde_kernel_tmem.cuh, VSMEM): 64 B per thread
+  const size_t vsm = (fixed_xs && path == PATH_TMEM && d.solver == CCVM_SOLVER_DL && d.algorithm == CCVM_ALG_ADAM)
+                         ? (size_t)256 * 16 : 0;  // floats
   auto smem_of = [&](int xs_) {
-    return ((size_t)2 * np + (size_t)ng * 2 * (np / kp) * xs_ + tail) * sizeof(float);
+    return ((size_t)2 * np + (size_t)ng * 2 * (np / kp) * xs_ + tail + vsm) * sizeof(float);
   };
   const int pipe_xs = path == PATH_HYB ? HYB_PIPE_XS : TMEM_PIPE_XS;
   if (fixed_xs && (RW * kp * rg > pipe_xs || smem_of(pipe_xs) > (size_t)di.max_smem))

@@ -149,15 +149,24 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   const int tid = threadIdx.x;
   constexpr bool HAS_TMEM = QSRC != QSRC_GMEM;
   // DL + Adam is the one tile at the edge of the register file (2 quadratures x (state, m, v) x 4
-  // columns: ~245 registers): ptxas schedules it measurably better (3.69 vs 3.90 ms at N = 70) with
-  // the padding-column noise masked and the contraction tail left inside the loop -- the two
-  // simplifications every other tile gains 5-13 % from.
-  constexpr bool DENSE_TILE = SOLVER == SOLVER_DL && ADAM;
+  // columns: ~245 registers): without the relief below ptxas schedules it measurably better (3.69 vs
+  // 3.90 ms at N = 70) with the padding-column noise masked and the contraction tail left inside the
+  // loop -- the two simplifications every other tile gains 5-13 % from (DENSE_TILE, kept for the
+  // hybrid / streamed / replay variants of this tile).
+  constexpr bool DL_ADAM = SOLVER == SOLVER_DL && ADAM;
+  // DL + Adam (production kernel, n <= 128): the Adam second moments are parked in shared memory
+  // between iterations (4 LDS.128 + 4 STS.128 per thread and iteration, conflict-free).  That takes
+  // the tile from 245 to 240 live registers at its peak and, more to the point, lets ptxas keep the
+  // peeled / unmasked / hoisted code shape of the other loops: 3.73 -> 3.59 ms at N = 70.  Each of
+  // the three changes alone, or any two of them, made this tile slower (3.82-4.04 ms); parking the
+  // first moments as well gave the gain back (3.74 ms).
+  constexpr bool VSMEM = DL_ADAM && PIPE && QSRC == QSRC_TMEM;
+  constexpr bool DENSE_TILE = DL_ADAM && !VSMEM;
   // Tiles whose drift-independent update math is evaluated inside the contraction (`precompute`):
   // chosen by measurement at N = 70 / 128 / 250 -- DL 3.23 -> 3.15 ms, Langevin + Adam 2.12 -> 2.02,
   // PumpedLangevin + Adam 2.17 -> 2.10; neutral or slower for the others (ptxas gives up FFMA2
   // overlap elsewhere), which keep the whole step after the contraction.
-  constexpr bool HOIST = PIPE && ((SOLVER == SOLVER_DL && !ADAM) || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM));
+  constexpr bool HOIST = PIPE && ((SOLVER == SOLVER_DL && !ADAM) || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM) || VSMEM);
   // compile-time panel stride (0: run time)
   constexpr int XSC = !PIPE ? 0
                       : QSRC == QSRC_TMEM ? TMEM_PIPE_XS
@@ -175,6 +184,8 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   float* av = hv + NP;                                // [NP]
   float* X = av + NP + (size_t)grp * 2 * PR * XS;     // this group's [2][PR][XS] panel
   float* qtail = av + NP + (size_t)L.ng * 2 * PR * XS;  // QSRC_HYB: Qs rows 128 .. NP-1, [NP - 128][HYB_LD]
+  // VSMEM: Adam second moments of the DL tile, [4 slots][256 threads] float4 (conflict-free), after the panels
+  float4* vsm = reinterpret_cast<float4*>(av + NP + (size_t)L.ng * 2 * PR * XS) + (tid & 255);
 
   // ------------------------------------------------------------------ prologue
   if (HAS_TMEM && warp == 0) tmem_alloc(&tmem_slot, L.tcols);
@@ -198,6 +209,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   }
   if (!idle)
     for (int i = lg; i < 2 * PR * XS; i += L.gt) X[i] = 0.f;
+  if constexpr (VSMEM) {
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) vsm[sl * 256] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   const int rg = l % RG, cg = l / RG;
   const bool active = cg < CG;
@@ -663,8 +678,25 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     if constexpr (SOLVER == SOLVER_DL) {
       if constexpr (!PIPE) draw(t);
       if constexpr (ADAM) {
+        if constexpr (VSMEM) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float4 tv = vsm[(q * 2 + h) * 256];
+              avv[q][2 * h] = pk(tv.x, tv.y);
+              avv[q][2 * h + 1] = pk(tv.z, tv.w);
+            }
+        }
         adam_tile4(acc[0], am[0], avv[0], p, cb.y, cb.z);
         adam_tile4(acc[1], am[1], avv[1], p, cb.y, cb.z);
+        if constexpr (VSMEM) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              vsm[(q * 2 + h) * 256] = make_float4(avv[q][2 * h].x, avv[q][2 * h].y, avv[q][2 * h + 1].x, avv[q][2 * h + 1].y);
+        }
       }
       const pf2 gain = dup(ca.x), d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
       const pf2 mdt = dup(-p.dt), half = dup(0.5f);
