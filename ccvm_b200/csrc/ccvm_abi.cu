@@ -333,9 +333,9 @@ __global__ void scale_q_kernel(const float* __restrict__ q, const float* __restr
   qs[idx] = val;
 }
 
-template <int SOLVER, bool ADAM, int QSRC, bool PIPE>
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
 static int launch_tmem_variant(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC, PIPE>;
+  auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC, PIPE, CGC>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
   CUDA_TRY(cudaGetLastError());
@@ -345,6 +345,23 @@ static int launch_tmem_variant(const SdeParams& p, const TmemPlan& P, cudaStream
 template <int SOLVER, bool ADAM>
 static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
   const bool pipe = P.L.pipe != 0;
+  // Column-group counts of the reference's benchmarking sizes (N = 40, 50, 60, 70; examples/
+  // benchmarking_instances/Size*) compiled in for the tiles that gain from a fully unrolled
+  // contraction with immediate addresses (measured at N = 70: MF 2.05 -> 1.87 ms, MF + Adam 2.11 -> 2.01,
+  // Langevin + Adam 2.03 -> 1.82, PumpedLangevin + Adam 2.11 -> 1.93; DL, DL + Adam, Langevin and
+  // PumpedLangevin are neutral or slower and keep the run-time loop).
+  constexpr bool CGC_TILE = SOLVER == SOLVER_MF || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM);
+  if constexpr (CGC_TILE) {
+    if (P.qsrc == QSRC_TMEM && pipe) {
+      switch (P.cg) {
+        case 10: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 10>(p, P, st);
+        case 13: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 13>(p, P, st);
+        case 15: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 15>(p, P, st);
+        case 18: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 18>(p, P, st);
+        default: break;
+      }
+    }
+  }
   if (P.qsrc == QSRC_TMEM)
     return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true>(p, P, st)
                 : launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, false>(p, P, st);

@@ -137,7 +137,7 @@ __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4]
 // issue slot free); the ALU / MUFU work and the dependent IMAD.WIDE chain of the generator fill
 // those slots, and the latency-bound phase between contraction and barrier shrinks to the SDE
 // update itself (profiles/r1_ncu_sde_dl_tmem_v3.txt: FMA pipe 73 % busy, 27 % bubbles, before).
-template <int SOLVER, bool ADAM, int QSRC, bool PIPE>
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
 __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaunch& L, const int cta, float* smem,
                                               uint32_t* tmem_slot_p) {
   constexpr int K = SolverTraits<SOLVER>::K;
@@ -172,7 +172,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
                       : QSRC == QSRC_TMEM ? TMEM_PIPE_XS
                       : QSRC == QSRC_HYB ? HYB_PIPE_XS : 0;
   constexpr int KP = (XSC != 0 && KT == 1 && QSRC == QSRC_HYB) ? 2 : 1;  // k rows per panel row (see HYB_PIPE_XS)
-  const int N = p.n, CG = p.cg, NP = 4 * CG, RG = L.rg, XS = XSC ? XSC : L.xs, T = p.iterations;
+  const int N = p.n, CG = CGC ? CGC : p.cg, NP = 4 * CG, RG = L.rg, XS = XSC ? XSC : L.xs, T = p.iterations;
   const int PR = NP / KP;                            // panel rows per buffer
   const bool idle = tid >= L.ng * L.gt;
   const int grp = idle ? 0 : tid / L.gt, lg = tid - grp * L.gt;
@@ -549,6 +549,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
             contract(qa, xa);
           }
         } else {
+#pragma unroll(CGC ? 32 : 1)
         for (; kc + 2 < CG; kc += 2) {
           tmem_wait_ld();
           tmem_ld16(tlane + 16 * (kc + 1), qb);
@@ -832,12 +833,12 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   }
 }
 
-template <int SOLVER, bool ADAM, int QSRC, bool PIPE>
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
 __global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
     sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
   extern __shared__ __align__(16) float smem[];
   __shared__ uint32_t tmem_slot;
-  sde_tile_body<SOLVER, ADAM, QSRC, PIPE>(p, L, blockIdx.x, smem, &tmem_slot);
+  sde_tile_body<SOLVER, ADAM, QSRC, PIPE, CGC>(p, L, blockIdx.x, smem, &tmem_slot);
 }
 
 // PIPE needs Philox noise and more than 4*K chunks of four Q rows (DL: n >= 33, others: n >= 17).
