@@ -486,7 +486,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
             dst[4 * kk] = v.x; dst[4 * kk + 1] = v.y; dst[4 * kk + 2] = v.z; dst[4 * kk + 3] = v.w;
           }
         };
-#pragma unroll 1
+#pragma unroll((SOLVER == SOLVER_DL && !ADAM) ? 1 : 4)
         for (; kc + 2 < HYB_TMEM_CHUNKS; kc += 2) {
           tmem_wait_ld();
           tmem_ld16(tlane + 16 * (kc + 1), qb);
@@ -510,6 +510,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
           xp += (8 / KP) * ROWB;
           kc += 2;
         }
+#pragma unroll((SOLVER == SOLVER_DL && !ADAM) ? 1 : 4)
         for (; kc + 2 < CG; kc += 2) {  // steady state; the last one or two chunks are peeled off
           lds_q(4, qb);
           load_x(4, xb);
