@@ -194,6 +194,7 @@ static int regs_one() {
 struct TmemPlan {
   TmemLaunch L;
   int cg, threads, ctas, qsrc;
+  int cgc;  // column-group count compiled into the kernel variant to launch (0: run-time loop)
   size_t smem;
 };
 
@@ -229,9 +230,15 @@ static int choose_path(const ccvm_solve_desc& d) {
   return PATH_GMEM;
 }
 
+// tiles that have compile-time column-group variants (launch_tmem): MF, and Langevin / PumpedLangevin + Adam
+static bool cgc_tile(int solver, bool adam) {
+  return solver == CCVM_SOLVER_MF || ((solver == CCVM_SOLVER_LANGEVIN || solver == CCVM_SOLVER_PUMPED_LANGEVIN) && adam);
+}
+
 // `share_hint` > 0 overrides the trajectories-per-SM estimate (batched launches plan every
 // instance against the load of the whole batch, not its own).
-static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, TmemPlan& P, int share_hint = 0) {
+static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, TmemPlan& P, int share_hint = 0,
+                     bool batched = false) {
   const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1, RW = 2 * K;
   const int cg = (d.n + 3) / 4, np = 4 * cg;
   const bool tm = path == PATH_TMEM || path == PATH_HYB;    // Q slices (partly) TMEM resident
@@ -272,6 +279,8 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   const bool fixed_xs = pipe && tm;  // compile-time panel stride, no row rotation
   // fixed-stride panels of the K = 1 solvers in the hybrid kernel hold two k rows per panel row
   // (sde_kernel_tmem.cuh, KP)
+  const bool cgc_variant = !batched && fixed_xs && path == PATH_TMEM && cgc_tile(d.solver, d.algorithm == CCVM_ALG_ADAM) &&
+                           (cg == 10 || cg == 13 || cg == 15 || cg == 18);
   const int kp = (fixed_xs && K == 1 && path == PATH_HYB) ? 2 : 1;
   // DL + Adam parks its second moments in shared memory (sde_kernel_tmem.cuh, VSMEM): 64 B per thread
   const size_t vsm = (fixed_xs && path == PATH_TMEM && d.solver == CCVM_SOLVER_DL && d.algorithm == CCVM_ALG_ADAM)
@@ -313,6 +322,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   if (const char* e = getenv("CCVM_PHASE_NS")) P.L.phase_ns = atoi(e);
   P.qsrc = path == PATH_TMEM ? QSRC_TMEM : path == PATH_HYB ? QSRC_HYB : QSRC_GMEM;
   P.cg = cg;
+  P.cgc = cgc_variant ? cg : 0;
   P.threads = ng * P.L.gt;
   P.ctas = (d.batch + ng * 2 * rg - 1) / (ng * 2 * rg);
   P.smem = smem_of(xs);
@@ -353,7 +363,7 @@ static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
   constexpr bool CGC_TILE = SOLVER == SOLVER_MF || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM);
   if constexpr (CGC_TILE) {
     if (P.qsrc == QSRC_TMEM && pipe) {
-      switch (P.cg) {
+      switch (P.cgc) {
         case 10: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 10>(p, P, st);
         case 13: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 13>(p, P, st);
         case 15: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 15>(p, P, st);
@@ -805,7 +815,7 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
   const int share = (int)((total_traj + di.sms - 1) / di.sms);
   for (size_t b = 0; b < batched.size(); ++b) {
     const ccvm_solve_desc& d = descs[batched[b]];
-    if ((rc = plan_tmem(d, di, choose_path(d), plans[b], share))) return rc;
+    if ((rc = plan_tmem(d, di, choose_path(d), plans[b], share, true))) return rc;
     jobs[b].a = sched_args(&d);
     jobs[b].offset = rows;
     rows += d.iterations;
