@@ -362,3 +362,23 @@ def test_device_record_pack_and_merge_match_host_logic():
     # merge_results on a CUDA record without a process group = identity reduction of one record
     best, idx, counts, vec = P.merge_results(recs_dev[0])
     assert best.item() == -recs_dev[0][0].item() and torch.equal(vec, recs_dev[0][9:])
+
+
+@pytest.mark.parametrize("n,b", [(1, 3), (5, 17), (33, 129), (70, 1000), (129, 40), (250, 333), (300, 50), (600, 9)])
+@pytest.mark.parametrize("pp", [None, "grad-descent"])
+def test_tiled_epilogue_matches_per_trajectory_kernel(monkeypatch, n, b, pp):
+    """The tiled epilogue (8 trajectories share every Q element) against the per-trajectory kernel it
+    replaced (CCVM_EPILOGUE_LEGACY): identical dot-product order, so the post-processed variables
+    are bit-identical; the energy differs only by the association of its final sum."""
+    torch.manual_seed(n + b)
+    q0, v0 = O.synthetic_boxqp(n, 2)
+    f = O.scaling_factor(q0, 0.05)
+    q, v = (q0 / f).cuda(), (v0 / f).cuda()
+    state = (torch.rand(b, n, device="cuda") - 0.5)
+    kw = dict(map1=(1.0, 0.5), post_processor=pp, pp_iterations=10, map2=(0.5, 0.25), scaled_by=float(f))
+    monkeypatch.delenv("CCVM_EPILOGUE_LEGACY", raising=False)
+    pv_t, e_t = E.epilogue(state, q, v, **kw)
+    monkeypatch.setenv("CCVM_EPILOGUE_LEGACY", "1")
+    pv_l, e_l = E.epilogue(state, q, v, **kw)
+    assert torch.equal(pv_t, pv_l)
+    assert torch.allclose(e_t, e_l, rtol=2e-6, atol=1e-5 * float(e_l.abs().max()))
