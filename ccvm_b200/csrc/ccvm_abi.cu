@@ -67,6 +67,22 @@ static int device_info(DeviceInfo& di) {
   return CCVM_OK;
 }
 
+// Stream-ordered scratch that is returned on EVERY exit path of an entry point (an early CUDA_TRY
+// return must not leak it into the pool for the life of the process).
+struct StreamBuf {
+  void* p = nullptr;
+  cudaStream_t st;
+  explicit StreamBuf(cudaStream_t s) : st(s) {}
+  StreamBuf(const StreamBuf&) = delete;
+  StreamBuf& operator=(const StreamBuf&) = delete;
+  ~StreamBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 // ------------------------------------------------------------------- schedule builder
 // The reference evaluates its per-iteration schedules (pump ramp, noise-ratio decay,
 // measurement-strength decay, Adam bias corrections) as fp64 host scalars
@@ -489,8 +505,9 @@ static int solve_tc(const ccvm_solve_desc* d, SdeParams& p, cudaStream_t st) {
   plan_tc(*d, P);
   const size_t plane = (size_t)P.rows_p * P.np;
   const size_t floats = 4 * plane + (size_t)P.n_aux * plane + 2 * (size_t)P.np * P.np + 2 * (size_t)P.np;
-  float* scratch = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&scratch, floats * sizeof(float), st));
+  StreamBuf scratch_buf(st);
+  CUDA_TRY(scratch_buf.alloc(floats * sizeof(float)));
+  float* scratch = scratch_buf.as<float>();
   TcParams tc;
   tc.xh = scratch;
   tc.xl = tc.xh + 2 * plane;
@@ -535,7 +552,6 @@ static int solve_tc(const ccvm_solve_desc* d, SdeParams& p, cudaStream_t st) {
       default: rc = launch_tc<SOLVER_PLV, true>(p, tc, P, M, st); break;
     }
   }
-  cudaFreeAsync(scratch, st);
   return rc;
 }
 
@@ -722,8 +738,9 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const bool adam = d->algorithm == CCVM_ALG_ADAM;
 
-  float* sched = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&sched, (size_t)d->iterations * SCHED_W * sizeof(float), st));
+  StreamBuf sched_buf(st), qs_buf(st);
+  CUDA_TRY(sched_buf.alloc((size_t)d->iterations * SCHED_W * sizeof(float)));
+  float* sched = sched_buf.as<float>();
   const SchedArgs sa = sched_args(d);
   build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(sa, sched);
   CUDA_TRY(cudaGetLastError());
@@ -734,15 +751,14 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
   p.xs = L.xs;
   p.use_tma = L.use_tma;
   if (path == PATH_TC) {
-    rc = solve_tc(d, p, st);
-    cudaFreeAsync(sched, st);
-    return rc;
+    return solve_tc(d, p, st);
   }
 
   float* qs_scratch = nullptr;
   if (use_tmem && TP.qsrc == QSRC_GMEM) {
     const int np = 4 * TP.cg;
-    CUDA_TRY(cudaMallocAsync((void**)&qs_scratch, (size_t)np * np * sizeof(float), st));
+    CUDA_TRY(qs_buf.alloc((size_t)np * np * sizeof(float)));
+    qs_scratch = qs_buf.as<float>();
     scale_q_kernel<<<(np * np + 255) / 256, 256, 0, st>>>(p.q, p.drift_s_vec, p.drift_s, p.a_half, p.n, np, qs_scratch);
     CUDA_TRY(cudaGetLastError());
     TP.L.qs = qs_scratch;
@@ -769,11 +785,7 @@ extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
     case 6: rc = launch_tb<SOLVER_PLV, false>(p, L, st); break;
     default: rc = launch_tb<SOLVER_PLV, true>(p, L, st); break;
   }
-  if (qs_scratch) cudaFreeAsync(qs_scratch, st);
-  cudaError_t fe = cudaFreeAsync(sched, st);
-  if (rc) return rc;
-  if (fe != cudaSuccess) return fail(CCVM_E_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(fe));
-  return CCVM_OK;
+  return rc;
 }
 
 
@@ -825,8 +837,11 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
   SchedJob* d_jobs = nullptr;
   BatchItem* d_items = nullptr;
   int2* d_map = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&sched, (size_t)rows * SCHED_W * sizeof(float), st));
-  CUDA_TRY(cudaMallocAsync((void**)&d_jobs, jobs.size() * sizeof(SchedJob), st));
+  StreamBuf sched_buf(st), jobs_buf(st), items_buf(st), map_buf(st);
+  CUDA_TRY(sched_buf.alloc((size_t)rows * SCHED_W * sizeof(float)));
+  CUDA_TRY(jobs_buf.alloc(jobs.size() * sizeof(SchedJob)));
+  sched = sched_buf.as<float>();
+  d_jobs = jobs_buf.as<SchedJob>();
   CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(SchedJob), cudaMemcpyHostToDevice, st));
   build_schedule_batch_kernel<<<dim3((max_t + 127) / 128, (unsigned)jobs.size()), 128, 0, st>>>(d_jobs, sched);
   CUDA_TRY(cudaGetLastError());
@@ -849,8 +864,10 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
   }
   size_t total_ctas = 0;
   for (int k = 0; k < NB; ++k) total_ctas += maps[k].size();
-  CUDA_TRY(cudaMallocAsync((void**)&d_items, items.size() * sizeof(BatchItem), st));
-  CUDA_TRY(cudaMallocAsync((void**)&d_map, total_ctas * sizeof(int2), st));
+  CUDA_TRY(items_buf.alloc(items.size() * sizeof(BatchItem)));
+  CUDA_TRY(map_buf.alloc(total_ctas * sizeof(int2)));
+  d_items = items_buf.as<BatchItem>();
+  d_map = map_buf.as<int2>();
   CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(BatchItem), cudaMemcpyHostToDevice, st));
   size_t off = 0;
   const bool adam = alg == CCVM_ALG_ADAM;
@@ -882,10 +899,6 @@ extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, voi
     if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(CCVM_E_CUDA, "batched launch failed");
     off += n;
   }
-  cudaFreeAsync(d_map, st);
-  cudaFreeAsync(d_items, st);
-  cudaFreeAsync(d_jobs, st);
-  cudaFreeAsync(sched, st);
   return rc;
 }
 
@@ -1523,8 +1536,9 @@ extern "C" int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue
   const size_t n = solve->n, b = solve->batch;
   if (solve->n < 1 || solve->batch < 1) return fail(CCVM_E_INVALID, "n and batch must be >= 1");
   const size_t words = n * n + n + 3 * b * n + b * n + b + 16;
-  float* buf = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&buf, words * sizeof(float), st));
+  StreamBuf host_buf(st);
+  CUDA_TRY(host_buf.alloc(words * sizeof(float)));
+  float* buf = host_buf.as<float>();
   float* d_q = buf;
   float* d_v = d_q + n * n;
   float* d_o0 = d_v + n;
@@ -1564,7 +1578,6 @@ extern "C" int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue
         (ce = cudaMemcpyAsync(h_stats, d_stats, sizeof(StatsOut), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
       rc = fail(CCVM_E_CUDA, "D2H copy failed: %s", cudaGetErrorString(ce));
   }
-  cudaFreeAsync(buf, st);
   ce = cudaStreamSynchronize(st);
   if (!rc && ce != cudaSuccess) rc = fail(CCVM_E_CUDA, "stream sync failed: %s", cudaGetErrorString(ce));
   return rc;
@@ -1612,8 +1625,9 @@ extern "C" int ccvm_microbench_fp32(int32_t mode, double* tflops, void* stream) 
   int rc = device_info(di);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  float* d = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&d, 64, st));
+  StreamBuf probe_buf(st);
+  CUDA_TRY(probe_buf.alloc(64));
+  float* d = probe_buf.as<float>();
   const int iters = 4096, grid = di.sms * 8, block = 256;
   cudaEvent_t e0, e1;
   CUDA_TRY(cudaEventCreate(&e0));
@@ -1633,7 +1647,6 @@ extern "C" int ccvm_microbench_fp32(int32_t mode, double* tflops, void* stream) 
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  cudaFreeAsync(d, st);
   CUDA_TRY(cudaStreamSynchronize(st));
   *tflops = best;
   return CCVM_OK;
