@@ -38,10 +38,13 @@ def synthetic_instance(n, seed, scaling_multiplier, device="cuda", name=None, on
 
 
 def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=None, gather=True, chunk=1,
-                **call_kwargs):
+                costs=None, **call_kwargs):
     """Solve ``instances`` (a sequence, or a ``(count, index -> instance)`` pair so that ranks only
     build their own) with ``solver``; returns the list of metadata dicts of ALL instances in order
     (on every rank when ``gather``), each extended with ``best_index``, ``rank`` and ``index``.
+
+    ``costs`` (one number per instance, e.g. N^2) switches the placement from round-robin to
+    longest-processing-time first (``parallel.lpt_owners``).
 
     ``chunk`` > 1 solves that many instances of this rank per launch through
     ``CCVMSolver.solve_many`` (one grid over instances x trajectory blocks, one statistics kernel,
@@ -55,7 +58,12 @@ def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=No
     count = instances[0] if isinstance(instances, tuple) else len(instances)
     getter = instances[1] if isinstance(instances, tuple) else instances.__getitem__
     local = {}
-    mine = [k for k in range(count) if parallel.instance_owner(k, world_size) == rank]
+    if costs is not None:
+        # size-aware placement (cost ~ N^2 per instance): longest-processing-time first
+        owners = parallel.lpt_owners(list(costs), world_size)
+        mine = [k for k in range(count) if owners[k] == rank]
+    else:
+        mine = [k for k in range(count) if parallel.instance_owner(k, world_size) == rank]
 
     def record(k, sol):
         rec = sol.get_metadata_dict()

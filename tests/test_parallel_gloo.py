@@ -23,6 +23,19 @@ def test_shard_bounds_cover_everything():
     assert [P.instance_owner(k, 4) for k in range(6)] == [0, 1, 2, 3, 0, 1]
 
 
+def test_lpt_placement_balances_heterogeneous_sweeps():
+    sizes = [20, 250, 30, 240, 40, 230, 50, 220, 60, 210, 70, 200]
+    costs = [n * n for n in sizes]
+    owners = P.lpt_owners(costs, 4)
+    load = [sum(c for c, o in zip(costs, owners) if o == r) for r in range(4)]
+    rr = [sum(c for k, c in enumerate(costs) if k % 4 == r) for r in range(4)]
+    assert sorted(set(owners)) == [0, 1, 2, 3]
+    assert max(load) / (sum(load) / 4) < 1.20            # 6 large instances on 4 ranks: 1.16 is the optimum
+    assert max(rr) / (sum(rr) / 4) > 1.4                 # round-robin is far off on this mix
+    assert P.lpt_owners(costs, 4) == owners              # deterministic: every rank derives the same map
+    assert P.lpt_owners([5.0, 5.0, 5.0], 2) == [0, 1, 0]  # ties: instance order, lowest rank first
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
