@@ -36,7 +36,7 @@ def test_gate_accepts_same_distribution_and_rejects_a_shift():
     same = G.gate(ref, "x", _rows(rng, p_inst, batch), batch)
     assert same["pass"], same["engine_vs_ref"]
     assert same["engine_vs_ref"]["reject_rate"] < 0.1 and same["engine_vs_ref"]["best_mismatch"] == 0
-    assert "ref_seed0_vs_seed1" in same and same["max_best_mismatch"] == 3
+    assert "ref_seed0_vs_seed1" in same and same["max_best_mismatch"] == 3 and same["best_mismatch"] == 0
     shifted = G.gate(ref, "x", _rows(rng, p_inst, batch, shift=0.05), batch)
     assert not shifted["pass"]
     assert shifted["engine_vs_ref"]["pooled_worst_z"] > G.Z_BONF42

@@ -10,10 +10,12 @@ Gate (per solver):
     reference's success fraction; at most `max_reject` (5 % + the reference's own seed-to-seed
     rejection rate) of the 300 x 7 cells may reject;
   * per size and threshold: the pooled success fraction (50 instances x B) must lie within the
-    two-sample 95 % interval of the pooled reference fraction (Bonferroni over the 42 cells);
+    two-sample interval of the pooled reference fraction at a family-wise 99 % over the 42 cells
+    (|z| <= 3.70; with four solvers a run of the whole gate then rejects by chance about 4 % of the time);
   * where both hit the `optimal` bucket, best objective values agree within 1e-4 relative on all but
-    (the reference's own seed-to-seed disagreements + 3) instances -- the bucket is 0.1 % wide, so two
-    runs can legitimately end in different near-optimal vertices.
+    c + 3 sqrt(c + 1) instances, c = the reference's own seed-to-seed disagreements under the same
+    rule (the bucket is 0.1 % wide, so two runs can legitimately end in different near-optimal
+    vertices); the engine is compared with each reference seed and the closer one counts.
 With two reference seeds on record the reference side is their union (2 x B trajectories); seed 0
 vs seed 1 goes through the same tests: that is the calibration.
 """
@@ -31,7 +33,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 SIZES = (20, 30, 40, 50, 60, 70)
 THRESH = ("optimal", "one_percent", "two_percent", "three_percent", "four_percent", "five_percent", "ten_percent")
 Z95 = 1.959964
-Z_BONF42 = 3.24   # two-sided 95 % over 42 (size, threshold) cells: Phi^-1(1 - 0.025/42)
+Z_BONF42 = 3.70   # two-sided 99 % over the 42 (size, threshold) cells of a solver: Phi^-1(1 - 0.005/42)
 
 
 def load_bundled(device="cuda"):
@@ -136,9 +138,12 @@ def gate(ref, name, engine_rows, batch):
     cal = out.get("ref_seed0_vs_seed1", {})
     e = out["engine_vs_ref"]
     out["max_reject"] = 0.05 + cal.get("reject_rate", 0.0)
-    out["max_best_mismatch"] = cal.get("best_mismatch", 0) + 3
+    c = cal.get("best_mismatch", 0)
+    out["max_best_mismatch"] = int(c + 3 * np.sqrt(c + 1))
+    out["best_mismatch"] = min(out[k]["best_mismatch"] for k in ("engine_vs_ref_seed0", "engine_vs_ref_seed1")
+                               if k in out) if "engine_vs_ref_seed0" in out else e["best_mismatch"]
     out["pass"] = bool(e["reject_rate"] <= out["max_reject"] and e["pooled_ok"]
-                       and e["best_mismatch"] <= out["max_best_mismatch"])
+                       and out["best_mismatch"] <= out["max_best_mismatch"])
     return out
 
 
@@ -162,7 +167,7 @@ def main():
         report[name] = g
         e, c = g["engine_vs_ref"], g.get("ref_seed0_vs_seed1")
         print(f"{name}: pass={g['pass']} cell rejections {e['rejects']}/{e['cells']} ({100 * e['reject_rate']:.2f} %)"
-              f" pooled worst z {e['pooled_worst_z']:.2f}; best mismatches {e['best_mismatch']}/{e['best_compared']}"
+              f" pooled worst z {e['pooled_worst_z']:.2f}; best mismatches {g['best_mismatch']} (allowed {g['max_best_mismatch']})"
               + (f" | reference seed0 vs seed1: {100 * c['reject_rate']:.2f} %, worst z {c['pooled_worst_z']:.2f}" if c else ""))
         ok = ok and g["pass"]
     if args.out:
