@@ -287,9 +287,14 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   if (rg < 1) rg = 1;
   if (ng == 2 && !tm && 2 * round32(rg * cg) > max_threads) ng = 1;
   // in-loop noise generation (sde_kernel_tmem.cuh, PIPE): Philox mode with enough Q chunks to hide it in
+  // small compile-time column-group variants (CG = 5, 8: all noise quanta unpinned at the top of the
+  // iteration; every tile has them): single launches on the TMEM path only
+  const bool small_cgc = !batched && path == PATH_TMEM && d.rng_mode == CCVM_RNG_PHILOX && (cg == 5 || cg == 8) &&
+                         getenv("CCVM_NO_SMALLCG") == nullptr;
   const bool pipe = getenv("CCVM_NO_PIPE") == nullptr &&
-                    (d.solver == CCVM_SOLVER_DL ? pipe_ok<SOLVER_DL>(cg, d.rng_mode == CCVM_RNG_PHILOX)
-                                                : pipe_ok<SOLVER_LV>(cg, d.rng_mode == CCVM_RNG_PHILOX));
+                    (small_cgc ||
+                     (d.solver == CCVM_SOLVER_DL ? pipe_ok<SOLVER_DL>(cg, d.rng_mode == CCVM_RNG_PHILOX)
+                                                 : pipe_ok<SOLVER_LV>(cg, d.rng_mode == CCVM_RNG_PHILOX)));
   int xs = 0, xmask = 31;
   const size_t tail = path == PATH_HYB ? (size_t)(np - 4 * HYB_TMEM_CHUNKS) * HYB_LD : 0;  // floats
   const bool fixed_xs = pipe && tm;  // compile-time panel stride, no row rotation
@@ -305,6 +310,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
     return ((size_t)2 * np + (size_t)ng * 2 * (np / kp) * xs_ + tail + vsm) * sizeof(float);
   };
   const int pipe_xs = path == PATH_HYB ? HYB_PIPE_XS : TMEM_PIPE_XS;
+  if (fixed_xs && RW * kp * rg > pipe_xs) rg = pipe_xs / (RW * kp);  // (DL at CG = 5: at most 17 pairs per row)
   if (fixed_xs && (RW * kp * rg > pipe_xs || smem_of(pipe_xs) > (size_t)di.max_smem))
     return fail(CCVM_E_INVALID, "internal: the fixed state-panel stride does not fit (n=%d rg=%d)", d.n, rg);
   for (; !fixed_xs;) {
@@ -338,7 +344,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   if (const char* e = getenv("CCVM_PHASE_NS")) P.L.phase_ns = atoi(e);
   P.qsrc = path == PATH_TMEM ? QSRC_TMEM : path == PATH_HYB ? QSRC_HYB : QSRC_GMEM;
   P.cg = cg;
-  P.cgc = cgc_variant ? cg : 0;
+  P.cgc = (cgc_variant || (small_cgc && pipe)) ? cg : 0;
   P.threads = ng * P.L.gt;
   P.ctas = (d.batch + ng * 2 * rg - 1) / (ng * 2 * rg);
   P.smem = smem_of(xs);
@@ -377,6 +383,10 @@ static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
   // Langevin + Adam 2.03 -> 1.82, PumpedLangevin + Adam 2.11 -> 1.93; DL, DL + Adam, Langevin and
   // PumpedLangevin are neutral or slower and keep the run-time loop).
   constexpr bool CGC_TILE = SOLVER == SOLVER_MF || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM);
+  if (P.qsrc == QSRC_TMEM && pipe) {
+    if (P.cgc == 5) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 5>(p, P, st);
+    if (P.cgc == 8) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 8>(p, P, st);
+  }
   if constexpr (CGC_TILE) {
     if (P.qsrc == QSRC_TMEM && pipe) {
       switch (P.cgc) {

@@ -452,11 +452,25 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         }
         return __float_as_uint(xx[XR - 1].x);
       };
-      constexpr int NQ = 2 * KT;
+      // Small compile-time column-group counts (CG = 5, 8 <-> N = 20, 30): the contraction is too short
+      // to hide a noise quantum per chunk pair -- pinned there, the quanta ran one after the other and
+      // their ~250-cycle dependent chains WERE the iteration.  All of them start at the top instead,
+      // unpinned: ptxas runs the chains side by side under the (fully unrolled) contraction.
+      constexpr bool SMALLCG = CGC != 0 && CGC <= 8;
+      constexpr int NQ = SMALLCG ? 2 : 2 * KT;
       const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
       tmem_ld16(tlane, qa);
       load_x(0, xa);
       int kc = 0;
+      if constexpr (SMALLCG) {
+#pragma unroll
+        for (int q = 0; q < KT; ++q)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if constexpr (SOLVER == SOLVER_MF) quantum(Wn, q, i, tn);
+            else quantum(W, q, i, tn);
+          }
+      }
 #pragma unroll
       for (int u = 0; u < NQ; ++u) {  // CG > 2*NQ: chunks 0 .. 2*NQ exist
         tmem_wait_ld();
@@ -471,8 +485,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         load_x(8, xa);
         contract(qb, xb);
         xp += (8 / KP) * ROWB;
-        if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
-        else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
+        if constexpr (!SMALLCG) {
+          if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
+          else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
+        }
       }
       if constexpr (HOIST) precompute();
       kc = 2 * NQ;
@@ -702,25 +718,15 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
               vsm[(q * 2 + h) * 256] = make_float4(avv[q][2 * h].x, avv[q][2 * h].y, avv[q][2 * h + 1].x, avv[q][2 * h + 1].y);
         }
       }
-      const pf2 gain = dup(ca.x), d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
-      const pf2 mdt = dup(-p.dt), half = dup(0.5f);
-      if constexpr (HOIST) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          st[0][jj] = fma2(gain, acc[0][jj], st[0][jj]);
-          st[1][jj] = fma2(gain, acc[1][jj], st[1][jj]);
-        }
-      } else
+      // every DL variant evaluates the step as  (drift-free part) + gain * drift  with the drift-free
+      // part from `precompute` -- inside the contraction where it is hoisted, here otherwise -- so that
+      // all of them (in-loop noise or not, single or batched launch) round identically
+      if constexpr (!HOIST) precompute();
+      const pf2 gain = dup(ca.x);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const pf2 c = st[0][jj], s = st[1][jj];
-        const pf2 r2 = fma2(c, c, mul2(s, s));
-        const pf2 rt = sqrt2(add2(r2, half));
-        const pf2 uc = fma2(r2, mdt, d1), us = fma2(r2, mdt, d2);
-        const pf2 nc = mul2(mul2(rt, n1), W[0][jj]);
-        const pf2 ns = mul2(mul2(rt, n2), W[1][jj]);
-        st[0][jj] = add2(c, fma2(c, uc, fma2(gain, acc[0][jj], nc)));
-        st[1][jj] = add2(s, fma2(s, us, fma2(gain, acc[1][jj], ns)));
+        st[0][jj] = fma2(gain, acc[0][jj], st[0][jj]);
+        st[1][jj] = fma2(gain, acc[1][jj], st[1][jj]);
       }
       stage(buf ^ 1, st[0], st[1]);
     } else if constexpr (SOLVER == SOLVER_MF) {
