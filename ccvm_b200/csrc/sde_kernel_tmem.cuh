@@ -456,7 +456,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       // to hide a noise quantum per chunk pair -- pinned there, the quanta ran one after the other and
       // their ~250-cycle dependent chains WERE the iteration.  All of them start at the top instead,
       // unpinned: ptxas runs the chains side by side under the (fully unrolled) contraction.
-      constexpr bool SMALLCG = CGC != 0 && CGC <= 8;
+      // The same holds, measured, for the larger compile-time variants up to CG = 13 (N <= 52) and for
+      // the Adam variants of Langevin / PumpedLangevin at every compile-time CG (N = 70: 1.88 -> 1.78 ms);
+      // MF at CG = 15, 18 keeps one pinned quantum per chunk pair (MF + Adam loses 12 % unpinned).
+      constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM));
       constexpr int NQ = SMALLCG ? 2 : 2 * KT;
       const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
       tmem_ld16(tlane, qa);
