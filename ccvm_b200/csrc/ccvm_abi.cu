@@ -246,9 +246,11 @@ static int choose_path(const ccvm_solve_desc& d) {
   return PATH_GMEM;
 }
 
-// tiles that have compile-time column-group variants (launch_tmem): MF, and Langevin / PumpedLangevin + Adam
+// tiles that have compile-time column-group variants (launch_tmem): everything but plain Langevin /
+// PumpedLangevin, which measured neutral or slower with them
 static bool cgc_tile(int solver, bool adam) {
-  return solver == CCVM_SOLVER_MF || ((solver == CCVM_SOLVER_LANGEVIN || solver == CCVM_SOLVER_PUMPED_LANGEVIN) && adam);
+  return solver == CCVM_SOLVER_MF || solver == CCVM_SOLVER_DL ||
+         ((solver == CCVM_SOLVER_LANGEVIN || solver == CCVM_SOLVER_PUMPED_LANGEVIN) && adam);
 }
 
 // `share_hint` > 0 overrides the trajectories-per-SM estimate (batched launches plan every
@@ -290,7 +292,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   // small compile-time column-group variants (CG = 5, 8: all noise quanta unpinned at the top of the
   // iteration; every tile has them): single launches on the TMEM path only
   const bool small_cgc = !batched && path == PATH_TMEM && d.rng_mode == CCVM_RNG_PHILOX && (cg == 5 || cg == 8) &&
-                         getenv("CCVM_NO_SMALLCG") == nullptr;
+                         getenv("CCVM_NO_CGC") == nullptr;
   const bool pipe = getenv("CCVM_NO_PIPE") == nullptr &&
                     (small_cgc ||
                      (d.solver == CCVM_SOLVER_DL ? pipe_ok<SOLVER_DL>(cg, d.rng_mode == CCVM_RNG_PHILOX)
@@ -300,7 +302,8 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   const bool fixed_xs = pipe && tm;  // compile-time panel stride, no row rotation
   // fixed-stride panels of the K = 1 solvers in the hybrid kernel hold two k rows per panel row
   // (sde_kernel_tmem.cuh, KP)
-  const bool cgc_variant = !batched && fixed_xs && path == PATH_TMEM && cgc_tile(d.solver, d.algorithm == CCVM_ALG_ADAM) &&
+  const bool cgc_variant = !batched && fixed_xs && path == PATH_TMEM && getenv("CCVM_NO_CGC") == nullptr &&
+                           cgc_tile(d.solver, d.algorithm == CCVM_ALG_ADAM) &&
                            (cg == 10 || cg == 13 || cg == 15 || cg == 18);
   const int kp = (fixed_xs && K == 1 && path == PATH_HYB) ? 2 : 1;
   // DL + Adam parks its second moments in shared memory (sde_kernel_tmem.cuh, VSMEM): 64 B per thread
@@ -382,7 +385,7 @@ static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
   // contraction with immediate addresses (measured at N = 70: MF 2.05 -> 1.87 ms, MF + Adam 2.11 -> 2.01,
   // Langevin + Adam 2.03 -> 1.82, PumpedLangevin + Adam 2.11 -> 1.93; DL, DL + Adam, Langevin and
   // PumpedLangevin are neutral or slower and keep the run-time loop).
-  constexpr bool CGC_TILE = SOLVER == SOLVER_MF || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM);
+  constexpr bool CGC_TILE = SOLVER == SOLVER_MF || SOLVER == SOLVER_DL || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM);
   if (P.qsrc == QSRC_TMEM && pipe) {
     if (P.cgc == 5) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 5>(p, P, st);
     if (P.cgc == 8) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 8>(p, P, st);

@@ -458,8 +458,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       // unpinned: ptxas runs the chains side by side under the (fully unrolled) contraction.
       // The same holds, measured, for the larger compile-time variants up to CG = 13 (N <= 52) and for
       // the Adam variants of Langevin / PumpedLangevin at every compile-time CG (N = 70: 1.88 -> 1.78 ms);
+      // and for DL / DL + Adam (N = 70: 3.16 -> 3.10 ms, 3.57 -> 3.39 ms);
       // MF at CG = 15, 18 keeps one pinned quantum per chunk pair (MF + Adam loses 12 % unpinned).
-      constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM));
+      constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM) ||
+                                            SOLVER == SOLVER_DL);
       constexpr int NQ = SMALLCG ? 2 : 2 * KT;
       const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
       tmem_ld16(tlane, qa);
