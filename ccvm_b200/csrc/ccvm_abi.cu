@@ -246,11 +246,11 @@ static int choose_path(const ccvm_solve_desc& d) {
   return PATH_GMEM;
 }
 
-// tiles that have compile-time column-group variants (launch_tmem): everything but plain Langevin /
-// PumpedLangevin, which measured neutral or slower with them
+// every tile has compile-time column-group variants (launch_tmem) at the reference's benchmarking sizes
 static bool cgc_tile(int solver, bool adam) {
-  return solver == CCVM_SOLVER_MF || solver == CCVM_SOLVER_DL ||
-         ((solver == CCVM_SOLVER_LANGEVIN || solver == CCVM_SOLVER_PUMPED_LANGEVIN) && adam);
+  (void)solver;
+  (void)adam;
+  return true;
 }
 
 // `share_hint` > 0 overrides the trajectories-per-SM estimate (batched launches plan every
@@ -380,12 +380,11 @@ static int launch_tmem_variant(const SdeParams& p, const TmemPlan& P, cudaStream
 template <int SOLVER, bool ADAM>
 static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
   const bool pipe = P.L.pipe != 0;
-  // Column-group counts of the reference's benchmarking sizes (N = 40, 50, 60, 70; examples/
-  // benchmarking_instances/Size*) compiled in for the tiles that gain from a fully unrolled
-  // contraction with immediate addresses (measured at N = 70: MF 2.05 -> 1.87 ms, MF + Adam 2.11 -> 2.01,
-  // Langevin + Adam 2.03 -> 1.82, PumpedLangevin + Adam 2.11 -> 1.93; DL, DL + Adam, Langevin and
-  // PumpedLangevin are neutral or slower and keep the run-time loop).
-  constexpr bool CGC_TILE = SOLVER == SOLVER_MF || SOLVER == SOLVER_DL || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM);
+  // Column-group counts of the reference's benchmarking sizes (N = 20 ... 70; examples/
+  // benchmarking_instances/Size*) compiled in: fully unrolled contraction with immediate addresses
+  // and (mostly) unpinned noise, see sde_kernel_tmem.cuh.  Measured at N = 70: DL + Adam 3.57 -> 3.39 ms,
+  // MF 2.05 -> 1.86, Langevin + Adam 2.03 -> 1.78, Langevin 1.73 -> 1.67; more at N = 20 ... 60.
+  constexpr bool CGC_TILE = true;
   if (P.qsrc == QSRC_TMEM && pipe) {
     if (P.cgc == 5) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 5>(p, P, st);
     if (P.cgc == 8) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 8>(p, P, st);

@@ -456,12 +456,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       // to hide a noise quantum per chunk pair -- pinned there, the quanta ran one after the other and
       // their ~250-cycle dependent chains WERE the iteration.  All of them start at the top instead,
       // unpinned: ptxas runs the chains side by side under the (fully unrolled) contraction.
-      // The same holds, measured, for the larger compile-time variants up to CG = 13 (N <= 52) and for
-      // the Adam variants of Langevin / PumpedLangevin at every compile-time CG (N = 70: 1.88 -> 1.78 ms);
-      // and for DL / DL + Adam (N = 70: 3.16 -> 3.10 ms, 3.57 -> 3.39 ms);
-      // MF at CG = 15, 18 keeps one pinned quantum per chunk pair (MF + Adam loses 12 % unpinned).
-      constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM) ||
-                                            SOLVER == SOLVER_DL);
+      // The same holds, measured, for every larger compile-time variant (N = 40 ... 70: DL + Adam 3.57 ->
+      // 3.39 ms at N = 70 and +12-15 % at N = 40 ... 60, Langevin +4-15 %, its Adam variant +6 %) except
+      // MF at CG = 15, 18, which keeps one pinned quantum per chunk pair (MF + Adam loses 12 % unpinned).
+      constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV || SOLVER == SOLVER_DL);
       constexpr int NQ = SMALLCG ? 2 : 2 * KT;
       const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
       tmem_ld16(tlane, qa);
