@@ -18,6 +18,16 @@
 //     sub-partition and group), each with its own named barrier: the groups drift out of phase, so
 //     one group's FMA/LSU-bound contraction overlaps the other's ALU/MUFU-bound noise + update.
 //     Threads t and t+128 share a TMEM lane and therefore the same column group.
+//
+// Variants of the one tile body (template parameters of sde_tile_body):
+//   QSRC  where the thread's Q slice lives: TMEM (n <= 128), TMEM + shared-memory tail (n <= 256),
+//         streamed from L2 (fallback);
+//   PIPE  production mode: Philox noise generated inside the contraction, compile-time panel stride;
+//         off for noise replay (validation) and for too few column groups;
+//   CGC   column-group count compiled in (N = 20, 30, ..., 70, the reference's benchmarking sizes):
+//         fully unrolled contraction, immediate addresses, noise quanta scheduled by ptxas;
+//   and per-tile choices made by measurement (HOIST, VSMEM, DENSE_TILE, unroll factors) -- at two
+//   warps per scheduler the static schedule decides +-5 % per tile, see DESIGN.md section 4.
 #pragma once
 #include <type_traits>
 
