@@ -25,8 +25,11 @@ EXPORTS = (
     "ccvm_microbench_fp32", "ccvm_query_launch", "ccvm_abi_version", "ccvm_last_error",
     "ccvm_eval_hook", "ccvm_change_variables", "ccvm_fit_to_constraints", "ccvm_scale_coefs",
     "ccvm_solve_batch", "ccvm_solution_stats_batch", "ccvm_generate_boxqp", "ccvm_microbench_tf32",
-    "ccvm_pack_record", "ccvm_merge_records",
+    "ccvm_pack_record", "ccvm_merge_records", "ccvm_solve_fused", "ccvm_solve_batch_fused", "ccvm_dump_noise",
 )
+ABI_VERSION = 2          # CCVM_ABI_VERSION of include/ccvm_b200.h this binding was written against
+RECORD_HEADER = 10       # CCVM_RECORD_HEADER
+FUSED_RESULT_BYTES = 56  # { float best; int32 arg_best; int32 counts[7]; uint32 ctas; uint64 loop_ns, tail_ns }
 
 _fp = C.c_void_p  # device / host pointers travel as plain addresses
 
@@ -92,8 +95,16 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.ccvm_last_error.restype = C.c_char_p
     lib.ccvm_abi_version.restype = C.c_int
+    if lib.ccvm_abi_version() != ABI_VERSION:
+        raise NativeError(
+            f"{LIB_PATH} has ABI version {lib.ccvm_abi_version()}, this package expects {ABI_VERSION}: the descriptor "
+            "layouts differ -- rebuild it with `python -c 'import __graft_entry__ as g; g.build(force=True)'`.")
     lib.ccvm_solve.argtypes = [C.POINTER(SolveDesc), _fp]
     lib.ccvm_solve_batch.argtypes = [C.POINTER(SolveDesc), C.c_int32, _fp]
+    lib.ccvm_solve_fused.argtypes = [C.POINTER(SolveDesc), C.POINTER(EpilogueDesc), C.c_double, _fp, _fp]
+    lib.ccvm_solve_batch_fused.argtypes = [C.POINTER(SolveDesc), C.POINTER(EpilogueDesc), C.POINTER(C.c_double),
+                                           C.c_int32, _fp, _fp]
+    lib.ccvm_dump_noise.argtypes = [C.POINTER(SolveDesc), _fp, _fp]
     lib.ccvm_solution_stats_batch.argtypes = [_fp, _fp, _fp, C.c_int32, _fp, _fp]
     lib.ccvm_epilogue.argtypes = [C.POINTER(EpilogueDesc), _fp]
     lib.ccvm_compute_energy.argtypes = [_fp, _fp, _fp, C.c_double, C.c_int32, C.c_int32, _fp, _fp]

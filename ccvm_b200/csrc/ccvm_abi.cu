@@ -11,59 +11,68 @@
 #include <vector>
 
 #include "../../include/ccvm_b200.h"
-#include "sde_kernel.cuh"
-#include "sde_kernel_tmem.cuh"
+#include "epilogue.cuh"
 #include "sde_kernel_tc.cuh"
+#include "sde_kernel_tmem.cuh"
+#include "sde_launch.h"
 
 using namespace ccvm;
 
 // ------------------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, ...) {
+int ccvm::set_error(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
 }
-
-#define CUDA_TRY(expr)                                                                      \
-  do {                                                                                      \
-    cudaError_t _e = (expr);                                                                \
-    if (_e != cudaSuccess)                                                                  \
-      return fail(CCVM_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-  } while (0)
+#define fail(...) ::ccvm::set_error(__VA_ARGS__)
 
 extern "C" const char* ccvm_last_error(void) { return g_err; }
 extern "C" int ccvm_abi_version(void) { return CCVM_ABI_VERSION; }
 
 struct DeviceInfo {
   int device = -1, sms = 0, max_smem = 0;
+  cudaMemPool_t pool = nullptr;
 };
+// Scratch comes from a PRIVATE stream-ordered pool per device (not the device's default pool, which
+// other libraries in the process share): freed blocks stay cached up to CCVM_POOL_KEEP_MB (default
+// 1024 MiB) across synchronisations -- the default pool hands memory back to the driver at every sync,
+// which cost ~50 ms per host-buffer solve -- and anything above that is returned to the driver.
 static int device_info(DeviceInfo& di) {
-  static thread_local DeviceInfo cache;
+  static thread_local DeviceInfo cache[64];
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
-  if (cache.device != dev) {
+  if (dev < 0 || dev >= 64) return fail(CCVM_E_CUDA, "unsupported device ordinal %d", dev);
+  DeviceInfo& c = cache[dev];
+  if (c.device != dev) {
     int sms = 0, smem = 0, major = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CUDA_TRY(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
     if (major != 10)
       return fail(CCVM_E_CUDA, "ccvm_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
-    // keep stream-ordered allocations cached across synchronisations (the default pool hands
-    // memory back to the driver at every sync, which cost ~50 ms per host-buffer solve)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    static cudaMemPool_t pools[64];  // one per device for the whole process
+    if (!pools[dev]) {
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      CUDA_TRY(cudaMemPoolCreate(&pools[dev], &props));
+      unsigned long long keep = 1024ull << 20;
+      if (const char* e = getenv("CCVM_POOL_KEEP_MB")) keep = (unsigned long long)atoll(e) << 20;
+      CUDA_TRY(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
     }
-    cache.device = dev;
-    cache.sms = sms;
-    cache.max_smem = smem;
+    c.device = dev;
+    c.sms = sms;
+    c.max_smem = smem;
+    c.pool = pools[dev];
   }
-  di = cache;
+  di = c;
   return CCVM_OK;
 }
 
@@ -78,143 +87,24 @@ struct StreamBuf {
   ~StreamBuf() {
     if (p) cudaFreeAsync(p, st);
   }
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+  cudaError_t alloc(size_t bytes) {
+    DeviceInfo di;
+    if (device_info(di) != CCVM_OK) return cudaErrorInvalidDevice;
+    return cudaMallocFromPoolAsync(&p, bytes, di.pool, st);
+  }
   template <class T>
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
 // ------------------------------------------------------------------- schedule builder
-// The reference evaluates its per-iteration schedules (pump ramp, noise-ratio decay,
-// measurement-strength decay, Adam bias corrections) as fp64 host scalars
-// (dl_solver.py:523-527,704,715; mf_solver.py:550-559; pumped_langevin_solver.py:278-283).
-// They are evaluated here once, in fp64, on the device, and rounded to fp32 per use.
-struct SchedArgs {
-  int solver, adam, iterations, flag;
-  double pump, dt, noise_ratio, j, fs, g, beta1, beta2;
-};
-
-__device__ __forceinline__ void schedule_row(const SchedArgs& a, int i, float* __restrict__ out) {
-  if (i >= a.iterations) return;
-  const double t = (double)(i + 1), T = (double)a.iterations;
-  const double rate = a.flag ? t / T : 1.0;
-  const double decay = exp(-t / T * 3.0);
-  float r[SCHED_W] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (a.solver == SOLVER_DL) {
-    const double ratio = (a.noise_ratio - 1.0) * decay + 1.0;
-    const double p = a.pump * rate;  // == pump*(i+1)/T when the flag is set, else pump
-    r[SC_A] = (float)(a.adam ? a.dt : a.dt * a.fs * (0.5 + rate));
-    r[SC_P1] = (float)(a.dt * (-1.0 + p));
-    r[SC_P2] = (float)(a.dt * (-1.0 - p));
-    r[SC_N1] = (float)(2.0 * a.g * sqrt(a.dt) * ratio);
-    r[SC_N2] = (float)(2.0 * a.g * sqrt(a.dt) / ratio);
-  } else if (a.solver == SOLVER_MF) {
-    const double ji = a.j * decay;
-    r[SC_A] = (float)(sqrt(1.0 / (4.0 * ji)) / sqrt(a.dt));
-    r[SC_P1] = (float)(a.pump * rate);
-    r[SC_P2] = (float)ji;
-    r[SC_N1] = (float)(sqrt(ji) / sqrt(a.dt));
-    r[SC_N2] = (float)(1.0 + ji);
-  } else if (a.solver == SOLVER_PLV) {
-    r[SC_P1] = (float)(a.dt * (a.pump * rate - 1.0));
-  }
-  if (a.adam) {
-    r[SC_IB1] = (float)(1.0 / (1.0 - pow(a.beta1, t)));
-    r[SC_IB2] = a.beta2 == 1.0 ? 0.f : (float)(1.0 / (1.0 - pow(a.beta2, t)));
-  }
-  float4* o = reinterpret_cast<float4*>(out + (size_t)i * SCHED_W);
-  o[0] = make_float4(r[0], r[1], r[2], r[3]);
-  o[1] = make_float4(r[4], r[5], r[6], r[7]);
-}
-
+// (SchedArgs / schedule_row: ccvm_common.cuh.)  Stand-alone kernels for the paths that do not
+// evaluate the table inside the persistent kernel: the tcgen05 path and batched launches.
 __global__ void build_schedule_kernel(SchedArgs a, float* __restrict__ out) {
   schedule_row(a, blockIdx.x * blockDim.x + threadIdx.x, out);
 }
 
-// ------------------------------------------------------------------------ launch plan
-struct LaunchPlan {
-  int tb, rg, cg, xs, threads, ctas, use_tma;
-  size_t smem;
-};
-
-static size_t sde_smem_bytes(int np, int xs) {
-  return ((size_t)np * np * 2 + (size_t)2 * np * xs + 2 * (size_t)np) * sizeof(float) + 16;
-}
-
-static int plan_launch(const ccvm_solve_desc& d, const DeviceInfo& di, LaunchPlan& L) {
-  const int K = d.solver == CCVM_SOLVER_DL ? 2 : 1;
-  const int cg = (d.n + 3) / 4, np = 4 * cg;
-  if (cg > 256) return fail(CCVM_E_TOO_LARGE, "n=%d exceeds the SIMT path (n <= 1024)", d.n);
-  const int share = (d.batch + di.sms - 1) / di.sms;
-  int tb = 4;
-  if (d.solver != CCVM_SOLVER_DL && share >= 64) tb = 8;
-  if (((share + tb - 1) / tb) * cg < 64) tb = 2;
-  if (const char* e = getenv("CCVM_TB")) {
-    const int v = atoi(e);
-    if (v == 2 || v == 4 || (v == 8 && d.solver != CCVM_SOLVER_DL)) tb = v;
-  }
-  int rg = (share + tb - 1) / tb;
-  if (const char* e = getenv("CCVM_RG")) {
-    const int v = atoi(e);
-    if (v > 0) rg = v;
-  }
-  if (rg < 1) rg = 1;
-  if (rg > 256 / cg) rg = 256 / cg;
-  auto xs_of = [&](int r) { return ((K * r * tb + 7) / 8) * 8 + 32; };
-  while (rg > 1 && sde_smem_bytes(np, xs_of(rg)) > (size_t)di.max_smem) --rg;
-  const size_t smem = sde_smem_bytes(np, xs_of(rg));
-  if (smem > (size_t)di.max_smem)
-    return fail(CCVM_E_TOO_LARGE, "n=%d needs %zu B of shared memory (> %d): use the large-n path", d.n, smem,
-                di.max_smem);
-  L.tb = tb;
-  L.rg = rg;
-  L.cg = cg;
-  L.xs = xs_of(rg);
-  L.threads = ((rg * cg + 31) / 32) * 32;
-  L.ctas = (d.batch + rg * tb - 1) / (rg * tb);
-  L.smem = smem;
-  const size_t qbytes = (size_t)d.n * d.n * 4;
-  L.use_tma = (qbytes % 16 == 0) && (((uintptr_t)d.q) % 16 == 0) && (qbytes <= (size_t)2 * np * L.xs * 4);
-  if (getenv("CCVM_NO_TMA")) L.use_tma = 0;
-  return CCVM_OK;
-}
-
-template <int SOLVER, bool ADAM, int TB>
-static int launch_one(const SdeParams& p, const LaunchPlan& L, cudaStream_t st) {
-  auto kern = sde_kernel<SOLVER, ADAM, TB>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem));
-  kern<<<L.ctas, L.threads, L.smem, st>>>(p);
-  CUDA_TRY(cudaGetLastError());
-  return CCVM_OK;
-}
-
-template <int SOLVER, bool ADAM>
-static int launch_tb(const SdeParams& p, const LaunchPlan& L, cudaStream_t st) {
-  switch (L.tb) {
-    case 2: return launch_one<SOLVER, ADAM, 2>(p, L, st);
-    case 4: return launch_one<SOLVER, ADAM, 4>(p, L, st);
-    case 8:
-      if constexpr (SOLVER != SOLVER_DL) return launch_one<SOLVER, ADAM, 8>(p, L, st);
-  }
-  return fail(CCVM_E_INVALID, "unsupported trajectory tile %d", L.tb);
-}
-
-template <int SOLVER, bool ADAM, int TB>
-static int regs_one() {
-  cudaFuncAttributes fa;
-  if (cudaFuncGetAttributes(&fa, sde_kernel<SOLVER, ADAM, TB>) != cudaSuccess) return -1;
-  return fa.numRegs;
-}
-
-
 // ---- tiled paths (sde_kernel_tmem.cuh): Q slice from TMEM (n <= 128) or streamed from L2 (any n)
-struct TmemPlan {
-  TmemLaunch L;
-  int cg, threads, ctas, qsrc;
-  int cgc;  // column-group count compiled into the kernel variant to launch (0: run-time loop)
-  size_t smem;
-};
-
-enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_LEGACY = 2, PATH_TC = 3, PATH_HYB = 4 };
+enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_TC = 3, PATH_HYB = 4 };
 
 // tcgen05 3xTF32 drift (sde_kernel_tc.cuh) where batch x N x N is a genuine dense GEMM:
 // n > 256 and at least 1024 contraction rows (8 CTAs of 128 rows).  n = 256 itself is also served by
@@ -238,19 +128,11 @@ static bool tc_eligible(const ccvm_solve_desc& d) {
 }
 
 static int choose_path(const ccvm_solve_desc& d) {
-  if (getenv("CCVM_LEGACY")) return PATH_LEGACY;  // first-generation shared-memory kernel (n <~ 160)
   if (tc_eligible(d)) return PATH_TC;
   if (d.n <= 128 && getenv("CCVM_NO_TMEM") == nullptr) return PATH_TMEM;
   // 128 < n <= 256: first 128 rows of every Q slice in TMEM, the rest in shared memory
   if (d.n <= 4 * 64 && getenv("CCVM_NO_TMEM") == nullptr && getenv("CCVM_NO_HYB") == nullptr) return PATH_HYB;
   return PATH_GMEM;
-}
-
-// every tile has compile-time column-group variants (launch_tmem) at the reference's benchmarking sizes
-static bool cgc_tile(int solver, bool adam) {
-  (void)solver;
-  (void)adam;
-  return true;
 }
 
 // `share_hint` > 0 overrides the trajectories-per-SM estimate (batched launches plan every
@@ -290,9 +172,9 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   if (ng == 2 && !tm && 2 * round32(rg * cg) > max_threads) ng = 1;
   // in-loop noise generation (sde_kernel_tmem.cuh, PIPE): Philox mode with enough Q chunks to hide it in
   // small compile-time column-group variants (CG = 5, 8: all noise quanta unpinned at the top of the
-  // iteration; every tile has them): single launches on the TMEM path only
-  const bool small_cgc = !batched && path == PATH_TMEM && d.rng_mode == CCVM_RNG_PHILOX && (cg == 5 || cg == 8) &&
-                         getenv("CCVM_NO_CGC") == nullptr;
+  // iteration; every tile has them), single and batched launches (bucketed by column-group count)
+  const bool cgc_off = getenv("CCVM_NO_CGC") != nullptr || (batched && getenv("CCVM_NO_BATCH_CGC") != nullptr);
+  const bool small_cgc = path == PATH_TMEM && d.rng_mode == CCVM_RNG_PHILOX && (cg == 5 || cg == 8) && !cgc_off;
   const bool pipe = getenv("CCVM_NO_PIPE") == nullptr &&
                     (small_cgc ||
                      (d.solver == CCVM_SOLVER_DL ? pipe_ok<SOLVER_DL>(cg, d.rng_mode == CCVM_RNG_PHILOX)
@@ -302,9 +184,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   const bool fixed_xs = pipe && tm;  // compile-time panel stride, no row rotation
   // fixed-stride panels of the K = 1 solvers in the hybrid kernel hold two k rows per panel row
   // (sde_kernel_tmem.cuh, KP)
-  const bool cgc_variant = !batched && fixed_xs && path == PATH_TMEM && getenv("CCVM_NO_CGC") == nullptr &&
-                           cgc_tile(d.solver, d.algorithm == CCVM_ALG_ADAM) &&
-                           (cg == 10 || cg == 13 || cg == 15 || cg == 18);
+  const bool cgc_variant = fixed_xs && path == PATH_TMEM && !cgc_off && (cg == 10 || cg == 13 || cg == 15 || cg == 18);
   const int kp = (fixed_xs && K == 1 && path == PATH_HYB) ? 2 : 1;
   // DL + Adam parks its second moments in shared memory (sde_kernel_tmem.cuh, VSMEM): 64 B per thread
   const size_t vsm = (fixed_xs && path == PATH_TMEM && d.solver == CCVM_SOLVER_DL && d.algorithm == CCVM_ALG_ADAM)
@@ -368,57 +248,6 @@ __global__ void scale_q_kernel(const float* __restrict__ q, const float* __restr
   qs[idx] = val;
 }
 
-template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
-static int launch_tmem_variant(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  auto kern = sde_tmem_kernel<SOLVER, ADAM, QSRC, PIPE, CGC>;
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-  kern<<<P.ctas, P.threads, P.smem, st>>>(p, P.L);
-  CUDA_TRY(cudaGetLastError());
-  return CCVM_OK;
-}
-
-template <int SOLVER, bool ADAM>
-static int launch_tmem(const SdeParams& p, const TmemPlan& P, cudaStream_t st) {
-  const bool pipe = P.L.pipe != 0;
-  // Column-group counts of the reference's benchmarking sizes (N = 20 ... 70; examples/
-  // benchmarking_instances/Size*) compiled in: fully unrolled contraction with immediate addresses
-  // and (mostly) unpinned noise, see sde_kernel_tmem.cuh.  Measured at N = 70: DL + Adam 3.57 -> 3.39 ms,
-  // MF 2.05 -> 1.86, Langevin + Adam 2.03 -> 1.78, Langevin 1.73 -> 1.67; more at N = 20 ... 60.
-  constexpr bool CGC_TILE = true;
-  if (P.qsrc == QSRC_TMEM && pipe) {
-    if (P.cgc == 5) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 5>(p, P, st);
-    if (P.cgc == 8) return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 8>(p, P, st);
-  }
-  if constexpr (CGC_TILE) {
-    if (P.qsrc == QSRC_TMEM && pipe) {
-      switch (P.cgc) {
-        case 10: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 10>(p, P, st);
-        case 13: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 13>(p, P, st);
-        case 15: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 15>(p, P, st);
-        case 18: return launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true, 18>(p, P, st);
-        default: break;
-      }
-    }
-  }
-  if (P.qsrc == QSRC_TMEM)
-    return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, true>(p, P, st)
-                : launch_tmem_variant<SOLVER, ADAM, QSRC_TMEM, false>(p, P, st);
-  if (P.qsrc == QSRC_HYB)
-    return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_HYB, true>(p, P, st)
-                : launch_tmem_variant<SOLVER, ADAM, QSRC_HYB, false>(p, P, st);
-  return pipe ? launch_tmem_variant<SOLVER, ADAM, QSRC_GMEM, true>(p, P, st)
-              : launch_tmem_variant<SOLVER, ADAM, QSRC_GMEM, false>(p, P, st);
-}
-
-template <int SOLVER, bool ADAM>
-static int regs_tmem(int qsrc) {
-  cudaFuncAttributes fa;
-  cudaError_t e = qsrc == QSRC_TMEM  ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_TMEM, true>)
-                  : qsrc == QSRC_HYB ? cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_HYB, true>)
-                                     : cudaFuncGetAttributes(&fa, sde_tmem_kernel<SOLVER, ADAM, QSRC_GMEM, true>);
-  return e == cudaSuccess ? fa.numRegs : -1;
-}
-
 // ------------------------------------------------------------------ tensor-core path
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -453,12 +282,6 @@ static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint6
   return CCVM_OK;
 }
 
-struct TcPlan {
-  int version;  // 1: single-CTA kernel (sde_tc_kernel), 2: CTA-pair kernel (sde_tc2_kernel)
-  int np, rows, rows_p, n_aux, ctas;
-  size_t smem;
-};
-
 static int tc_version() {
   if (const char* e = getenv("CCVM_TC")) {
     const int v = atoi(e);
@@ -479,36 +302,6 @@ static void plan_tc(const ccvm_solve_desc& d, TcPlan& P) {
   P.ctas = P.rows_p / TC_BM;
   P.smem = P.version == 2 ? (size_t)T2_SMEM_BYTES
                           : 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)2 * P.np * sizeof(float);
-}
-
-struct TcMaps {
-  CUtensorMap xh, xl, qh, ql, oh, ol;
-};
-
-template <int SOLVER, bool ADAM>
-static int launch_tc(const SdeParams& p, const TcParams& tc, const TcPlan& P, const TcMaps& M, cudaStream_t st) {
-  const size_t plane = (size_t)tc.rows_p * tc.np;
-  tc_init_state_kernel<SOLVER><<<(unsigned)((plane / 4 + 255) / 256), 256, 0, st>>>(p, tc, P.n_aux);
-  CUDA_TRY(cudaGetLastError());
-  if (P.version == 2) {
-    auto kern = sde_tc2_kernel<SOLVER, ADAM>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-    kern<<<P.ctas, TC_THREADS, P.smem, st>>>(p, tc, M.xh, M.xl, M.qh, M.ql, M.oh, M.ol);
-  } else {
-    auto kern = sde_tc_kernel<SOLVER, ADAM>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-    kern<<<P.ctas, TC_THREADS, P.smem, st>>>(p, tc, M.xh, M.xl, M.qh, M.ql);
-  }
-  CUDA_TRY(cudaGetLastError());
-  return CCVM_OK;
-}
-
-template <int SOLVER, bool ADAM>
-static int regs_tc() {
-  cudaFuncAttributes fa;
-  const cudaError_t e = tc_version() == 2 ? cudaFuncGetAttributes(&fa, sde_tc2_kernel<SOLVER, ADAM>)
-                                          : cudaFuncGetAttributes(&fa, sde_tc_kernel<SOLVER, ADAM>);
-  return e == cudaSuccess ? fa.numRegs : -1;
 }
 
 // `p` carries everything but the launch geometry; sched is already being built on `st`
@@ -553,16 +346,9 @@ static int solve_tc(const ccvm_solve_desc* d, SdeParams& p, cudaStream_t st) {
   }
   if (!rc) {
     const bool adam = d->algorithm == CCVM_ALG_ADAM;
-    switch (d->solver * 2 + (adam ? 1 : 0)) {
-      case 0: rc = launch_tc<SOLVER_DL, false>(p, tc, P, M, st); break;
-      case 1: rc = launch_tc<SOLVER_DL, true>(p, tc, P, M, st); break;
-      case 2: rc = launch_tc<SOLVER_MF, false>(p, tc, P, M, st); break;
-      case 3: rc = launch_tc<SOLVER_MF, true>(p, tc, P, M, st); break;
-      case 4: rc = launch_tc<SOLVER_LV, false>(p, tc, P, M, st); break;
-      case 5: rc = launch_tc<SOLVER_LV, true>(p, tc, P, M, st); break;
-      case 6: rc = launch_tc<SOLVER_PLV, false>(p, tc, P, M, st); break;
-      default: rc = launch_tc<SOLVER_PLV, true>(p, tc, P, M, st); break;
-    }
+#define LAUNCH_TC(S, A) rc = launch_tc<S, A>(p, tc, P, M, st)
+    CCVM_DISPATCH_TILE(d->solver, adam, LAUNCH_TC)
+#undef LAUNCH_TC
   }
   return rc;
 }
@@ -673,6 +459,8 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
   const int path = choose_path(*d);
+  const bool adam = d->algorithm == CCVM_ALG_ADAM;
+  int regs = -1;
   if (path == PATH_TC) {
     TcPlan P;
     plan_tc(*d, P);
@@ -680,561 +468,36 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
     info5[1] = P.ctas;
     info5[2] = TC_BM / (d->solver == CCVM_SOLVER_DL ? 2 : 1);
     info5[3] = (int)P.smem;
-    const bool a = d->algorithm == CCVM_ALG_ADAM;
-    int r = -1;
-    if (d->solver == SOLVER_DL) r = a ? regs_tc<SOLVER_DL, true>() : regs_tc<SOLVER_DL, false>();
-    if (d->solver == SOLVER_MF) r = a ? regs_tc<SOLVER_MF, true>() : regs_tc<SOLVER_MF, false>();
-    if (d->solver == SOLVER_LV) r = a ? regs_tc<SOLVER_LV, true>() : regs_tc<SOLVER_LV, false>();
-    if (d->solver == SOLVER_PLV) r = a ? regs_tc<SOLVER_PLV, true>() : regs_tc<SOLVER_PLV, false>();
-    info5[4] = r;
+#define REGS_TC(S, A) regs = regs_tc<S, A>(P.version)
+    CCVM_DISPATCH_TILE(d->solver, adam, REGS_TC)
+#undef REGS_TC
+    info5[4] = regs;
     return CCVM_OK;
   }
-  if (path != PATH_LEGACY) {
-    TmemPlan P;
-    if ((rc = plan_tmem(*d, di, path, P))) return rc;
-    info5[0] = P.threads;
-    info5[1] = P.ctas;
-    info5[2] = P.L.ng * 2 * P.L.rg;
-    info5[3] = (int)P.smem;
-    const bool a = d->algorithm == CCVM_ALG_ADAM;
-    int r = -1;
-    if (d->solver == SOLVER_DL) r = a ? regs_tmem<SOLVER_DL, true>(P.qsrc) : regs_tmem<SOLVER_DL, false>(P.qsrc);
-    if (d->solver == SOLVER_MF) r = a ? regs_tmem<SOLVER_MF, true>(P.qsrc) : regs_tmem<SOLVER_MF, false>(P.qsrc);
-    if (d->solver == SOLVER_LV) r = a ? regs_tmem<SOLVER_LV, true>(P.qsrc) : regs_tmem<SOLVER_LV, false>(P.qsrc);
-    if (d->solver == SOLVER_PLV) r = a ? regs_tmem<SOLVER_PLV, true>(P.qsrc) : regs_tmem<SOLVER_PLV, false>(P.qsrc);
-    info5[4] = r;
-    return CCVM_OK;
-  }
-  LaunchPlan L;
-  if ((rc = plan_launch(*d, di, L))) return rc;
-  info5[0] = L.threads;
-  info5[1] = L.ctas;
-  info5[2] = L.rg * L.tb;
-  info5[3] = (int)L.smem;
-  int regs = -1;
-  const bool ad = d->algorithm == CCVM_ALG_ADAM;
-#define REGS_CASE(S)                                                                             \
-  if (d->solver == S) {                                                                          \
-    if (L.tb == 2) regs = ad ? regs_one<S, true, 2>() : regs_one<S, false, 2>();                 \
-    if (L.tb == 4) regs = ad ? regs_one<S, true, 4>() : regs_one<S, false, 4>();                 \
-  }
-  REGS_CASE(SOLVER_DL) REGS_CASE(SOLVER_MF) REGS_CASE(SOLVER_LV) REGS_CASE(SOLVER_PLV)
-#undef REGS_CASE
-  if (L.tb == 8) {
-    if (d->solver == SOLVER_MF) regs = ad ? regs_one<SOLVER_MF, true, 8>() : regs_one<SOLVER_MF, false, 8>();
-    if (d->solver == SOLVER_LV) regs = ad ? regs_one<SOLVER_LV, true, 8>() : regs_one<SOLVER_LV, false, 8>();
-    if (d->solver == SOLVER_PLV) regs = ad ? regs_one<SOLVER_PLV, true, 8>() : regs_one<SOLVER_PLV, false, 8>();
-  }
+  TmemPlan P;
+  if ((rc = plan_tmem(*d, di, path, P))) return rc;
+  info5[0] = P.threads;
+  info5[1] = P.ctas;
+  info5[2] = P.L.ng * 2 * P.L.rg;
+  info5[3] = (int)P.smem;
+#define REGS_TMEM(S, A) regs = regs_tmem<S, A>(P.qsrc)
+  CCVM_DISPATCH_TILE(d->solver, adam, REGS_TMEM)
+#undef REGS_TMEM
   info5[4] = regs;
   return CCVM_OK;
 }
 
-extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
-  int rc = validate_solve(d);
-  if (rc) return rc;
-  DeviceInfo di;
-  if ((rc = device_info(di))) return rc;
-  const int path = choose_path(*d);
-  const bool use_tmem = path == PATH_TMEM || path == PATH_GMEM || path == PATH_HYB;  // tiled SIMT kernel
-  LaunchPlan L;
-  TmemPlan TP;
-  memset(&L, 0, sizeof(L));
-  if (path == PATH_TC) {
-    // planned inside solve_tc
-  } else if (use_tmem) {
-    if ((rc = plan_tmem(*d, di, path, TP))) return rc;
-    L.cg = TP.cg;
-  } else if ((rc = plan_launch(*d, di, L))) {
-    return rc;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool adam = d->algorithm == CCVM_ALG_ADAM;
-
-  StreamBuf sched_buf(st), qs_buf(st);
-  CUDA_TRY(sched_buf.alloc((size_t)d->iterations * SCHED_W * sizeof(float)));
-  float* sched = sched_buf.as<float>();
-  const SchedArgs sa = sched_args(d);
-  build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(sa, sched);
-  CUDA_TRY(cudaGetLastError());
-
-  SdeParams p;
-  fill_params(d, sched, L.cg, p);
-  p.rg = L.rg;
-  p.xs = L.xs;
-  p.use_tma = L.use_tma;
-  if (path == PATH_TC) {
-    return solve_tc(d, p, st);
-  }
-
-  float* qs_scratch = nullptr;
-  if (use_tmem && TP.qsrc == QSRC_GMEM) {
-    const int np = 4 * TP.cg;
-    CUDA_TRY(qs_buf.alloc((size_t)np * np * sizeof(float)));
-    qs_scratch = qs_buf.as<float>();
-    scale_q_kernel<<<(np * np + 255) / 256, 256, 0, st>>>(p.q, p.drift_s_vec, p.drift_s, p.a_half, p.n, np, qs_scratch);
-    CUDA_TRY(cudaGetLastError());
-    TP.L.qs = qs_scratch;
-  }
-  if (use_tmem) {
-    switch (d->solver * 2 + (adam ? 1 : 0)) {
-      case 0: rc = launch_tmem<SOLVER_DL, false>(p, TP, st); break;
-      case 1: rc = launch_tmem<SOLVER_DL, true>(p, TP, st); break;
-      case 2: rc = launch_tmem<SOLVER_MF, false>(p, TP, st); break;
-      case 3: rc = launch_tmem<SOLVER_MF, true>(p, TP, st); break;
-      case 4: rc = launch_tmem<SOLVER_LV, false>(p, TP, st); break;
-      case 5: rc = launch_tmem<SOLVER_LV, true>(p, TP, st); break;
-      case 6: rc = launch_tmem<SOLVER_PLV, false>(p, TP, st); break;
-      default: rc = launch_tmem<SOLVER_PLV, true>(p, TP, st); break;
-    }
-  } else
-  switch (d->solver * 2 + (adam ? 1 : 0)) {
-    case 0: rc = launch_tb<SOLVER_DL, false>(p, L, st); break;
-    case 1: rc = launch_tb<SOLVER_DL, true>(p, L, st); break;
-    case 2: rc = launch_tb<SOLVER_MF, false>(p, L, st); break;
-    case 3: rc = launch_tb<SOLVER_MF, true>(p, L, st); break;
-    case 4: rc = launch_tb<SOLVER_LV, false>(p, L, st); break;
-    case 5: rc = launch_tb<SOLVER_LV, true>(p, L, st); break;
-    case 6: rc = launch_tb<SOLVER_PLV, false>(p, L, st); break;
-    default: rc = launch_tb<SOLVER_PLV, true>(p, L, st); break;
-  }
-  return rc;
-}
-
-
-// ------------------------------------------------------------------ batched instances
-struct SchedJob {
-  SchedArgs a;
-  long long offset;  // first row of this problem in the shared schedule table
-};
-
-__global__ void build_schedule_batch_kernel(const SchedJob* __restrict__ jobs, float* __restrict__ out);
-
-extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, void* stream) {
-  if (!descs || count < 1) return fail(CCVM_E_INVALID, "ccvm_solve_batch needs at least one descriptor");
-  DeviceInfo di;
-  int rc = device_info(di);
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  const int solver = descs[0].solver, alg = descs[0].algorithm;
-  std::vector<int> batched, single;
-  for (int i = 0; i < count; ++i) {
-    if ((rc = validate_solve(&descs[i]))) return rc;
-    if (descs[i].solver != solver || descs[i].algorithm != alg)
-      return fail(CCVM_E_INVALID, "all descriptors of a batch must share solver and algorithm");
-    if (descs[i].rng_mode != CCVM_RNG_PHILOX || descs[i].evolution_step > 0)
-      return fail(CCVM_E_INVALID, "batched solves use Philox noise and no evolution sampling");
-    const int path = choose_path(descs[i]);
-    (path == PATH_TMEM || path == PATH_HYB ? batched : single).push_back(i);
-  }
-  for (int i : single)
-    if ((rc = ccvm_solve(&descs[i], stream))) return rc;
-  if (batched.empty()) return CCVM_OK;
-
-  // plans, schedule table offsets
-  std::vector<TmemPlan> plans(batched.size());
-  std::vector<SchedJob> jobs(batched.size());
-  long long rows = 0, total_traj = 0;
-  int max_t = 0;
-  for (int i : batched) total_traj += descs[i].batch;
-  const int share = (int)((total_traj + di.sms - 1) / di.sms);
-  for (size_t b = 0; b < batched.size(); ++b) {
-    const ccvm_solve_desc& d = descs[batched[b]];
-    if ((rc = plan_tmem(d, di, choose_path(d), plans[b], share, true))) return rc;
-    jobs[b].a = sched_args(&d);
-    jobs[b].offset = rows;
-    rows += d.iterations;
-    if (d.iterations > max_t) max_t = d.iterations;
-  }
-  float* sched = nullptr;
-  SchedJob* d_jobs = nullptr;
-  BatchItem* d_items = nullptr;
-  int2* d_map = nullptr;
-  StreamBuf sched_buf(st), jobs_buf(st), items_buf(st), map_buf(st);
-  CUDA_TRY(sched_buf.alloc((size_t)rows * SCHED_W * sizeof(float)));
-  CUDA_TRY(jobs_buf.alloc(jobs.size() * sizeof(SchedJob)));
-  sched = sched_buf.as<float>();
-  d_jobs = jobs_buf.as<SchedJob>();
-  CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(SchedJob), cudaMemcpyHostToDevice, st));
-  build_schedule_batch_kernel<<<dim3((max_t + 127) / 128, (unsigned)jobs.size()), 128, 0, st>>>(d_jobs, sched);
-  CUDA_TRY(cudaGetLastError());
-
-  // items + CTA maps, bucketed by Q source and block size so small instances do not pay for big blocks
-  std::vector<BatchItem> items(batched.size());
-  const int bucket_threads[4] = {32, 64, 128, 256};
-  constexpr int NB = 8;  // buckets 0-3: QSRC_TMEM, 4-7: QSRC_HYB
-  std::vector<int2> maps[NB];
-  size_t bucket_smem[NB] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (size_t b = 0; b < batched.size(); ++b) {
-    const ccvm_solve_desc& d = descs[batched[b]];
-    fill_params(&d, sched + jobs[b].offset * SCHED_W, plans[b].cg, items[b].p);
-    items[b].L = plans[b].L;
-    int k = 0;
-    while (bucket_threads[k] < plans[b].threads) ++k;
-    if (plans[b].qsrc == QSRC_HYB) k += 4;
-    for (int c = 0; c < plans[b].ctas; ++c) maps[k].push_back(make_int2((int)b, c));
-    if (plans[b].smem > bucket_smem[k]) bucket_smem[k] = plans[b].smem;
-  }
-  size_t total_ctas = 0;
-  for (int k = 0; k < NB; ++k) total_ctas += maps[k].size();
-  CUDA_TRY(items_buf.alloc(items.size() * sizeof(BatchItem)));
-  CUDA_TRY(map_buf.alloc(total_ctas * sizeof(int2)));
-  d_items = items_buf.as<BatchItem>();
-  d_map = map_buf.as<int2>();
-  CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(BatchItem), cudaMemcpyHostToDevice, st));
-  size_t off = 0;
-  const bool adam = alg == CCVM_ALG_ADAM;
-  for (int k = 0; k < NB && !rc; ++k) {
-    if (maps[k].empty()) continue;
-    const size_t n = maps[k].size();
-    CUDA_TRY(cudaMemcpyAsync(d_map + off, maps[k].data(), n * sizeof(int2), cudaMemcpyHostToDevice, st));
-#define BATCH_LAUNCH_Q(S, A, Q)                                                                            \
-  {                                                                                                        \
-    auto kern = sde_tmem_batch_kernel<S, A, Q>;                                                            \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bucket_smem[k]); \
-    if (e != cudaSuccess) rc = fail(CCVM_E_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));      \
-    else kern<<<(unsigned)n, bucket_threads[k & 3], bucket_smem[k], st>>>(d_items, d_map + off);           \
-  }
-#define BATCH_LAUNCH(S, A)                                \
-  if (k < 4) BATCH_LAUNCH_Q(S, A, QSRC_TMEM) else BATCH_LAUNCH_Q(S, A, QSRC_HYB)
-    switch (solver * 2 + (adam ? 1 : 0)) {
-      case 0: BATCH_LAUNCH(SOLVER_DL, false) break;
-      case 1: BATCH_LAUNCH(SOLVER_DL, true) break;
-      case 2: BATCH_LAUNCH(SOLVER_MF, false) break;
-      case 3: BATCH_LAUNCH(SOLVER_MF, true) break;
-      case 4: BATCH_LAUNCH(SOLVER_LV, false) break;
-      case 5: BATCH_LAUNCH(SOLVER_LV, true) break;
-      case 6: BATCH_LAUNCH(SOLVER_PLV, false) break;
-      default: BATCH_LAUNCH(SOLVER_PLV, true) break;
-    }
-#undef BATCH_LAUNCH
-#undef BATCH_LAUNCH_Q
-    if (!rc && cudaGetLastError() != cudaSuccess) rc = fail(CCVM_E_CUDA, "batched launch failed");
-    off += n;
-  }
-  return rc;
-}
-
-__global__ void build_schedule_batch_kernel(const SchedJob* __restrict__ jobs, float* __restrict__ out) {
-  const SchedJob job = jobs[blockIdx.y];
-  if (blockIdx.x * blockDim.x >= job.a.iterations) return;
-  schedule_row(job.a, blockIdx.x * blockDim.x + threadIdx.x, out + job.offset * SCHED_W);
-}
-
-// ------------------------------------------------------------------------- epilogue
-// One warp walks one trajectory at a time; lanes own variables j = lane, lane+32, ...
-// The working vector x lives in a per-warp shared buffer; Q is staged in shared memory with an
-// odd leading dimension (row and column sweeps are both conflict-free) when it fits, else read
-// through L2.  The objective is reduced with warp shuffles.
-struct EpiParams {
-  const float* q;
-  const float* v;
-  const float* state;
-  const float* m1vec;
-  const float* m2vec;
-  float* pv;
-  float* energy;
-  int n, batch, ld, q_in_smem;
-  int map1, map2, pp, pp_iters;
-  float m1s, m1o, m2s, m2o, step, lo, hi, scaled_by;
-};
-
-constexpr int EPI_WARPS = 8;
-
+// ------------------------------------------------------------------------- epilogue (stand-alone)
+// The bodies live in epilogue.cuh (shared with the tail of the persistent kernels).
 __global__ void __launch_bounds__(EPI_WARPS * 32) epilogue_kernel(const EpiParams p) {
   extern __shared__ __align__(16) float esm[];
-  const int N = p.n, LD = p.ld;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* qs = esm;
-  float* xbuf = esm + (p.q_in_smem ? (size_t)N * LD : 0) + (size_t)warp * 2 * N;
-  const float* Q = p.q;
-  int ld = N;
-  if (p.q_in_smem) {
-    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
-      const int i = idx / N, j = idx - i * N;
-      qs[i * LD + j] = p.q[idx];
-    }
-    Q = qs;
-    ld = LD;
-  }
-  __syncthreads();
-
-  for (int b = blockIdx.x * EPI_WARPS + warp; b < p.batch; b += gridDim.x * EPI_WARPS) {
-    float* x = xbuf;
-    float* y = xbuf + N;
-    for (int j = lane; j < N; j += 32) {
-      float val = p.state[(size_t)b * N + j];
-      if (p.map1) val = val * (p.m1vec ? p.m1vec[j] : p.m1s) + p.m1o;
-      x[j] = val;
-    }
-    __syncwarp();
-    if (p.pp == CCVM_PP_GRAD_DESCENT) {
-      // x <- clamp(x - step (xQ + V), lo, hi), all variables from the OLD x (grad_descent.py:61-64)
-      for (int it = 0; it < p.pp_iters; ++it) {
-        for (int j = lane; j < N; j += 32) {
-          float acc = 0.f;
-          for (int i = 0; i < N; ++i) acc = fmaf(x[i], Q[i * ld + j], acc);
-          const float g = acc + p.v[j];
-          y[j] = clampf(x[j] + (-p.step) * g, p.lo, p.hi);
-        }
-        __syncwarp();
-        float* tmp = x;
-        x = y;
-        y = tmp;
-      }
-    } else if (p.pp == CCVM_PP_ADAM) {
-      // one torch.optim.Adam step on 1/2 xQx + Vx then clamp (adam.py:58-66):
-      // g = 1/2 (xQ + x Q^T) + V ; x <- clamp(x - lr * (m/(1-b1)) / (sqrt(v/(1-b2)) + eps))
-      for (int j = lane; j < N; j += 32) {
-        float a1 = 0.f, a2 = 0.f;
-        for (int i = 0; i < N; ++i) {
-          a1 = fmaf(x[i], Q[i * ld + j], a1);
-          a2 = fmaf(x[i], Q[j * ld + i], a2);
-        }
-        const float g = 0.5f * (a1 + a2) + p.v[j];
-        const float m = (1.f - 0.9f) * g, vv = (1.f - 0.99f) * g * g;
-        const float den = sqrtf(vv) / sqrtf(1.f - 0.99f) + 1e-8f;
-        y[j] = clampf(x[j] - (p.step / (1.f - 0.9f)) * (m / den), p.lo, p.hi);
-      }
-      __syncwarp();
-      float* tmp = x;
-      x = y;
-      y = tmp;
-    }
-    if (p.pv)
-      for (int j = lane; j < N; j += 32) p.pv[(size_t)b * N + j] = x[j];
-    if (p.energy) {
-      if (p.map2) {
-        for (int j = lane; j < N; j += 32) y[j] = x[j] * (p.m2vec ? p.m2vec[j] : p.m2s) + p.m2o;
-        __syncwarp();
-        x = y;
-      }
-      // E = (1/2 x Q x + V x) * scaled_by   (problem_instance.py:226-241)
-      float e1 = 0.f, e2 = 0.f;
-      for (int j = lane; j < N; j += 32) {
-        float acc = 0.f;
-        for (int i = 0; i < N; ++i) acc = fmaf(x[i], Q[i * ld + j], acc);
-        e1 = fmaf(acc, x[j], e1);
-        e2 = fmaf(p.v[j], x[j], e2);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        e1 += __shfl_xor_sync(0xffffffffu, e1, o);
-        e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-      }
-      if (lane == 0) p.energy[b] = 0.5f * (e1 * p.scaled_by) + e2 * p.scaled_by;
-    }
-    __syncwarp();
-  }
+  epilogue_run(p, esm, 0, p.batch, blockIdx.x, gridDim.x);
 }
 
-// Tiled variant for the change of variables + gradient-descent post-processor + energy (everything but
-// the Adam post-processor, whose gradient also walks Q by rows).  The kernel above reads the whole
-// matrix once per TRAJECTORY and iteration (2.5 GB through L2 for B = 1000, n = 250, 10 iterations:
-// 660 us, a third of the solve it follows); here a tile of 8 trajectories shares every Q element:
-// `wpt` warps split the columns of the tile (one column per lane and 32 * wpt columns per pass, CPL
-// passes), the 8 x-values of a row come from one broadcast LDS.128 pair, and the dot products keep
-// the single-accumulator, ascending-i order of the reference einsum (same values as the kernel above;
-// only the final energy sum is associated differently).
-constexpr int EPT = 8;  // trajectories per tile
-
-template <int CPL>
-__global__ void __launch_bounds__(256) epilogue_tile_kernel(const EpiParams p, const int wpt) {
-  extern __shared__ __align__(16) float esm[];
-  const int N = p.n;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tpc = 8 / wpt;                      // tiles per CTA
-  const int tile = warp / wpt, wt = warp - tile * wpt;
-  float* qs = esm;
-  float* xall = esm + (p.q_in_smem ? (((size_t)N * N + 3) & ~(size_t)3) : 0);  // 16-byte aligned (LDS.128)
-  float* red = xall + (size_t)tpc * 2 * N * EPT;  // [tpc][wpt][EPT][2]
-  if (p.q_in_smem) {
-    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) qs[idx] = p.q[idx];
-  }
-  __syncthreads();
-  if (tile >= tpc) return;                      // warps that do not fill a tile (8 % wpt != 0)
-  const float* Q = p.q_in_smem ? qs : p.q;
-  float* x = xall + (size_t)tile * 2 * N * EPT;
-  float* y = x + (size_t)N * EPT;
-  const int nthr = wpt * 32, tl = wt * 32 + lane;
-  auto tile_sync = [&]() {
-    if (wpt == 1) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(1 + tile), "r"(nthr) : "memory");
-  };
-  int jc[CPL];
-  bool jok[CPL];
-  float vj[CPL];
-#pragma unroll
-  for (int c = 0; c < CPL; ++c) {
-    const int j = (wt * CPL + c) * 32 + lane;
-    jok[c] = j < N;
-    jc[c] = jok[c] ? j : 0;
-    vj[c] = p.v[jc[c]];
-  }
-  // acc[c][tb] = sum_i x[i][tb] * Q[i][j_c]   (single accumulator per element, ascending i)
-  auto contract = [&](const float* xs, float (&acc)[CPL][EPT]) {
-#pragma unroll
-    for (int c = 0; c < CPL; ++c)
-#pragma unroll
-      for (int tb = 0; tb < EPT; ++tb) acc[c][tb] = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < N; ++i) {
-      const float4 x0 = *reinterpret_cast<const float4*>(xs + (size_t)i * EPT);
-      const float4 x1 = *reinterpret_cast<const float4*>(xs + (size_t)i * EPT + 4);
-      const float xv[EPT] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-#pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        const float q = Q[(size_t)i * N + jc[c]];
-#pragma unroll
-        for (int tb = 0; tb < EPT; ++tb) acc[c][tb] = fmaf(xv[tb], q, acc[c][tb]);
-      }
-    }
-  };
-
-  for (long long b0 = ((long long)blockIdx.x * tpc + tile) * EPT; b0 < p.batch; b0 += (long long)gridDim.x * tpc * EPT) {
-    for (int idx = tl; idx < N * EPT; idx += nthr) {
-      const int tb = idx / N, j = idx - tb * N;
-      float val = 0.f;
-      if (b0 + tb < p.batch) {
-        val = p.state[(size_t)(b0 + tb) * N + j];
-        if (p.map1) val = val * (p.m1vec ? p.m1vec[j] : p.m1s) + p.m1o;
-      }
-      x[(size_t)j * EPT + tb] = val;
-    }
-    tile_sync();
-    float acc[CPL][EPT];
-    if (p.pp == CCVM_PP_GRAD_DESCENT) {
-      // x <- clamp(x - step (xQ + V), lo, hi), all variables from the OLD x (grad_descent.py:61-64)
-      for (int it = 0; it < p.pp_iters; ++it) {
-        contract(x, acc);
-#pragma unroll
-        for (int c = 0; c < CPL; ++c)
-          if (jok[c]) {
-#pragma unroll
-            for (int tb = 0; tb < EPT; ++tb) {
-              const float g = acc[c][tb] + vj[c];
-              y[(size_t)jc[c] * EPT + tb] = clampf(x[(size_t)jc[c] * EPT + tb] + (-p.step) * g, p.lo, p.hi);
-            }
-          }
-        tile_sync();
-        float* tmp = x;
-        x = y;
-        y = tmp;
-      }
-    }
-    if (p.pv)
-      for (int idx = tl; idx < N * EPT; idx += nthr) {
-        const int tb = idx / N, j = idx - tb * N;
-        if (b0 + tb < p.batch) p.pv[(size_t)(b0 + tb) * N + j] = x[(size_t)j * EPT + tb];
-      }
-    if (p.energy) {
-      if (p.map2) {
-        for (int idx = tl; idx < N * EPT; idx += nthr) {
-          const int j = idx / EPT;
-          y[idx] = x[idx] * (p.m2vec ? p.m2vec[j] : p.m2s) + p.m2o;
-        }
-        tile_sync();
-        float* tmp = x;
-        x = y;
-        y = tmp;
-      }
-      // E = (1/2 x Q x + V x) * scaled_by   (problem_instance.py:226-241)
-      contract(x, acc);
-      float e1[EPT], e2[EPT];
-#pragma unroll
-      for (int tb = 0; tb < EPT; ++tb) {
-        e1[tb] = 0.f;
-        e2[tb] = 0.f;
-#pragma unroll
-        for (int c = 0; c < CPL; ++c)
-          if (jok[c]) {
-            const float xj = x[(size_t)jc[c] * EPT + tb];
-            e1[tb] = fmaf(acc[c][tb], xj, e1[tb]);
-            e2[tb] = fmaf(vj[c], xj, e2[tb]);
-          }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          e1[tb] += __shfl_xor_sync(0xffffffffu, e1[tb], o);
-          e2[tb] += __shfl_xor_sync(0xffffffffu, e2[tb], o);
-        }
-      }
-      float* rt = red + (size_t)tile * wpt * EPT * 2;
-      if (lane == 0) {
-#pragma unroll
-        for (int tb = 0; tb < EPT; ++tb) {
-          rt[(wt * EPT + tb) * 2] = e1[tb];
-          rt[(wt * EPT + tb) * 2 + 1] = e2[tb];
-        }
-      }
-      tile_sync();
-      if (wt == 0 && lane < EPT && b0 + lane < p.batch) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int w = 0; w < wpt; ++w) {
-          s1 += rt[(w * EPT + lane) * 2];
-          s2 += rt[(w * EPT + lane) * 2 + 1];
-        }
-        p.energy[b0 + lane] = 0.5f * (s1 * p.scaled_by) + s2 * p.scaled_by;
-      }
-    }
-    tile_sync();
-  }
-}
-
-static int run_epilogue_tiled(EpiParams p, const DeviceInfo& di, cudaStream_t st, bool& done) {
-  done = false;
-  const int N = p.n;
-  if (p.pp == CCVM_PP_ADAM || N > 1024 || getenv("CCVM_EPILOGUE_LEGACY")) return CCVM_OK;
-  int wpt = (N + 31) / 32;
-  if (wpt > 8) wpt = 8;
-  const int cpl = (N + 32 * wpt - 1) / (32 * wpt);   // 1 for n <= 256, 2 for <= 512, 4 for <= 1024
-  const int tpc = 8 / wpt;
-  const size_t xb = ((size_t)tpc * 2 * N * EPT + (size_t)tpc * wpt * EPT * 2) * sizeof(float);
-  const size_t qb = (((size_t)N * N + 3) & ~(size_t)3) * sizeof(float);
-  p.q_in_smem = (qb + xb) <= (size_t)di.max_smem;
-  const size_t smem = xb + (p.q_in_smem ? qb : 0);
-  if (smem > (size_t)di.max_smem) return CCVM_OK;
-  long long grid = ((long long)p.batch + tpc * EPT - 1) / (tpc * EPT);
-  if (grid > 4LL * di.sms) grid = 4LL * di.sms;
-#define EPI_TILE_LAUNCH(C)                                                                                     \
-  {                                                                                                            \
-    CUDA_TRY(cudaFuncSetAttribute(epilogue_tile_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    epilogue_tile_kernel<C><<<(unsigned)grid, 256, smem, st>>>(p, wpt);                                       \
-  }
-  if (cpl <= 1) EPI_TILE_LAUNCH(1) else if (cpl == 2) EPI_TILE_LAUNCH(2) else EPI_TILE_LAUNCH(4)
-#undef EPI_TILE_LAUNCH
-  CUDA_TRY(cudaGetLastError());
-  done = true;
-  return CCVM_OK;
-}
-
-static int run_epilogue(const EpiParams& p0, cudaStream_t st) {
-  EpiParams p = p0;
-  DeviceInfo di;
-  int rc = device_info(di);
-  if (rc) return rc;
-  bool done = false;
-  if ((rc = run_epilogue_tiled(p, di, st, done))) return rc;
-  if (done) return CCVM_OK;
-  p.ld = p.n | 1;
-  size_t xb = (size_t)EPI_WARPS * 2 * p.n * sizeof(float);
-  size_t qb = (size_t)p.n * p.ld * sizeof(float);
-  p.q_in_smem = (qb + xb) <= (size_t)di.max_smem;
-  const size_t smem = xb + (p.q_in_smem ? qb : 0);
-  if (smem > (size_t)di.max_smem) return fail(CCVM_E_TOO_LARGE, "n=%d too large for the epilogue kernel", p.n);
-  CUDA_TRY(cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = (p.batch + EPI_WARPS - 1) / EPI_WARPS;
-  if (grid > 2 * di.sms) grid = 2 * di.sms;
-  epilogue_kernel<<<grid, EPI_WARPS * 32, smem, st>>>(p);
-  CUDA_TRY(cudaGetLastError());
-  return CCVM_OK;
-}
-
-extern "C" int ccvm_epilogue(const ccvm_epilogue_desc* d, void* stream) {
+static int epi_params_from_desc(const ccvm_epilogue_desc* d, EpiParams& p) {
   if (!d) return fail(CCVM_E_INVALID, "null descriptor");
-  if (d->n < 1 || d->batch < 1) return fail(CCVM_E_INVALID, "n and batch must be >= 1");
-  if (!d->q || !d->v || !d->state) return fail(CCVM_E_INVALID, "q, v and state are required");
   if (d->post_processor < CCVM_PP_NONE || d->post_processor > CCVM_PP_ADAM)
     return fail(CCVM_E_INVALID, "unknown post-processor id %d", d->post_processor);
-  EpiParams p;
   memset(&p, 0, sizeof(p));
   p.q = d->q;
   p.v = d->v;
@@ -1257,6 +520,53 @@ extern "C" int ccvm_epilogue(const ccvm_epilogue_desc* d, void* stream) {
   p.lo = (float)d->pp_lower;
   p.hi = (float)d->pp_upper;
   p.scaled_by = (float)d->scaled_by;
+  return CCVM_OK;
+}
+
+// Picks the body (tiles of 8 trajectories, or a warp per trajectory for the Adam post-processor),
+// decides whether Q is staged in shared memory and returns the dynamic shared memory `p` needs in
+// CTAs of `nwarps` warps.
+static int plan_epilogue(EpiParams& p, int nwarps, int max_smem, size_t& smem) {
+  bool allow_tiled = getenv("CCVM_EPILOGUE_LEGACY") == nullptr;
+  for (;;) {
+    p.wpt = p.cpl = 0;
+    const EpiGeometry g = epi_geometry(p, nwarps, allow_tiled);
+    p.q_in_smem = g.floats_q * sizeof(float) <= (size_t)max_smem;
+    smem = (p.q_in_smem ? g.floats_q : g.floats_noq) * sizeof(float);
+    if (smem <= (size_t)max_smem) return CCVM_OK;
+    if (!g.tiled) return fail(CCVM_E_TOO_LARGE, "n=%d too large for the epilogue", p.n);
+    allow_tiled = false;  // the tile buffers alone do not fit: warp per trajectory
+  }
+}
+
+static int run_epilogue(const EpiParams& p0, cudaStream_t st) {
+  EpiParams p = p0;
+  DeviceInfo di;
+  int rc = device_info(di);
+  if (rc) return rc;
+  size_t smem = 0;
+  if ((rc = plan_epilogue(p, EPI_WARPS, di.max_smem, smem))) return rc;
+  long long grid;
+  if (p.wpt > 0) {
+    const int per_cta = (EPI_WARPS / p.wpt) * EPT;
+    grid = ((long long)p.batch + per_cta - 1) / per_cta;
+    if (grid > 4LL * di.sms) grid = 4LL * di.sms;
+  } else {
+    grid = (p.batch + EPI_WARPS - 1) / EPI_WARPS;
+    if (grid > 2LL * di.sms) grid = 2LL * di.sms;
+  }
+  CUDA_TRY(cudaFuncSetAttribute(epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  epilogue_kernel<<<(unsigned)grid, EPI_WARPS * 32, smem, st>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
+extern "C" int ccvm_epilogue(const ccvm_epilogue_desc* d, void* stream) {
+  EpiParams p;
+  int rc = epi_params_from_desc(d, p);
+  if (rc) return rc;
+  if (d->n < 1 || d->batch < 1) return fail(CCVM_E_INVALID, "n and batch must be >= 1");
+  if (!d->q || !d->v || !d->state) return fail(CCVM_E_INVALID, "q, v and state are required");
   return run_epilogue(p, (cudaStream_t)stream);
 }
 
@@ -1316,74 +626,10 @@ extern "C" int ccvm_postprocess_adam(float* x, const float* q, const float* v, i
 }
 
 // -------------------------------------------------------------------- solution stats
-struct StatsOut {
-  float best;
-  int arg_best;
-  int counts[7];
-};
-
-__device__ __forceinline__ void stats_body(const float* __restrict__ energy, int batch, float optimal,
-                                           StatsOut* out) {
-  __shared__ float s_best[32];
-  __shared__ int s_arg[32];
-  __shared__ int s_cnt[7];
-  __shared__ int s_nan;
-  const float thr[7] = {0.1f, 1.f, 2.f, 3.f, 4.f, 5.f, 10.f};
-  if (threadIdx.x < 7) s_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_nan = 0;
-  __syncthreads();
-  float best = -INFINITY;
-  int arg = 0x7fffffff, cnt[7] = {0, 0, 0, 0, 0, 0, 0};
-  bool saw_nan = false;
-  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
-    const float val = -energy[b];
-    if (val != val) saw_nan = true;
-    if (val > best) {
-      best = val;
-      arg = b;
-    }
-    // gap = (optimal - val) * 100 / |val|   (solution.py:125-129), fp32 like the reference
-    const float gap = __fdiv_rn(__fmul_rn(__fsub_rn(optimal, val), 100.f), fabsf(val));
-#pragma unroll
-    for (int k = 0; k < 7; ++k) cnt[k] += (gap <= thr[k]) ? 1 : 0;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-    if (ob > best || (ob == best && oa < arg)) {
-      best = ob;
-      arg = oa;
-    }
-#pragma unroll
-    for (int k = 0; k < 7; ++k) cnt[k] += __shfl_xor_sync(0xffffffffu, cnt[k], o);
-  }
-  if (saw_nan) atomicOr(&s_nan, 1);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
-    s_best[warp] = best;
-    s_arg[warp] = arg;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) atomicAdd(&s_cnt[k], cnt[k]);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float bb = s_best[0];
-    int ba = s_arg[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-      if (s_best[w] > bb || (s_best[w] == bb && s_arg[w] < ba)) {
-        bb = s_best[w];
-        ba = s_arg[w];
-      }
-    out->best = s_nan ? NAN : bb;  // torch.max propagates NaN
-    out->arg_best = ba == 0x7fffffff ? 0 : ba;
-    for (int k = 0; k < 7; ++k) out->counts[k] = s_cnt[k];
-  }
-}
-
 __global__ void __launch_bounds__(1024) stats_kernel(const float* __restrict__ energy, int batch, float optimal,
                                                      StatsOut* out) {
-  stats_body(energy, batch, optimal, out);
+  StatsPartial sp;
+  if (stats_block_reduce(energy, 0, batch, optimal, sp)) stats_finalize(sp, out);
 }
 
 // one block per instance: energies concatenated, instance i = energy[offsets[i] .. offsets[i+1])
@@ -1392,7 +638,8 @@ __global__ void __launch_bounds__(1024) stats_batch_kernel(const float* __restri
                                                            const float* __restrict__ optimal, StatsOut* out) {
   const int i = blockIdx.x;
   const long long lo = offsets[i];
-  stats_body(energy + lo, (int)(offsets[i + 1] - lo), optimal[i], out + i);
+  StatsPartial sp;
+  if (stats_block_reduce(energy + lo, 0, offsets[i + 1] - lo, optimal[i], sp)) stats_finalize(sp, out + i);
 }
 
 extern "C" int ccvm_solution_stats_batch(const float* energy, const int64_t* offsets, const float* optimal_values,
@@ -1413,25 +660,346 @@ extern "C" int ccvm_solution_stats(const float* energy, int32_t batch, double op
   return CCVM_OK;
 }
 
+// --------------------------------------------------------------------------- one Solver.__call__
+// Fills the tail of a persistent kernel from an epilogue descriptor: the epilogue runs on the solve's
+// own q / v / final state (`epi`'s q, v, state, n and batch are ignored) in CTAs of `threads` threads
+// whose loop needs `loop_smem` bytes; `smem` returns the dynamic shared memory of the launch.
+static int plan_fused_tail(const ccvm_solve_desc& d, const ccvm_epilogue_desc* epi, double optimal, int threads,
+                           size_t loop_smem, int max_smem, unsigned ctas, StatsAccum* accum, FusedOut* out,
+                           FusedTail& f, size_t& smem) {
+  smem = loop_smem;
+  f.epilogue = f.stats = 0;
+  if (!epi) return CCVM_OK;
+  int rc = epi_params_from_desc(epi, f.epi);
+  if (rc) return rc;
+  EpiParams& e = f.epi;
+  e.q = d.q;
+  e.v = d.v;
+  e.n = d.n;
+  e.batch = d.batch;
+  e.state = d.solver == CCVM_SOLVER_MF ? d.out1 : d.out0;
+  if (out && !e.energy) return fail(CCVM_E_INVALID, "solution statistics need the energy buffer");
+  size_t need = 0;
+  if ((rc = plan_epilogue(e, threads / 32, max_smem, need))) return rc;
+  if (need > smem) smem = need;
+  f.epilogue = 1;
+  f.stats = out != nullptr;
+  f.total_ctas = ctas;
+  f.optimal = (float)optimal;
+  f.accum = accum;
+  f.out = out;
+  return CCVM_OK;
+}
+
+static int solve_impl(const ccvm_solve_desc* d, const ccvm_epilogue_desc* epi, double optimal, FusedOut* result,
+                      cudaStream_t st) {
+  int rc = validate_solve(d);
+  if (rc) return rc;
+  DeviceInfo di;
+  if ((rc = device_info(di))) return rc;
+  const int path = choose_path(*d);
+  const bool adam = d->algorithm == CCVM_ALG_ADAM;
+  const size_t sched_row_bytes = (size_t)d->iterations * SCHED_W * sizeof(float);
+  StreamBuf sched_buf(st), qs_buf(st), accum_buf(st);
+  SdeParams p;
+  bool fused = false;
+
+  if (path == PATH_TC) {
+    CUDA_TRY(sched_buf.alloc(sched_row_bytes));
+    build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(sched_args(d), sched_buf.as<float>());
+    CUDA_TRY(cudaGetLastError());
+    fill_params(d, sched_buf.as<float>(), 0, p);
+    if ((rc = solve_tc(d, p, st))) return rc;
+  } else {
+    TmemPlan TP;
+    if ((rc = plan_tmem(*d, di, path, TP))) return rc;
+    FusedTail f;
+    memset(&f, 0, sizeof(f));
+    // the schedule table is evaluated by every CTA in its prologue (one launch per solve)
+    CUDA_TRY(sched_buf.alloc(sched_row_bytes * TP.ctas));
+    f.sched_inline = 1;
+    f.sa = sched_args(d);
+    f.sched_scratch = sched_buf.as<float>();
+    fill_params(d, nullptr, TP.cg, p);
+    if (TP.qsrc == QSRC_GMEM) {
+      const int np = 4 * TP.cg;
+      CUDA_TRY(qs_buf.alloc((size_t)np * np * sizeof(float)));
+      scale_q_kernel<<<(np * np + 255) / 256, 256, 0, st>>>(p.q, p.drift_s_vec, p.drift_s, p.a_half, p.n, np,
+                                                            qs_buf.as<float>());
+      CUDA_TRY(cudaGetLastError());
+      TP.L.qs = qs_buf.as<float>();
+    }
+    if (epi && getenv("CCVM_NO_FUSE") == nullptr) {
+      StatsAccum* accum = nullptr;
+      if (result) {
+        CUDA_TRY(accum_buf.alloc(sizeof(StatsAccum)));
+        accum = accum_buf.as<StatsAccum>();
+        CUDA_TRY(cudaMemsetAsync(accum, 0, sizeof(StatsAccum), st));
+      }
+      if ((rc = plan_fused_tail(*d, epi, optimal, TP.threads, TP.smem, di.max_smem, (unsigned)TP.ctas, accum, result, f,
+                                TP.smem)))
+        return rc;
+      fused = true;
+    }
+#define LAUNCH_TMEM(S, A) rc = launch_tmem<S, A>(p, TP, f, st)
+    CCVM_DISPATCH_TILE(d->solver, adam, LAUNCH_TMEM)
+#undef LAUNCH_TMEM
+    if (rc) return rc;
+  }
+  if (epi && !fused) {
+    ccvm_epilogue_desc ed = *epi;
+    ed.n = d->n;
+    ed.batch = d->batch;
+    ed.q = d->q;
+    ed.v = d->v;
+    ed.state = d->solver == CCVM_SOLVER_MF ? d->out1 : d->out0;
+    if ((rc = ccvm_epilogue(&ed, st))) return rc;
+    if (result) {
+      if (!ed.energy) return fail(CCVM_E_INVALID, "solution statistics need the energy buffer");
+      CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(FusedOut), st));
+      if ((rc = ccvm_solution_stats(ed.energy, d->batch, optimal, &result->stats, st))) return rc;
+    }
+  }
+  return CCVM_OK;
+}
+
+extern "C" int ccvm_solve(const ccvm_solve_desc* d, void* stream) {
+  return solve_impl(d, nullptr, 0.0, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ccvm_solve_fused(const ccvm_solve_desc* d, const ccvm_epilogue_desc* epi, double optimal_value,
+                                void* result, void* stream) {
+  if (!epi) return fail(CCVM_E_INVALID, "ccvm_solve_fused needs an epilogue descriptor");
+  return solve_impl(d, epi, optimal_value, (FusedOut*)result, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ batched instances
+struct SchedJob {
+  SchedArgs a;
+  long long offset;  // first row of this problem in the shared schedule table
+};
+
+__global__ void build_schedule_batch_kernel(const SchedJob* __restrict__ jobs, float* __restrict__ out) {
+  const SchedJob job = jobs[blockIdx.y];
+  if (blockIdx.x * blockDim.x >= job.a.iterations) return;
+  schedule_row(job.a, blockIdx.x * blockDim.x + threadIdx.x, out + job.offset * SCHED_W);
+}
+
+static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_desc* epis, const double* optimal,
+                            int32_t count, FusedOut* results, cudaStream_t st) {
+  if (!descs || count < 1) return fail(CCVM_E_INVALID, "ccvm_solve_batch needs at least one descriptor");
+  if (results && (!epis || !optimal)) return fail(CCVM_E_INVALID, "statistics need epilogue descriptors and optimal values");
+  DeviceInfo di;
+  int rc = device_info(di);
+  if (rc) return rc;
+  const int solver = descs[0].solver, alg = descs[0].algorithm;
+  std::vector<int> batched, single;
+  for (int i = 0; i < count; ++i) {
+    if ((rc = validate_solve(&descs[i]))) return rc;
+    if (descs[i].solver != solver || descs[i].algorithm != alg)
+      return fail(CCVM_E_INVALID, "all descriptors of a batch must share solver and algorithm");
+    if (descs[i].rng_mode != CCVM_RNG_PHILOX || descs[i].evolution_step > 0)
+      return fail(CCVM_E_INVALID, "batched solves use Philox noise and no evolution sampling");
+    const int path = choose_path(descs[i]);
+    (path == PATH_TMEM || path == PATH_HYB ? batched : single).push_back(i);
+  }
+  for (int i : single)
+    if ((rc = solve_impl(&descs[i], epis ? &epis[i] : nullptr, optimal ? optimal[i] : 0.0, results ? results + i : nullptr, st)))
+      return rc;
+  if (batched.empty()) return CCVM_OK;
+
+  // plans, schedule table offsets
+  std::vector<TmemPlan> plans(batched.size());
+  std::vector<SchedJob> jobs(batched.size());
+  long long rows = 0, total_traj = 0;
+  int max_t = 0;
+  for (int i : batched) total_traj += descs[i].batch;
+  const int share = (int)((total_traj + di.sms - 1) / di.sms);
+  for (size_t b = 0; b < batched.size(); ++b) {
+    const ccvm_solve_desc& d = descs[batched[b]];
+    if ((rc = plan_tmem(d, di, choose_path(d), plans[b], share, true))) return rc;
+    jobs[b].a = sched_args(&d);
+    jobs[b].offset = rows;
+    rows += d.iterations;
+    if (d.iterations > max_t) max_t = d.iterations;
+  }
+  StreamBuf sched_buf(st), jobs_buf(st), items_buf(st), map_buf(st), accum_buf(st);
+  CUDA_TRY(sched_buf.alloc((size_t)rows * SCHED_W * sizeof(float)));
+  CUDA_TRY(jobs_buf.alloc(jobs.size() * sizeof(SchedJob)));
+  float* sched = sched_buf.as<float>();
+  SchedJob* d_jobs = jobs_buf.as<SchedJob>();
+  CUDA_TRY(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(SchedJob), cudaMemcpyHostToDevice, st));
+  build_schedule_batch_kernel<<<dim3((max_t + 127) / 128, (unsigned)jobs.size()), 128, 0, st>>>(d_jobs, sched);
+  CUDA_TRY(cudaGetLastError());
+  const bool fuse = epis != nullptr && getenv("CCVM_NO_FUSE") == nullptr;
+  StatsAccum* accum = nullptr;
+  if (fuse && results) {
+    CUDA_TRY(accum_buf.alloc(batched.size() * sizeof(StatsAccum)));
+    accum = accum_buf.as<StatsAccum>();
+    CUDA_TRY(cudaMemsetAsync(accum, 0, batched.size() * sizeof(StatsAccum), st));
+  }
+
+  // items + CTA maps, bucketed by (Q source, block size, compiled-in column-group count) so that small
+  // instances do not pay for big blocks and the benchmarking sizes get the fully unrolled kernels
+  struct Bucket {
+    int threads, qsrc, cgc;
+    size_t smem;
+    std::vector<int2> map;
+  };
+  std::vector<Bucket> buckets;
+  std::vector<BatchItem> items(batched.size());
+  const int bucket_threads[4] = {32, 64, 128, 256};
+  for (size_t b = 0; b < batched.size(); ++b) {
+    const ccvm_solve_desc& d = descs[batched[b]];
+    fill_params(&d, sched + jobs[b].offset * SCHED_W, plans[b].cg, items[b].p);
+    items[b].L = plans[b].L;
+    memset(&items[b].f, 0, sizeof(FusedTail));
+    int k = 0;
+    while (bucket_threads[k] < plans[b].threads) ++k;
+    size_t smem = plans[b].smem;
+    if (fuse) {
+      if ((rc = plan_fused_tail(d, &epis[batched[b]], optimal ? optimal[batched[b]] : 0.0, bucket_threads[k], plans[b].smem,
+                                di.max_smem, (unsigned)plans[b].ctas, accum ? accum + b : nullptr,
+                                results ? results + batched[b] : nullptr, items[b].f, smem)))
+        return rc;
+    }
+    size_t which = buckets.size();
+    for (size_t u = 0; u < buckets.size(); ++u)
+      if (buckets[u].threads == bucket_threads[k] && buckets[u].qsrc == plans[b].qsrc && buckets[u].cgc == plans[b].cgc)
+        which = u;
+    if (which == buckets.size()) buckets.push_back(Bucket{bucket_threads[k], plans[b].qsrc, plans[b].cgc, 0, {}});
+    Bucket& B = buckets[which];
+    for (int c = 0; c < plans[b].ctas; ++c) B.map.push_back(make_int2((int)b, c));
+    if (smem > B.smem) B.smem = smem;
+  }
+  size_t total_ctas = 0;
+  for (const Bucket& B : buckets) total_ctas += B.map.size();
+  CUDA_TRY(items_buf.alloc(items.size() * sizeof(BatchItem)));
+  CUDA_TRY(map_buf.alloc(total_ctas * sizeof(int2)));
+  BatchItem* d_items = items_buf.as<BatchItem>();
+  int2* d_map = map_buf.as<int2>();
+  CUDA_TRY(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(BatchItem), cudaMemcpyHostToDevice, st));
+  {
+    std::vector<int2> all;
+    all.reserve(total_ctas);
+    for (const Bucket& B : buckets) all.insert(all.end(), B.map.begin(), B.map.end());
+    CUDA_TRY(cudaMemcpyAsync(d_map, all.data(), total_ctas * sizeof(int2), cudaMemcpyHostToDevice, st));
+    // `all` is pageable host memory: the copy is staged before cudaMemcpyAsync returns
+  }
+  size_t off = 0;
+  const bool adam = alg == CCVM_ALG_ADAM;
+  for (const Bucket& B : buckets) {
+    BatchBucket bb;
+    bb.items = d_items;
+    bb.map = d_map + off;
+    bb.ctas = (unsigned)B.map.size();
+    bb.threads = B.threads;
+    bb.qsrc = B.qsrc;
+    bb.cgc = B.cgc;
+    bb.smem = B.smem;
+#define LAUNCH_BATCH(S, A) rc = launch_tmem_batch<S, A>(bb, st)
+    CCVM_DISPATCH_TILE(solver, adam, LAUNCH_BATCH)
+#undef LAUNCH_BATCH
+    if (rc) return rc;
+    off += B.map.size();
+  }
+  if (epis && !fuse) {
+    for (int i : batched) {
+      ccvm_epilogue_desc ed = epis[i];
+      ed.n = descs[i].n;
+      ed.batch = descs[i].batch;
+      ed.q = descs[i].q;
+      ed.v = descs[i].v;
+      ed.state = descs[i].solver == CCVM_SOLVER_MF ? descs[i].out1 : descs[i].out0;
+      if ((rc = ccvm_epilogue(&ed, st))) return rc;
+      if (results) {
+        CUDA_TRY(cudaMemsetAsync(results + i, 0, sizeof(FusedOut), st));
+        if ((rc = ccvm_solution_stats(ed.energy, descs[i].batch, optimal[i], &results[i].stats, st))) return rc;
+      }
+    }
+  }
+  return CCVM_OK;
+}
+
+extern "C" int ccvm_solve_batch(const ccvm_solve_desc* descs, int32_t count, void* stream) {
+  return solve_batch_impl(descs, nullptr, nullptr, count, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int ccvm_solve_batch_fused(const ccvm_solve_desc* descs, const ccvm_epilogue_desc* epis,
+                                      const double* optimal_values, int32_t count, void* results, void* stream) {
+  if (!epis) return fail(CCVM_E_INVALID, "ccvm_solve_batch_fused needs epilogue descriptors");
+  return solve_batch_impl(descs, epis, optimal_values, count, (FusedOut*)results, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------- noise dump (validation)
+// The normals a production solve draws, written in the replay layout noise[T][K][n][batch]: feeding this
+// tensor to the CPU oracle (or back to the engine in replay mode) reproduces a production run exactly,
+// which pins the production kernel variants (in-loop noise, compile-time column groups) to the oracle.
+__global__ void dump_noise_kernel(uint32_t k0, uint32_t k1, uint32_t off_lo, long long traj_base, int n, int batch,
+                                  int iterations, int K, float* __restrict__ noise) {
+  const int cg_count = (n + 3) / 4;
+  const size_t total = (size_t)iterations * K * cg_count * batch;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx % batch);
+    size_t r = idx / batch;
+    const int cg = (int)(r % cg_count);
+    r /= cg_count;
+    const int q = (int)(r % K);
+    const int t = (int)(r / K);
+    float w[4];
+    noise_normals4(k0, k1, off_lo, (unsigned long long)(traj_base + b), (uint32_t)t, (uint32_t)cg, (uint32_t)q, w[0], w[1],
+                   w[2], w[3]);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * cg + jj;
+      if (j < n) noise[(((size_t)t * K + q) * n + j) * (size_t)batch + b] = w[jj];
+    }
+  }
+}
+
+extern "C" int ccvm_dump_noise(const ccvm_solve_desc* d, float* noise, void* stream) {
+  if (!d || !noise) return fail(CCVM_E_INVALID, "bad argument to ccvm_dump_noise");
+  if (d->n < 1 || d->batch < 1 || d->iterations < 1) return fail(CCVM_E_INVALID, "n, batch and iterations must be >= 1");
+  if (d->solver < 0 || d->solver > 3) return fail(CCVM_E_INVALID, "unknown solver id %d", d->solver);
+  const int K = d->solver == CCVM_SOLVER_DL ? 2 : 1;
+  const size_t total = (size_t)d->iterations * K * ((d->n + 3) / 4) * d->batch;
+  size_t grid = (total + 255) / 256;
+  if (grid > 148 * 64) grid = 148 * 64;
+  dump_noise_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      (uint32_t)d->seed, (uint32_t)(d->seed >> 32) ^ (uint32_t)(d->offset >> 32), (uint32_t)d->offset, d->traj_base, d->n,
+      d->batch, d->iterations, K, noise);
+  CUDA_TRY(cudaGetLastError());
+  return CCVM_OK;
+}
+
 // ------------------------------------------------------- multi-GPU result records
-// One record per rank: [min energy, global trajectory index of the winner, 7 success counters,
-// winner's solution vector (n)] -- written by ONE kernel from the statistics block of
-// ccvm_solution_stats, all-gathered by the host layer, and reduced by ONE kernel on every rank
-// (ties go to the lowest rank, a NaN objective wins like torch.max(-E) propagates it).
+// One record per rank: [min energy, global trajectory index of the winner (two 32-bit halves), 7
+// success counters, winner's solution vector (n)] -- CCVM_RECORD_HEADER + n 32-bit words; the integer
+// fields are stored as INTEGERS (bit patterns inside the float buffer), so indices and counts beyond
+// 2^24 stay exact.  Written by ONE kernel from the statistics block of ccvm_solution_stats,
+// all-gathered by the host layer, and reduced by ONE kernel on every rank (ties go to the lowest rank,
+// a NaN objective wins like torch.max(-E) propagates it).
+constexpr int REC_H = CCVM_RECORD_HEADER;
+
 __global__ void pack_record_kernel(const StatsOut* __restrict__ stats, const float* __restrict__ pv, int n,
                                    long long traj_base, float* __restrict__ rec) {
   const int arg = stats->arg_best;
+  int* reci = reinterpret_cast<int*>(rec);
   if (threadIdx.x == 0) {
+    const unsigned long long g = (unsigned long long)(traj_base + arg);
     rec[0] = -stats->best;
-    rec[1] = (float)(traj_base + arg);
+    reci[1] = (int)(uint32_t)g;
+    reci[2] = (int)(uint32_t)(g >> 32);
   }
-  if (threadIdx.x < 7) rec[2 + threadIdx.x] = (float)stats->counts[threadIdx.x];
-  for (int j = threadIdx.x; j < n; j += blockDim.x) rec[9 + j] = pv[(size_t)arg * n + j];
+  if (threadIdx.x < 7) reci[3 + threadIdx.x] = stats->counts[threadIdx.x];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) rec[REC_H + j] = pv[(size_t)arg * n + j];
 }
 
 __global__ void merge_records_kernel(const float* __restrict__ gathered, int world, int n, float* __restrict__ out) {
   __shared__ int s_owner;
-  const int len = 9 + n;
+  const int len = REC_H + n;
+  const int* gi = reinterpret_cast<const int*>(gathered);
+  int* outi = reinterpret_cast<int*>(out);
   if (threadIdx.x == 0) {
     int owner = 0;
     float best = gathered[0];
@@ -1444,16 +1012,17 @@ __global__ void merge_records_kernel(const float* __restrict__ gathered, int wor
     }
     s_owner = owner;
     out[0] = -best;
-    out[1] = gathered[(size_t)owner * len + 1];
+    outi[1] = gi[(size_t)owner * len + 1];
+    outi[2] = gi[(size_t)owner * len + 2];
   }
   if (threadIdx.x < 7) {
-    float tot = 0.f;
-    for (int r = 0; r < world; ++r) tot += gathered[(size_t)r * len + 2 + threadIdx.x];
-    out[2 + threadIdx.x] = tot;
+    int tot = 0;
+    for (int r = 0; r < world; ++r) tot += gi[(size_t)r * len + 3 + threadIdx.x];
+    outi[3 + threadIdx.x] = tot;
   }
   __syncthreads();
-  const float* src = gathered + (size_t)s_owner * len + 9;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) out[9 + j] = src[j];
+  const float* src = gathered + (size_t)s_owner * len + REC_H;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) out[REC_H + j] = src[j];
 }
 
 extern "C" int ccvm_pack_record(const void* stats, const float* problem_variables, int32_t n, int64_t traj_base,
@@ -1547,7 +1116,7 @@ extern "C" int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = solve->n, b = solve->batch;
   if (solve->n < 1 || solve->batch < 1) return fail(CCVM_E_INVALID, "n and batch must be >= 1");
-  const size_t words = n * n + n + 3 * b * n + b * n + b + 16;
+  const size_t words = n * n + n + 3 * b * n + b * n + b + 16 + sizeof(FusedOut) / 4;
   StreamBuf host_buf(st);
   CUDA_TRY(host_buf.alloc(words * sizeof(float)));
   float* buf = host_buf.as<float>();
@@ -1574,17 +1143,11 @@ extern "C" int ccvm_solve_host(const ccvm_solve_desc* solve, const ccvm_epilogue
   sd.out2 = d_o2;
   sd.evolution_step = 0;
   sd.samples = nullptr;
-  if (!rc) rc = ccvm_solve(&sd, stream);
   ccvm_epilogue_desc ed = *epi;
-  ed.n = solve->n;
-  ed.batch = solve->batch;
-  ed.q = d_q;
-  ed.v = d_v;
-  ed.state = solve->solver == CCVM_SOLVER_MF ? d_o1 : d_o0;
   ed.problem_variables = d_pv;
   ed.energy = d_e;
-  if (!rc) rc = ccvm_epilogue(&ed, stream);
-  if (!rc) rc = ccvm_solution_stats(d_e, solve->batch, optimal_value, d_stats, stream);
+  // ONE launch: schedule, all iterations, change of variables, post-processor, energy, statistics
+  if (!rc) rc = solve_impl(&sd, &ed, optimal_value, (FusedOut*)d_stats, st);
   if (!rc) {
     if ((ce = cudaMemcpyAsync(h_energy, d_e, b * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
         (ce = cudaMemcpyAsync(h_stats, d_stats, sizeof(StatsOut), cudaMemcpyDeviceToHost, st)) != cudaSuccess)

@@ -7,6 +7,16 @@ namespace ccvm {
 
 enum : int { SOLVER_DL = 0, SOLVER_MF = 1, SOLVER_LV = 2, SOLVER_PLV = 3 };
 
+template <int SOLVER>
+struct SolverTraits {
+  static constexpr int K = (SOLVER == SOLVER_DL) ? 2 : 1;        // contraction inputs per trajectory
+  static constexpr int NSTATE = (SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) ? 1 : 2;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
 constexpr int SCHED_W = 8;  // floats per iteration in the schedule table
 // schedule slots (meaning depends on the solver, see build_schedule_kernel)
 enum : int { SC_A = 0, SC_P1 = 1, SC_P2 = 2, SC_N1 = 3, SC_N2 = 4, SC_IB1 = 5, SC_IB2 = 6 };
@@ -99,6 +109,19 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   n1 = r * sn;
 }
 
+// The engine's noise stream: four standard normals for (global trajectory gb, iteration t, column group
+// cg = j / 4, quadrature qi) under key (k0, k1) and stream offset off_lo -- one Philox4x32-10 call and two
+// Box-Muller pairs.  EVERY consumer (the tiled SIMT kernels, the tcgen05 kernels, ccvm_dump_noise)
+// goes through this one function, so a dumped noise tensor is exactly what a production solve draws.
+__device__ __forceinline__ void noise_normals4(uint32_t k0, uint32_t k1, uint32_t off_lo, unsigned long long gb,
+                                               uint32_t t, uint32_t cg, uint32_t qi, float& n0, float& n1, float& n2,
+                                               float& n3) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)gb, t, cg | (qi << 24) | ((uint32_t)(gb >> 32) << 25), off_lo),
+                                make_uint2(k0, k1));
+  box_muller(r.x, r.y, n0, n1);
+  box_muller(r.z, r.w, n2, n3);
+}
+
 // ---- launch parameters of the persistent SDE kernel ------------------------------------
 struct SdeParams {
   const float* q;          // [n][n]
@@ -127,6 +150,105 @@ struct SdeParams {
   int add_assign, beta2_is_one;
   uint32_t seed_lo, seed_hi, off_lo, off_hi;
   uint32_t pin_mask;       // always 0 (a run-time zero the compiler cannot fold; see sde_kernel_tmem.cuh, PIPE)
+};
+
+// ---- per-iteration schedules --------------------------------------------------------------
+// The reference evaluates its per-iteration schedules (pump ramp, noise-ratio decay,
+// measurement-strength decay, Adam bias corrections) as fp64 host scalars
+// (dl_solver.py:523-527,704,715; mf_solver.py:550-559; pumped_langevin_solver.py:278-283).
+// They are evaluated once per launch, in fp64, on the device, and rounded to fp32 per use: by every
+// CTA of a single-instance launch in its prologue (FusedTail::sched_inline, no extra launch), or by
+// build_schedule_batch_kernel for a batched launch.
+struct SchedArgs {
+  int solver, adam, iterations, flag;
+  double pump, dt, noise_ratio, j, fs, g, beta1, beta2;
+};
+
+__device__ __forceinline__ void schedule_row(const SchedArgs& a, int i, float* __restrict__ out) {
+  if (i >= a.iterations) return;
+  const double t = (double)(i + 1), T = (double)a.iterations;
+  const double rate = a.flag ? t / T : 1.0;
+  const double decay = exp(-t / T * 3.0);
+  float r[SCHED_W] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.solver == SOLVER_DL) {
+    const double ratio = (a.noise_ratio - 1.0) * decay + 1.0;
+    const double p = a.pump * rate;  // == pump*(i+1)/T when the flag is set, else pump
+    r[SC_A] = (float)(a.adam ? a.dt : a.dt * a.fs * (0.5 + rate));
+    r[SC_P1] = (float)(a.dt * (-1.0 + p));
+    r[SC_P2] = (float)(a.dt * (-1.0 - p));
+    r[SC_N1] = (float)(2.0 * a.g * sqrt(a.dt) * ratio);
+    r[SC_N2] = (float)(2.0 * a.g * sqrt(a.dt) / ratio);
+  } else if (a.solver == SOLVER_MF) {
+    const double ji = a.j * decay;
+    r[SC_A] = (float)(sqrt(1.0 / (4.0 * ji)) / sqrt(a.dt));
+    r[SC_P1] = (float)(a.pump * rate);
+    r[SC_P2] = (float)ji;
+    r[SC_N1] = (float)(sqrt(ji) / sqrt(a.dt));
+    r[SC_N2] = (float)(1.0 + ji);
+  } else if (a.solver == SOLVER_PLV) {
+    r[SC_P1] = (float)(a.dt * (a.pump * rate - 1.0));
+  }
+  if (a.adam) {
+    r[SC_IB1] = (float)(1.0 / (1.0 - pow(a.beta1, t)));
+    r[SC_IB2] = a.beta2 == 1.0 ? 0.f : (float)(1.0 / (1.0 - pow(a.beta2, t)));
+  }
+  float4* o = reinterpret_cast<float4*>(out + (size_t)i * SCHED_W);
+  o[0] = make_float4(r[0], r[1], r[2], r[3]);
+  o[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+
+// ---- tail of Solver.__call__ (epilogue.cuh) ---------------------------------------------------
+struct EpiParams {
+  const float* q;
+  const float* v;
+  const float* state;
+  const float* m1vec;
+  const float* m2vec;
+  float* pv;
+  float* energy;
+  int n, batch, ld, q_in_smem;
+  int map1, map2, pp, pp_iters;
+  float m1s, m1o, m2s, m2o, step, lo, hi, scaled_by;
+  int wpt, cpl;  // tiled body: warps per tile of 8 trajectories, columns per lane (1, 2 or 4)
+};
+
+// result block of ccvm_solution_stats (36 bytes) ...
+struct StatsOut {
+  float best;
+  int arg_best;
+  int counts[7];
+};
+// ... and of a fused launch (ccvm_solve_fused): the same block followed by the device-measured
+// duration of the two phases (max over CTAs, nanoseconds of %globaltimer)
+struct FusedOut {
+  StatsOut stats;
+  uint32_t ctas;
+  unsigned long long loop_ns, tail_ns;
+};
+// cross-CTA accumulators of a fused launch (zeroed by the host before the launch)
+struct StatsAccum {
+  unsigned long long key;   // (orderable(-E) << 32) | (0xffffffff - trajectory): atomicMax = best, ties to the lowest index
+  int counts[7];
+  int saw_nan;
+  unsigned int done;        // CTAs that have merged; the last one writes FusedOut
+  unsigned int pad;
+  unsigned long long loop_ns, tail_ns;
+};
+
+// What a persistent SDE kernel does besides the loop, so that one Solver.__call__ is ONE launch:
+// the schedule table in its prologue and -- on the CTA's own trajectories -- the change of
+// variables, the post-processor, the BoxQP energy and the solution statistics after the loop.
+struct FusedTail {
+  int sched_inline;        // 1: evaluate the schedule table into sched_scratch[cta][T][SCHED_W] in the prologue
+  int epilogue;            // 1: run `epi` on trajectories [cta range) after the loop
+  int stats;               // 1: merge best / argmin / success counters into `accum`, last CTA writes `out`
+  unsigned int total_ctas;
+  float optimal;
+  SchedArgs sa;
+  float* sched_scratch;
+  EpiParams epi;
+  StatsAccum* accum;
+  FusedOut* out;
 };
 
 }  // namespace ccvm

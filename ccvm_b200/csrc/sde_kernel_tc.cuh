@@ -33,7 +33,6 @@
 #include <cuda.h>
 
 #include "ccvm_common.cuh"
-#include "sde_kernel.cuh"
 #include "sde_kernel_tmem.cuh"
 
 namespace ccvm {
@@ -48,17 +47,6 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 8 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;   // 16 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;  // 48 KB
 constexpr int TC_MAX_CHUNKS = 8;  // n <= 2048
-
-struct TcParams {
-  float* xh;        // [2][rows_p][np]  hi part of the contraction input (ping-pong)
-  float* xl;        // [2][rows_p][np]  lo part
-  float* aux;       // [n_aux][rows_p][np] FP32 in-place state: MF mu, sigma; Adam m, v
-  const float* hvec;    // [np] affine drift term h_j (0 in the padding)
-  const float* svec;    // [np] clamp bound S_j (0 in the padding)
-  int np;           // n rounded up to a multiple of TC_BN
-  int rows;         // valid rows = K * batch
-  int rows_p;       // rows rounded up to a multiple of TC_BM
-};
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -126,7 +114,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
 // ---------------------------------------------------------------- one-off preparation
 // Qs^T split:  qt_hi[j][k] + qt_lo[j][k] = Qs[k][j] = -alpha_k alpha_j Q[k][j]  (zero padded), and the
 // per-column vectors h_j = -alpha_j ((u+l)/2 colsum_j(Q) + V_j), S_j.
-__global__ void tc_prepare_q_kernel(const float* __restrict__ q, const float* __restrict__ v,
+static __global__ void tc_prepare_q_kernel(const float* __restrict__ q, const float* __restrict__ v,
                                     const float* __restrict__ drift_s_vec, float drift_s,
                                     const float* __restrict__ clamp_s_vec, float clamp_s, float a_half, float b_half,
                                     int n, int np, float* __restrict__ qt_hi, float* __restrict__ qt_lo,
@@ -163,11 +151,7 @@ __global__ void tc_prepare_q_kernel(const float* __restrict__ q, const float* __
 // the SIMT kernels draw (sde_kernel_tmem.cuh `draw`), so both paths see identical noise.
 __device__ __forceinline__ void tc_philox4(const SdeParams& p, unsigned long long gb, int t, int cg, uint32_t qi,
                                            float (&n)[4]) {
-  const uint4 r = philox4x32_10(
-      make_uint4((uint32_t)gb, (uint32_t)t, (uint32_t)cg | (qi << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
-      make_uint2(p.seed_lo, p.seed_hi ^ p.off_hi));
-  box_muller(r.x, r.y, n[0], n[1]);
-  box_muller(r.z, r.w, n[2], n[3]);
+  noise_normals4(p.seed_lo, p.seed_hi ^ p.off_hi, p.off_lo, gb, (uint32_t)t, (uint32_t)cg, qi, n[0], n[1], n[2], n[3]);
 }
 
 // noise of 4 consecutive columns j0..j0+3 of one row at iteration t (0 beyond column n)

@@ -1,5 +1,5 @@
 // Persistent Euler-Maruyama kernel, TMEM variant (n <= 128): the production path at the
-// benchmark sizes.  Same contract as sde_kernel.cuh; what changes is where the operands live.
+// benchmark sizes: one launch runs ALL iterations of one Solver._solve / Solver._solve_adam call.
 //
 // Why (ncu, profiles/r1_ncu_sde_dl_adam_v1.txt): with the scaled matrix Qs in shared memory the
 // loop was bound by shared-memory wavefronts (every LDS.128 costs 4 wavefronts no matter how much
@@ -32,32 +32,11 @@
 #include <type_traits>
 
 #include "ccvm_common.cuh"
-#include "sde_kernel.cuh"
+#include "epilogue.cuh"
+#include "sde_launch.h"
 
 namespace ccvm {
 
-struct TmemLaunch {
-  int rg;      // trajectory pairs per group
-  int ng;      // groups per CTA
-  int gt;      // threads per group (TMEM source: 128 when ng > 1)
-  int xs;      // floats per k-row of a group's X panel
-  int tcols;   // TMEM columns to allocate (power of two >= 4*NP, >= 32); unused for QSRC_GMEM
-  int phase_ns;  // start delay of odd groups (experiment knob; 0 in production)
-  int xmask;        // 31: per-column-group bank offsets inside an X row (needs 32 floats of slack); 0: none
-  int pipe;         // 1: in-loop noise generation (PIPE kernels); decided once by the host plan
-  const float* qs;  // QSRC_GMEM: the scaled matrix Qs[NP][NP] (zero padded) in global memory
-};
-
-// Where the thread's Q slice comes from.
-//   QSRC_TMEM (n <= 128): the thread's own TMEM lane (tcgen05.ld), see the header comment.
-//   QSRC_GMEM (any n):    streamed from global memory / L2 with read-only 128-bit loads; the matrix
-//                         is too large for on-chip replication, so it stays L2-resident (4 MB at
-//                         n = 1024) and every CTA re-reads it once per iteration.
-//   QSRC_HYB (128 < n <= 256): rows k < 128 of the slice in the thread's TMEM lane (all 512 columns),
-//                         rows k >= 128 in shared memory, zero padded to HYB_LD columns per row so
-//                         that every address of the tail is base + immediate (4 LDS.128 per chunk;
-//                         lanes of one column group broadcast, neighbouring groups are contiguous).
-enum : int { QSRC_TMEM = 0, QSRC_GMEM = 1, QSRC_HYB = 2 };
 constexpr int HYB_TMEM_CHUNKS = 32;  // chunks of 4 rows held in TMEM (128 rows x 4 columns = 512 TMEM columns)
 constexpr int HYB_LD = 256;          // floats per row of the shared-memory tail
 
@@ -105,6 +84,11 @@ __device__ __forceinline__ void group_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// schedule table of one launch, evaluated by the calling CTA (fp64; see SchedArgs)
+static __device__ __noinline__ void build_schedule_cta(const SchedArgs& a, float* out) {
+  for (int i = threadIdx.x; i < a.iterations; i += blockDim.x) schedule_row(a, i, out);
+}
+
 // Adam transform on a 4-variable tile of trajectory pairs (dl_solver.py:699-727 and siblings).
 // The moments are kept pre-divided by (1 - beta):  ms = m / (1 - beta1),  vs = v / (1 - beta2), so
 //   m_hat = ms (1 - beta1) ib1,   sqrt(v_hat) = sqrt(vs) sqrt((1 - beta2) ib2)
@@ -148,8 +132,8 @@ __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4]
 // those slots, and the latency-bound phase between contraction and barrier shrinks to the SDE
 // update itself (profiles/r1_ncu_sde_dl_tmem_v3.txt: FMA pipe 73 % busy, 27 % bubbles, before).
 template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
-__device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaunch& L, const int cta, float* smem,
-                                              uint32_t* tmem_slot_p) {
+__device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaunch& L, const FusedTail& f, const int cta,
+                                              float* smem, uint32_t* tmem_slot_p) {
   constexpr int K = SolverTraits<SOLVER>::K;
   constexpr int KT = K;      // quadratures handled by one thread
   constexpr bool SPLIT = false;
@@ -198,7 +182,16 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   float4* vsm = reinterpret_cast<float4*>(av + NP + (size_t)L.ng * 2 * PR * XS) + (tid & 255);
 
   // ------------------------------------------------------------------ prologue
+  const unsigned long long t_start = f.stats ? global_timer_ns() : 0ull;
   if (HAS_TMEM && warp == 0) tmem_alloc(&tmem_slot, L.tcols);
+  // single-instance launches evaluate the schedule table here (every CTA its own copy: T rows of 32 B,
+  // fp64, ~6 rows per thread) instead of in a kernel of its own; published by the barriers below
+  const float* sched = p.sched;
+  if (f.sched_inline) {
+    float* mine = f.sched_scratch + (size_t)cta * p.iterations * SCHED_W;
+    build_schedule_cta(f.sa, mine);
+    sched = mine;
+  }
   for (int j = tid; j < NP; j += blockDim.x) {
     float a = 0.f;
     if (j < N) a = p.a_half / (p.drift_s_vec ? p.drift_s_vec[j] : p.drift_s);
@@ -290,12 +283,8 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   auto quantum = [&](pf2 (&Wd)[KT][4], int q, int i, int t) {
     const unsigned long long gb = (unsigned long long)(p.traj_base + gb0 + i);
     const uint32_t qi = (uint32_t)(q + half);  // which quadrature's stream
-    const uint4 r = philox4x32_10(
-        make_uint4((uint32_t)gb, (uint32_t)t, (uint32_t)cgc | (qi << 24) | ((uint32_t)(gb >> 32) << 25), p.off_lo),
-        key);
     float n0, n1, n2, n3;
-    box_muller(r.x, r.y, n0, n1);
-    box_muller(r.z, r.w, n2, n3);
+    noise_normals4(key.x, key.y, p.off_lo, gb, (uint32_t)t, (uint32_t)cgc, qi, n0, n1, n2, n3);
     // Padding columns (j >= n) draw noise like any other: their state stays finite (zero drift, the
     // solver's own saturating terms / a zero clamp), it only ever meets the zero rows of Qs and is
     // never written out -- masking it cost a SEL per normal.
@@ -352,8 +341,9 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   };
 
   const int bar_id = 1 + grp, bar_n = L.gt;
-  const float4* sched4 = reinterpret_cast<const float4*>(p.sched);
-  float4 sa = __ldg(sched4), sb = __ldg(sched4 + 1);
+  // plain loads: the table may have been written by this CTA (sched_inline)
+  const float4* sched4 = reinterpret_cast<const float4*>(sched);
+  float4 sa = sched4[0], sb = sched4[1];
 
   if constexpr (SOLVER == SOLVER_MF) {
     draw(0);  // measurement of iteration 0 (mf_solver.py:551-554): mu = 0
@@ -371,8 +361,8 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     const int buf = t & 1;
     const float4 ca = sa, cb = sb;
     if (t + 1 < T) {
-      sa = __ldg(sched4 + 2 * (t + 1));
-      sb = __ldg(sched4 + 2 * (t + 1) + 1);
+      sa = sched4[2 * (t + 1)];
+      sb = sched4[2 * (t + 1) + 1];
     }
 
     // ---- drift contraction: acc = h + X . Qs   (Qs from TMEM, X from shared memory)
@@ -707,7 +697,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       }
     }
 
-    // ---- elementwise SDE step (same arithmetic as sde_kernel.cuh)
+    // ---- elementwise SDE step
     if constexpr (SOLVER == SOLVER_DL) {
       if constexpr (!PIPE) draw(t);
       if constexpr (ADAM) {
@@ -848,6 +838,25 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     }
   }
   }  // !idle
+  // ------------------------------------------------------------------ fused tail of Solver.__call__
+  // change of variables -> post-processor -> energy on the CTA's own trajectories (the stand-alone
+  // epilogue's code, so the values are identical), then best / argmin / success counters merged across
+  // CTAs with a handful of atomics: the whole call is this one launch (dl_solver.py:936-959,
+  // grad_descent.py:58-64, adam.py:58-66, solution.py:125-136).
+  if (f.epilogue) {
+    __syncthreads();  // every group has written its outputs
+    const unsigned long long t_loop = f.stats ? global_timer_ns() : 0ull;
+    const long long per_cta = (long long)L.ng * 2 * L.rg;
+    const long long b_begin = (long long)cta * per_cta;
+    const long long b_end = b_begin + per_cta < p.batch ? b_begin + per_cta : p.batch;
+    epilogue_run(f.epi, smem, b_begin, b_end, 0, 1);
+    if (f.stats) {
+      __syncthreads();  // the CTA's energies are in global memory
+      StatsPartial sp;
+      if (stats_block_reduce(f.epi.energy, b_begin, b_end, f.optimal, sp))
+        stats_merge(sp, f.accum, f.out, f.total_ctas, t_loop - t_start, global_timer_ns() - t_loop);
+    }
+  }
   if constexpr (HAS_TMEM) {
     tc_fence_before();
     __syncthreads();
@@ -857,10 +866,10 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
 
 template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
 __global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
-    sde_tmem_kernel(const SdeParams p, const TmemLaunch L) {
+    sde_tmem_kernel(const SdeParams p, const TmemLaunch L, const FusedTail f) {
   extern __shared__ __align__(16) float smem[];
   __shared__ uint32_t tmem_slot;
-  sde_tile_body<SOLVER, ADAM, QSRC, PIPE, CGC>(p, L, blockIdx.x, smem, &tmem_slot);
+  sde_tile_body<SOLVER, ADAM, QSRC, PIPE, CGC>(p, L, f, blockIdx.x, smem, &tmem_slot);
 }
 
 // PIPE needs Philox noise and more than 4*K chunks of four Q rows (DL: n >= 33, others: n >= 17).
@@ -869,15 +878,10 @@ __host__ __device__ __forceinline__ bool pipe_ok(int cg, bool philox) {
   return philox && cg > 4 * SolverTraits<SOLVER>::K;
 }
 
-// One launch over MANY problem instances (grid = sum of the instances' CTAs): the reference's user
-// loop over instance files (examples/ccvm_boxqp_*.py) folded into the grid.  Each CTA looks up
-// (instance, CTA index inside the instance) and runs the same body with that instance's parameters.
-struct BatchItem {
-  SdeParams p;
-  TmemLaunch L;
-};
-
-template <int SOLVER, bool ADAM, int QSRC>
+// One launch over MANY problem instances (BatchItem, sde_launch.h): each CTA looks up (instance, CTA
+// index inside the instance) and runs the same body with that instance's parameters.  CGC != 0: every
+// instance of the bucket has that column-group count (compile-time variants of the PIPE kernels).
+template <int SOLVER, bool ADAM, int QSRC, int CGC = 0>
 __global__ void __launch_bounds__(256, 1)
     sde_tmem_batch_kernel(const BatchItem* __restrict__ items, const int2* __restrict__ cta_map) {
   extern __shared__ __align__(16) float smem[];
@@ -892,10 +896,14 @@ __global__ void __launch_bounds__(256, 1)
   __syncthreads();
   const SdeParams p = s_item.p;
   const TmemLaunch L = s_item.L;
-  if (L.pipe)
-    sde_tile_body<SOLVER, ADAM, QSRC, true>(p, L, m.y, smem, &tmem_slot);
-  else
-    sde_tile_body<SOLVER, ADAM, QSRC, false>(p, L, m.y, smem, &tmem_slot);
+  if constexpr (CGC != 0) {
+    sde_tile_body<SOLVER, ADAM, QSRC, true, CGC>(p, L, s_item.f, m.y, smem, &tmem_slot);
+  } else {
+    if (L.pipe)
+      sde_tile_body<SOLVER, ADAM, QSRC, true>(p, L, s_item.f, m.y, smem, &tmem_slot);
+    else
+      sde_tile_body<SOLVER, ADAM, QSRC, false>(p, L, s_item.f, m.y, smem, &tmem_slot);
+  }
 }
 
 }  // namespace ccvm

@@ -28,6 +28,31 @@ def next_philox_stream(device, increment):
     return seed & 0xFFFFFFFFFFFFFFFF, offset
 
 
+class _NvtxRange:
+    """NVTX range around one solver call (tracing hooks); a no-op when torch was built
+    without NVTX."""
+
+    def __init__(self, name):
+        self.name, self.on = name, False
+
+    def __enter__(self):
+        try:
+            torch.cuda.nvtx.range_push(self.name)
+            self.on = True
+        except Exception:
+            self.on = False
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
+def nvtx_range(name):
+    return _NvtxRange(name)
+
+
 class PlannedSolve:
     """A filled ``ccvm_solve_desc`` together with the tensors its pointers refer to."""
 
@@ -103,6 +128,21 @@ def solve(solver, algorithm, q, v, batch, iterations, **kwargs):
     return plan.outputs, plan.samples
 
 
+def dump_noise(solver, n, batch, iterations, seed, offset, traj_base=0, device=None):
+    """The standard normals a Philox-mode solve with these (seed, offset, traj_base) draws, as a replay
+    tensor [iterations][K][n][batch] (``ccvm_dump_noise``): validation only."""
+    nat.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    d = nat.SolveDesc()
+    d.solver, d.n, d.batch, d.iterations = solver, int(n), int(batch), int(iterations)
+    d.seed, d.offset, d.traj_base = int(seed), int(offset), int(traj_base)
+    k = 2 if solver == nat.SOLVER_DL else 1
+    out = torch.empty((iterations, k, n, batch), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(nat.load().ccvm_dump_noise(C.byref(d), nat.ptr(out), nat.current_stream_ptr(dev)))
+    return out
+
+
 def solve_batch(plans):
     """Launch many planned solves (same solver and algorithm, Philox noise) as ONE grid over
     instances x trajectory blocks (``ccvm_solve_batch``).  Outputs are those of the plans."""
@@ -130,6 +170,84 @@ def _vec_or_scalar(val, n, dev):
             raise ValueError("Tensor S size should be equal to problem size.")
         return 0.0, nat.as_f32(val, dev)
     return float(val), None
+
+
+class PlannedEpilogue:
+    """A filled ``ccvm_epilogue_desc`` with its output tensors (pv, energy)."""
+
+    __slots__ = ("desc", "pv", "energy", "_keep")
+
+    def __init__(self, desc, pv, energy, keep):
+        self.desc, self.pv, self.energy, self._keep = desc, pv, energy, keep
+
+
+def plan_epilogue(b, n, dev, *, map1=None, post_processor=None, pp_iterations=10, pp_step=None, pp_lower=0.0,
+                  pp_upper=1.0, map2=None, scaled_by=1.0, want_pv=True, energy_out=None):
+    """Descriptor of the tail of ``Solver.__call__`` for a fused launch (``solve_fused`` /
+    ``solve_batch_fused``): q, v and the state come from the solve it is attached to."""
+    d = nat.EpilogueDesc()
+    d.n, d.batch = n, b
+    keep = []
+    if map1 is not None:
+        sc, vec = _vec_or_scalar(map1[0], n, dev)
+        keep.append(vec)
+        d.apply_map1, d.map1_scale, d.map1_shift, d.map1_scale_vec = 1, sc, float(map1[1]), nat.ptr(vec)
+    if map2 is not None:
+        sc, vec = _vec_or_scalar(map2[0], n, dev)
+        keep.append(vec)
+        d.apply_map2, d.map2_scale, d.map2_shift, d.map2_scale_vec = 1, sc, float(map2[1]), nat.ptr(vec)
+    if post_processor not in nat.PP_IDS:
+        raise AssertionError(f"Method type is not valid. Provided: {post_processor}")
+    d.post_processor = nat.PP_IDS[post_processor]
+    d.pp_iterations = int(pp_iterations)
+    if pp_step is None:
+        pp_step = 0.1 if post_processor == "grad-descent" else 0.01
+    d.pp_step, d.pp_lower, d.pp_upper = float(pp_step), float(pp_lower), float(pp_upper)
+    d.scaled_by = float(scaled_by)
+    pv = torch.empty((b, n), dtype=torch.float32, device=dev) if want_pv else None
+    en = energy_out if energy_out is not None else torch.empty((b,), dtype=torch.float32, device=dev)
+    if en.numel() != b or en.dtype != torch.float32 or not en.is_contiguous() or en.device != dev:
+        raise ValueError("energy_out must be a contiguous fp32 tensor of batch elements on the state's device")
+    d.problem_variables, d.energy = nat.ptr(pv), nat.ptr(en)
+    return PlannedEpilogue(d, pv, en, keep)
+
+
+def decode_fused_results(raw):
+    """Host view of ``count`` 56-byte result blocks (a CPU uint8 tensor): list of dicts with best,
+    arg_best, counts, ctas, loop_ns, tail_ns."""
+    raw = raw.contiguous().view(-1, nat.FUSED_RESULT_BYTES)
+    best = raw[:, 0:4].contiguous().view(torch.float32).reshape(-1).tolist()
+    ints = raw[:, 4:40].contiguous().view(torch.int32).reshape(-1, 9).tolist()
+    ns = raw[:, 40:56].contiguous().view(torch.int64).reshape(-1, 2).tolist()
+    return [dict(best=best[i], arg_best=ints[i][0], counts=ints[i][1:8], ctas=ints[i][8], loop_ns=ns[i][0],
+                 tail_ns=ns[i][1]) for i in range(raw.shape[0])]
+
+
+def solve_fused(plan, epi, optimal_value=0.0, want_stats=True):
+    """ONE launch for a whole ``Solver.__call__``: schedules, loop, change of variables, post-processor,
+    energy, statistics (``ccvm_solve_fused``).  Returns the device result block (uint8[56]) or None."""
+    lib = nat.load()
+    dev = plan.device
+    res = torch.empty(nat.FUSED_RESULT_BYTES, dtype=torch.uint8, device=dev) if want_stats else None
+    with torch.cuda.device(dev):
+        nat.check(lib.ccvm_solve_fused(C.byref(plan.desc), C.byref(epi.desc), float(optimal_value), nat.ptr(res),
+                                       nat.current_stream_ptr(dev)))
+    return res
+
+
+def solve_batch_fused(plans, epis, optimal_values):
+    """Many planned solves AND their tails in one launch per bucket (``ccvm_solve_batch_fused``).
+    Returns the device result blocks, uint8[count][56]."""
+    lib = nat.load()
+    dev = plans[0].device
+    count = len(plans)
+    arr = (nat.SolveDesc * count)(*[p.desc for p in plans])
+    earr = (nat.EpilogueDesc * count)(*[e.desc for e in epis])
+    opt = (C.c_double * count)(*[float(o) for o in optimal_values])
+    res = torch.empty((count, nat.FUSED_RESULT_BYTES), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        nat.check(lib.ccvm_solve_batch_fused(arr, earr, opt, count, nat.ptr(res), nat.current_stream_ptr(dev)))
+    return res
 
 
 def epilogue(state, q, v, *, map1=None, post_processor=None, pp_iterations=10, pp_step=None,

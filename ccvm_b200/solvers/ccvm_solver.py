@@ -42,13 +42,13 @@ _HOOKS = ("calculate_drift", "calculate_grads", "change_variables", "fit_to_cons
 
 
 class _PendingSolution:
-    """An instance whose solve was planned but not yet launched (``CCVMSolver.solve_many``)."""
+    """An instance whose solve and tail were planned but not yet launched (``CCVMSolver.solve_many``)."""
 
-    __slots__ = ("instance", "batch_size", "iterations", "run_epilogue", "make_solution")
+    __slots__ = ("instance", "batch_size", "iterations", "plan", "epilogue", "make_solution")
 
-    def __init__(self, instance, batch_size, iterations, run_epilogue, make_solution):
+    def __init__(self, instance, batch_size, iterations, plan, epilogue, make_solution):
         self.instance, self.batch_size, self.iterations = instance, batch_size, iterations
-        self.run_epilogue, self.make_solution = run_epilogue, make_solution
+        self.plan, self.epilogue, self.make_solution = plan, epilogue, make_solution
 
 
 class CCVMSolver(ABC):
@@ -217,8 +217,10 @@ class CCVMSolver(ABC):
 
     def _engine_solve(self, solver_id, algorithm, batch_size, iterations, S, evolution_step_size,
                       hyperparameters=None, **scalars):
-        """Common body of every ``_solve`` / ``_solve_adam``: one engine call, evolution samples
-        stored on ``self`` the way the reference does."""
+        """Common body of every ``_solve`` / ``_solve_adam``.  Called directly (the reference's
+        function-level API) it launches the loop kernel and returns the state tensors.  Inside
+        ``__call__`` / ``solve_many`` it only PLANS the launch (descriptor + output tensors) so that
+        the loop and the tail of the call can go to the GPU as one fused launch."""
         if self.device != "cuda":
             raise engine.nat.NativeError(
                 "ccvm_b200 solves on CUDA only (device='cuda'); there is no CPU implementation.")
@@ -230,13 +232,10 @@ class CCVMSolver(ABC):
                       noise=self.noise_source, evolution_step=evolution_step_size or None,
                       num_samples=num_samples or 0, **scalars)
         if self._deferred is not None:
-            # solve_many: plan only; the whole batch of instances is launched as one grid later
-            if self.noise_source is not None or evolution_step_size:
-                raise ValueError("solve_many supports neither noise replay nor evolution sampling.")
             plan = engine.plan_solve(solver_id, algorithm, self.q_matrix, self.v_vector, batch_size, iterations,
                                      **kwargs)
             self._deferred.append(plan)
-            self._samples = None
+            self._samples = plan.samples
             return plan.outputs
         outs, samples = engine.solve(solver_id, algorithm, self.q_matrix, self.v_vector, batch_size, iterations,
                                      **kwargs)
@@ -247,32 +246,40 @@ class CCVMSolver(ABC):
              algorithm_parameters, iterations, S, solve_args, finish):
         """Shared ``__call__`` body.  ``solve_args(adam)`` yields the positional arguments of
         ``_solve`` / ``_solve_adam``; ``finish(outs)`` maps raw loop outputs to
-        (state, map1, map2, variables-dict-builder)."""
+        (state, map1, map2, variables-dict-builder).
+
+        The whole call is ONE kernel launch (``ccvm_solve_fused``): schedules, iteration loop, change of
+        variables, post-processor, energy and solution statistics, followed by one 56-byte read-back.
+        ``solve_time`` / ``pp_time`` split the measured wall time of that launch (with a stream
+        synchronise on both sides -- the reference stops its clock without one) in the
+        ratio of the device-measured durations of the loop and of the tail; ``pp_time`` therefore
+        covers change of variables + post-processor + energy + statistics, and is 0 without a
+        post-processor, as in the reference."""
         batch_size = self.batch_size
         num_samples, evolution_file = self._evolution_plan(instance, iterations, evolution_step_size,
                                                            evolution_file)
         self._samples = None
-        deferred = self._deferred is not None
-        if self.device == "cuda" and not deferred:
-            torch.cuda.current_stream().synchronize()  # stream-level: other streams may be solving too
-        solve_time_start = time.time()
-        if algorithm_parameters is None:
-            outs = self._solve(*solve_args(False))
-        elif isinstance(algorithm_parameters, AdamParameters):
-            outs = self._solve_adam(*solve_args(True), algorithm_parameters.to_dict())
-        else:
-            raise ValueError(f"Solver option type {type(algorithm_parameters)} is not supported.")
-        if self.device == "cuda" and not deferred:
-            torch.cuda.current_stream().synchronize()  # the reference stops its clock without one (SURVEY.md 5)
-        solve_time = (time.time() - solve_time_start) / batch_size
+        in_batch = self._deferred is not None          # solve_many is collecting plans
+        if in_batch and (self.noise_source is not None or evolution_step_size):
+            raise ValueError("solve_many supports neither noise replay nor evolution sampling.")
+        if not in_batch:
+            self._deferred = []
+        try:
+            if algorithm_parameters is None:
+                outs = self._solve(*solve_args(False))
+            elif isinstance(algorithm_parameters, AdamParameters):
+                outs = self._solve_adam(*solve_args(True), algorithm_parameters.to_dict())
+            else:
+                raise ValueError(f"Solver option type {type(algorithm_parameters)} is not supported.")
+            plan = self._deferred[-1]
+        finally:
+            if not in_batch:
+                self._deferred = None
 
         state, map1, map2, make_variables = finish(outs)
-        q_matrix, v_vector = self.q_matrix, self.v_vector
-        scaled_by = _as_float(instance.scaled_by)
-
-        def run_epilogue(energy_out=None):
-            return engine.epilogue(state, q_matrix, v_vector, map1=map1, post_processor=post_processor,
-                                   pp_iterations=10, map2=map2, scaled_by=scaled_by, energy_out=energy_out)
+        epi = engine.plan_epilogue(batch_size, instance.problem_size, plan.device, map1=map1,
+                                   post_processor=post_processor, pp_iterations=10, map2=map2,
+                                   scaled_by=_as_float(instance.scaled_by))
 
         def make_solution(pv, objval, solve_time, pp_time, stats=None):
             return Solution(
@@ -292,29 +299,37 @@ class CCVMSolver(ABC):
                 precomputed_stats=stats,
             )
 
-        if deferred:
-            return _PendingSolution(instance, batch_size, iterations, run_epilogue, make_solution)
+        if in_batch:
+            return _PendingSolution(instance, batch_size, iterations, plan, epi, make_solution)
 
-        pp_start = time.time()
-        pv, objval = run_epilogue()
-        pp_time = 0.0
-        if post_processor:
-            torch.cuda.current_stream().synchronize()
-            pp_time = (time.time() - pp_start) / batch_size
+        stream = torch.cuda.current_stream(plan.device)
+        stream.synchronize()  # stream-level: other streams may be solving too
+        start = time.time()
+        with engine.nvtx_range(f"ccvm_b200.{type(self).__name__}.__call__ n={instance.problem_size} B={batch_size}"):
+            raw = engine.solve_fused(plan, epi, _as_float(instance.optimal_sol))
+            res = engine.decode_fused_results(raw.cpu())[0]   # the copy synchronises the stream
+        wall = time.time() - start
+        device_ns = res["loop_ns"] + res["tail_ns"]
+        loop_share = res["loop_ns"] / device_ns if device_ns else 1.0
+        solve_time = wall * loop_share / batch_size
+        pp_time = wall * (1.0 - loop_share) / batch_size if post_processor else 0.0
 
         if evolution_step_size:
-            self._write_evolution(evolution_file, objval)
+            self._publish_samples(self._sample_names)   # the snapshots exist now that the launch has run
+            self._write_evolution(evolution_file, epi.energy)
 
-        solution = make_solution(pv, objval, solve_time, pp_time)
+        solution = make_solution(epi.pv, epi.energy, solve_time, pp_time,
+                                 (res["best"], res["arg_best"], res["counts"]))
         if evolution_step_size:
             solution.evolution_file = evolution_file
         return solution
 
     # ------------------------------------------------------------- many instances
     def solve_many(self, instances, post_processor=None, algorithm_parameters=None, **call_kwargs):
-        """Solve a sequence of instances with ONE solver-loop launch (grid over instances x
-        trajectory blocks, ``ccvm_solve_batch``), per-instance fused epilogues enqueued without any
-        host synchronisation, and one batched statistics kernel with a single device->host copy.
+        """Solve a sequence of instances with ONE launch per kernel bucket (grid over instances x
+        trajectory blocks, ``ccvm_solve_batch_fused``): every CTA also finishes its own trajectories
+        (change of variables, post-processor, energy) and merges the statistics of its instance, so a
+        chunk ends with a single device->host copy of 56 bytes per instance.
 
         Returns the list of ``Solution`` objects ``[self(instance=i, ...) for i in instances]``
         would return under the same generator state (the reference's user loop over instance
@@ -338,27 +353,35 @@ class CCVMSolver(ABC):
         finally:
             self._deferred = None
         dev = plans[0].device
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        ev[0].record()
-        engine.solve_batch(plans)
-        ev[1].record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         offsets = [0]
         for p in pending:
             offsets.append(offsets[-1] + p.batch_size)
+        # one energy vector for the chunk: the per-instance epilogues write their slices of it
         energy = torch.empty(offsets[-1], dtype=torch.float32, device=dev)
-        pvs = [p.run_epilogue(energy[offsets[i]:offsets[i + 1]])[0] for i, p in enumerate(pending)]
-        ev[2].record()
-        stats = engine.solution_stats_batch(energy, offsets, [p.instance.optimal_sol for p in pending])
-        # solution_stats_batch ended with a device->host copy: the events have completed
-        t_solve, t_pp = ev[0].elapsed_time(ev[1]) * 1e-3, ev[1].elapsed_time(ev[2]) * 1e-3
+        for i, p in enumerate(pending):
+            sl = energy[offsets[i]:offsets[i + 1]]
+            p.epilogue.energy, p.epilogue.desc.energy = sl, sl.data_ptr()
+        stream = torch.cuda.current_stream(dev)
+        ev[0].record(stream)
+        with engine.nvtx_range(f"ccvm_b200.{type(self).__name__}.solve_many x{len(pending)}"):
+            raw = engine.solve_batch_fused(plans, [p.epilogue for p in pending],
+                                           [_as_float(p.instance.optimal_sol) for p in pending])
+        ev[1].record(stream)
+        stats = engine.decode_fused_results(raw.cpu())   # ONE device->host copy for the whole chunk
+        ev[1].synchronize()
+        t_total = ev[0].elapsed_time(ev[1]) * 1e-3
         work = [p.batch_size * p.iterations * p.instance.problem_size ** 2 for p in pending]
         total = float(sum(work)) or 1.0
         out = []
         for i, p in enumerate(pending):
-            share = work[i] / total
-            out.append(p.make_solution(pvs[i], energy[offsets[i]:offsets[i + 1]],
-                                       t_solve * share / p.batch_size,
-                                       (t_pp * share / p.batch_size) if post_processor else 0.0, stats[i]))
+            r = stats[i]
+            device_ns = r["loop_ns"] + r["tail_ns"]
+            loop_share = r["loop_ns"] / device_ns if device_ns else 1.0
+            t_inst = t_total * work[i] / total
+            out.append(p.make_solution(p.epilogue.pv, p.epilogue.energy, t_inst * loop_share / p.batch_size,
+                                       (t_inst * (1.0 - loop_share) / p.batch_size) if post_processor else 0.0,
+                                       (r["best"], r["arg_best"], r["counts"])))
         return out
 
     # ----------------------------------------------------------- evolution sampling
@@ -367,6 +390,7 @@ class CCVMSolver(ABC):
     def _publish_samples(self, names):
         """Expose the engine's [K][samples][B][N] snapshot buffer as the reference's per-array
         CPU tensors of shape (B, N, samples) (dl_solver.py:877-886)."""
+        self._sample_names = names
         for k, name in enumerate(names):
             val = None
             if self._samples is not None:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CCVM_ABI_VERSION 1
+#define CCVM_ABI_VERSION 2
 
 /* error codes */
 #define CCVM_OK 0
@@ -44,7 +44,8 @@ extern "C" {
 #define CCVM_ALG_ADAM 1     /* Solver._solve_adam */
 
 /* noise source */
-#define CCVM_RNG_PHILOX 0 /* in-kernel Philox4x32-10 + Box-Muller, keyed by (seed, offset, trajectory, step, variable) */
+#define CCVM_RNG_PHILOX 0 /* in-kernel Philox4x32-10 + Box-Muller, keyed by (seed, offset, trajectory, step, variable);
+                             ccvm_dump_noise writes exactly the normals this mode draws */
 #define CCVM_RNG_REPLAY 1 /* validation: consume a recorded noise tensor [T][K][N][B]                 */
 
 /* post-processor ids (post_processor/factory.py:12-35; only the two batched ones are on the hot path) */
@@ -112,6 +113,17 @@ typedef struct ccvm_solve_desc {
 int ccvm_solve(const ccvm_solve_desc* desc, void* stream);
 
 /*
+ * Validation aid, no reference counterpart: writes the standard normals that ccvm_solve(desc) draws in
+ * CCVM_RNG_PHILOX mode (same seed / offset / traj_base / n / batch / iterations / solver) into
+ * noise[iterations][K][n][batch] (device, K = 2 for DL else 1) -- the layout CCVM_RNG_REPLAY consumes and
+ * the layout in which the reference's per-iteration draws are recorded (dl_solver.py:512-519:
+ * Normal(0,1).sample((N,)).T, one [n][batch] slab per draw).  Replaying this tensor through the
+ * reference arithmetic reproduces a production run, which pins the production kernel variants
+ * (in-loop noise generation, compile-time column-group counts) to the oracle.
+ */
+int ccvm_dump_noise(const ccvm_solve_desc* desc, float* noise, void* stream);
+
+/*
  * Many instances in ONE launch (grid over instances x trajectory blocks).
  *
  * Replaces: the user-level loop over instance files around Solver.__call__
@@ -161,6 +173,31 @@ typedef struct ccvm_epilogue_desc {
 
 int ccvm_epilogue(const ccvm_epilogue_desc* desc, void* stream);
 
+/*
+ * One whole Solver.__call__ as ONE kernel launch: the per-iteration schedules, the iteration loop,
+ * the change of variables, the post-processor, the BoxQP energy and the solution statistics
+ * (dl_solver.py:771-999 and siblings, including solution.py:65-146).  Every CTA of the persistent kernel
+ * finishes its own trajectories (same device code as ccvm_epilogue, so the values are identical) and
+ * merges best / argmin / the seven success counters across CTAs with a handful of atomics.
+ *
+ * `solve` is an ordinary ccvm_solve descriptor (its outputs are still written); `epi` supplies the maps,
+ * the post-processor and the output buffers problem_variables (optional) and energy (required when
+ * `result` is given) -- its q, v, state, n and batch are ignored (taken from `solve`: the state is out0,
+ * or out1 = mu_tilde for MF).  `result` (device, 56 bytes, may be NULL) receives
+ *   { float best; int32 arg_best; int32 counts[7]; uint32 ctas; uint64 loop_ns; uint64 tail_ns }
+ * i.e. the block of ccvm_solution_stats followed by the number of CTAs and the device-measured duration
+ * (max over CTAs) of the loop and of the tail.  Paths that cannot fuse (the tcgen05 kernels) run the
+ * stand-alone kernels behind the same call; loop_ns / tail_ns are 0 then.
+ */
+int ccvm_solve_fused(const ccvm_solve_desc* solve, const ccvm_epilogue_desc* epi, double optimal_value,
+                     void* result, void* stream);
+
+/* ccvm_solve_batch with the fused tail of ccvm_solve_fused: `epis[i]` / `optimal_values[i]` (host arrays)
+ * belong to `descs[i]`, `results` is device memory of count x 56 bytes (may be NULL).  A sweep chunk is
+ * one launch per bucket instead of 1 + count epilogues + 1 statistics kernel. */
+int ccvm_solve_batch_fused(const ccvm_solve_desc* descs, const ccvm_epilogue_desc* epis,
+                           const double* optimal_values, int32_t count, void* results, void* stream);
+
 /* Replaces ProblemInstance.compute_energy (problem_instance.py:226-241). */
 int ccvm_compute_energy(const float* x, const float* q, const float* v, double scaled_by,
                         int32_t batch, int32_t n, float* energy, void* stream);
@@ -197,13 +234,16 @@ int ccvm_solution_stats_batch(const float* energy, const int64_t* offsets,
 
 /*
  * Multi-GPU result records (no reference counterpart: the reference is single-device).
- * ccvm_pack_record: from the 9-word block written by ccvm_solution_stats and the local solution
- *   matrix problem_variables[batch][n], writes record[9 + n] (device floats):
- *   [min energy, traj_base + local argmin, 7 success counters, the winner's solution vector].
- * ccvm_merge_records: reduces world_size such records (gathered[world_size][9 + n], e.g. the output
- *   of an all-gather) to merged[9 + n] = [best objective = max(-E), global index of the winner,
- *   summed counters, winner's vector]; ties go to the lowest rank, NaN propagates.
+ * A record is CCVM_RECORD_HEADER + n 32-bit words in a float buffer:
+ *   [0] min energy (f32)   [1],[2] global index of the winner, low / high 32 bits (integers)
+ *   [3..9] the 7 success counters (int32)   [10..] the winner's solution vector (f32 x n).
+ * ccvm_pack_record: from the 9-word block written by ccvm_solution_stats (or the head of a
+ *   ccvm_solve_fused result) and the local solution matrix problem_variables[batch][n].
+ * ccvm_merge_records: reduces world_size such records (gathered[world_size][HEADER + n], e.g. the
+ *   output of an all-gather) to one whose slot [0] is the best objective = max(-E); counters are
+ *   summed, ties go to the lowest rank, NaN propagates.
  */
+#define CCVM_RECORD_HEADER 10
 int ccvm_pack_record(const void* stats, const float* problem_variables, int32_t n, int64_t traj_base,
                      float* record, void* stream);
 int ccvm_merge_records(const float* gathered, int32_t world_size, int32_t n, float* merged,
@@ -275,7 +315,7 @@ int ccvm_generate_boxqp(float* q, float* v, int32_t n, uint64_t seed, double q_o
 
 /*
  * Host-buffer convenience used for end-to-end timing: copies Q and V from HOST memory,
- * runs ccvm_solve + ccvm_epilogue + ccvm_solution_stats on `stream`, copies energy[batch] and the
+ * runs ccvm_solve_fused (one launch) on `stream`, copies energy[batch] and the
  * 9-word stats block back to HOST memory and synchronises the stream.  `solve` and `epi` carry
  * the scalar parameters; their device pointers (q, v, state, outputs) are ignored and replaced
  * by internal buffers.  `h_*` pointers are host memory (pinned recommended).

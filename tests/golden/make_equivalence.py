@@ -38,6 +38,13 @@ KEYS = {
     "dl": dict(pump=8.0, feedback_scale=100, dt=0.001, iterations=ITERS, noise_ratio=10),
 }
 POST = {"mf": "grad-descent", "langevin": "grad-descent", "pumped_langevin": "grad-descent", "dl": None}
+# `_solve_adam` loops (round 2): the same keys and post-processors, run with the AdamParameters of the
+# reference's examples (examples/ccvm_boxqp_dl.py:45-47) on the first ADAM_PER_SIZE instances of a size
+ADAM = dict(alpha=0.001, beta1=0.9, beta2=0.999, add_assign=False)
+ADAM_PER_SIZE = 10
+for _name in ("mf", "langevin", "pumped_langevin", "dl"):
+    KEYS[_name + "_adam"] = KEYS[_name]
+    POST[_name + "_adam"] = POST[_name]
 
 
 def instance_files(n):
@@ -71,11 +78,24 @@ def run(seeds, solvers, threads):
     torch.set_num_threads(threads)
     from ccvm_simulators.problem_classes.boxqp import ProblemInstance
     from ccvm_simulators.solvers import DLSolver, MFSolver, LangevinSolver, PumpedLangevinSolver
-    cls = {"mf": MFSolver, "langevin": LangevinSolver, "pumped_langevin": PumpedLangevinSolver, "dl": DLSolver}
+    from ccvm_simulators.solvers.algorithms import AdamParameters
+
+    class DLSolverAdamCallable(DLSolver):
+        """The reference's DLSolver.__call__ hands feedback_scale to _solve_adam, which does not take it
+        (TypeError); this adapter drops that one positional argument and nothing else."""
+
+        def _solve_adam(self, problem_size, batch_size, device, S, pump, dt, iterations, noise_ratio, feedback_scale,
+                        *rest):
+            return DLSolver._solve_adam(self, problem_size, batch_size, device, S, pump, dt, iterations, noise_ratio,
+                                        *rest)
+
+    cls = {"mf": MFSolver, "langevin": LangevinSolver, "pumped_langevin": PumpedLangevinSolver, "dl": DLSolver,
+           "mf_adam": MFSolver, "langevin_adam": LangevinSolver, "pumped_langevin_adam": PumpedLangevinSolver,
+           "dl_adam": DLSolverAdamCallable}
     path_out = os.path.join(HERE, "equivalence_ref.json")
     res = json.load(open(path_out)) if os.path.exists(path_out) else {}
     res["_meta"] = {"batch": BATCH, "iterations": ITERS, "keys": KEYS, "post_processor": POST,
-                    "torch": torch.__version__, "device": "cpu",
+                    "torch": torch.__version__, "device": "cpu", "adam": ADAM, "adam_per_size": ADAM_PER_SIZE,
                     "what": "unmodified reference Solver.__call__ under torch.manual_seed(seed); "
                             "per instance: [optimal, 1%, 2%, 3%, 4%, 5%, 10%] success fractions + best objective"}
     for name in solvers:
@@ -89,12 +109,15 @@ def run(seeds, solvers, threads):
                 solver.parameter_key = {n: dict(KEYS[name])}
                 rows = []
                 t0 = time.time()
-                for k, path in enumerate(instance_files(n)):
+                adam = name.endswith("_adam")
+                files = instance_files(n)[:ADAM_PER_SIZE] if adam else instance_files(n)
+                for k, path in enumerate(files):
                     inst = ProblemInstance(instance_type="tuning", file_path=path, device="cpu")
                     inst.scale_coefs(solver.get_scaling_factor(inst.q_matrix))
                     torch.manual_seed(seed * 1000 + k)
                     with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
-                        sol = solver(instance=inst, post_processor=POST[name])
+                        sol = solver(instance=inst, post_processor=POST[name],
+                                     algorithm_parameters=AdamParameters(**ADAM) if adam else None)
                     p = sol.solution_performance
                     rows.append([p["optimal"], p["one_percent"], p["two_percent"], p["three_percent"],
                                  p["four_percent"], p["five_percent"], p["ten_percent"],

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in ccvm_b200.h but not exported"
     assert set(nat.EXPORTS) == declared
-    assert lib.ccvm_abi_version() == 1
+    assert lib.ccvm_abi_version() == nat.ABI_VERSION == int(re.search(r"#define CCVM_ABI_VERSION (\d+)", header).group(1))
 
 
 @pytest.mark.parametrize("cls", SOLVERS)

@@ -339,29 +339,35 @@ def test_device_record_pack_and_merge_match_host_logic():
         pv = torch.rand(b, n, device="cuda")
         res = torch.empty(9, dtype=torch.int32, device="cuda")
         nat.check(nat.load().ccvm_solution_stats(en.data_ptr(), b, 95.0, res.data_ptr(), nat.current_stream_ptr()))
-        counts = res[2:9].to(torch.float32)
-        ref = P.pack_local_result(en, pv, counts, 1000 * r)
-        dev = P.pack_from_stats(res, pv, 1000 * r)
-        assert torch.equal(ref, dev)
+        counts = res[2:9]
+        ref = P.pack_local_result(en, pv, counts, 1000 * r + (1 << 33))   # index beyond 2^32: both halves in use
+        dev = P.pack_from_stats(res, pv, 1000 * r + (1 << 33))
+        assert torch.equal(ref.view(torch.int32), dev.view(torch.int32))
         recs_dev.append(dev)
         recs_ref.append(ref.cpu())
+    H = P.HEADER
     gathered = torch.stack(recs_dev).contiguous()
     out = torch.empty_like(recs_dev[0])
     nat.check(nat.load().ccvm_merge_records(gathered.data_ptr(), 4, n, out.data_ptr(), nat.current_stream_ptr()))
     g = torch.stack(recs_ref)
     owner = int(torch.argmin(g[:, 0]))
     assert owner == 2
-    assert out[0].item() == -g[owner, 0].item() and out[1].item() == g[owner, 1].item() == 2017.0
-    assert torch.equal(out[2:9].cpu(), g[:, 2:9].sum(dim=0))
-    assert torch.equal(out[9:].cpu(), g[owner, 9:])
+    best, idx, counts, vec = P.unpack_record(out, slot0_is_objective=True)
+    assert best.item() == -g[owner, 0].item() and idx.item() == 2017 + (1 << 33)
+    assert torch.equal(counts.cpu(), g.view(torch.int32)[:, 3:H].sum(dim=0, dtype=torch.int32))
+    assert torch.equal(vec.cpu(), g[owner, H:])
     # ties go to the lowest rank
     gathered[3, 0] = gathered[2, 0]
     gathered[1, 0] = gathered[2, 0]
     nat.check(nat.load().ccvm_merge_records(gathered.data_ptr(), 4, n, out.data_ptr(), nat.current_stream_ptr()))
-    assert out[1].item() == gathered[1, 1].item()
+    assert P.unpack_record(out, True)[1].item() == P.unpack_record(recs_dev[1])[1].item()
+    # a NaN objective wins on the device and in the host branch alike
+    gathered[3, 0] = float("nan")
+    nat.check(nat.load().ccvm_merge_records(gathered.data_ptr(), 4, n, out.data_ptr(), nat.current_stream_ptr()))
+    assert torch.isnan(out[0])
     # merge_results on a CUDA record without a process group = identity reduction of one record
     best, idx, counts, vec = P.merge_results(recs_dev[0])
-    assert best.item() == -recs_dev[0][0].item() and torch.equal(vec, recs_dev[0][9:])
+    assert best.item() == -recs_dev[0][0].item() and torch.equal(vec, recs_dev[0][H:])
 
 
 @pytest.mark.parametrize("n,b", [(1, 3), (5, 17), (33, 129), (70, 1000), (129, 40), (250, 333), (300, 50), (600, 9)])

@@ -13,13 +13,20 @@ from tools import equivalence_gpu as G
 pytestmark = pytest.mark.gpu
 
 REF = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "equivalence_ref.json")))
-SOLVERS = [s for s in ("mf", "langevin", "pumped_langevin", "dl") if f"{s}/seed0/70" in REF]
+SOLVERS = [s for s in G.ALL_LOOPS if f"{s}/seed0/70" in REF]
 
 
+@pytest.mark.parametrize("route", ["many", "single"])
 @pytest.mark.parametrize("name", SOLVERS)
-def test_statistically_equivalent_on_bundled_instances(name):
+def test_statistically_equivalent_on_bundled_instances(name, route):
+    """All eight loops (the _solve_adam ones on the first 10 instances of every size, with the
+    AdamParameters of the reference's examples), through batched launches (solve_many) AND through
+    one Solver.__call__ per instance (the single-launch kernel instantiations)."""
     meta = REF["_meta"]
-    rows = G.run_engine(name, meta["keys"][name], meta["post_processor"][name], seed=0, batch=meta["batch"])
+    if route == "single" and not name.endswith("_adam"):
+        pytest.skip("300 single calls per solver: run with tools/equivalence_gpu.py --route single")
+    rows = G.run_engine(name, meta["keys"][name], meta["post_processor"][name], seed=0, batch=meta["batch"],
+                        adam=meta.get("adam"), per_size=meta.get("adam_per_size"), route=route)
     g = G.gate(REF, name, rows, meta["batch"])
     e = g["engine_vs_ref"]
     assert e["reject_rate"] <= g["max_reject"], (name, e["rejects"], e["cells"], g["max_reject"])

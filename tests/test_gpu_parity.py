@@ -45,25 +45,36 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("solver,adam,n,b,t,tol", CASES)
-def test_replay_parity_vs_oracle(solver, adam, n, b, t, tol):
+SOLVER_IDS = {"dl": nat.SOLVER_DL, "mf": nat.SOLVER_MF, "lv": nat.SOLVER_LANGEVIN, "plv": nat.SOLVER_PUMPED_LANGEVIN}
+
+
+def parity_case(solver, adam, n, b, t, tol, philox=None):
+    """CUDA loop vs oracle on the same noise.  philox=None: both replay a torch-drawn noise tensor
+    (validation mode).  philox=(seed, offset): the engine runs in PRODUCTION mode (in-kernel Philox,
+    the kernel instantiations a user gets) and the oracle replays the tensor ccvm_dump_noise writes
+    for the same (seed, offset) -- this is what pins the production variants to the oracle."""
     mult = 0.2 if solver == "dl" else 0.05
     q, v, sb = instance(n, n + 7, mult)
     k = 2 if solver == "dl" else 1
-    noise = O.make_replay_noise(3, t, k, n, b)
+    qg, vg = q.cuda(), v.cuda()
+    if philox is None:
+        noise = O.make_replay_noise(3, t, k, n, b)
+        nkw = dict(noise=noise.cuda())
+    else:
+        noise = E.dump_noise(SOLVER_IDS[solver], n, b, t, philox[0], philox[1]).cpu()
+        nkw = dict(seed=philox[0], offset=philox[1])
     src = O.NoiseSource(n, b, replay=noise)
-    qg, vg, ng = q.cuda(), v.cuda(), noise.cuda()
     alg = nat.ALG_ADAM if adam else nat.ALG_ORIGINAL
     if solver == "dl":
         if adam:
             c_ref, _ = O.dl_solve_adam(q, v, b, t, 8.0, 0.001, 10.0, src, HP)
             outs, _ = E.solve(nat.SOLVER_DL, alg, qg, vg, b, t, s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0, g=0.05,
-                              hyperparameters=HP, noise=ng)
+                              hyperparameters=HP, **nkw)
             s_map = np.sqrt(7.0)
         else:
             c_ref, _ = O.dl_solve(q, v, b, t, 8.0, 0.001, 10.0, 100.0, src)
             outs, _ = E.solve(nat.SOLVER_DL, alg, qg, vg, b, t, s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0,
-                              feedback_scale=100.0, g=0.05, noise=ng)
+                              feedback_scale=100.0, g=0.05, **nkw)
             s_map = 1.0
         x_ref, x_gpu = O.change_variables(c_ref, 0, 1, s_map), O.change_variables(outs[0].cpu(), 0, 1, s_map)
     elif solver == "mf":
@@ -71,25 +82,46 @@ def test_replay_parity_vs_oracle(solver, adam, n, b, t, tol):
         args = (q, v, b, t, 20.0, 0.0, 0.0025, 5.0, 4000.0, src) + ((HP,) if adam else ())
         _, mt_ref, _ = fn(*args)
         outs, _ = E.solve(nat.SOLVER_MF, alg, qg, vg, b, t, s=20.0, pump=0.0, dt=0.0025, j=5.0, feedback_scale=4000.0,
-                          g=0.01, hyperparameters=HP if adam else None, noise=ng)
+                          g=0.01, hyperparameters=HP if adam else None, **nkw)
         x_ref, x_gpu = O.change_variables(mt_ref, 0, 1, 20.0), O.change_variables(outs[1].cpu(), 0, 1, 20.0)
     elif solver == "lv":
         fn = O.langevin_solve_adam if adam else O.langevin_solve
         args = (q, v, b, t, 0.5, 0.002, 0.5, 1.0, src) + ((HP,) if adam else ())
         c_ref = fn(*args)
         outs, _ = E.solve(nat.SOLVER_LANGEVIN, alg, qg, vg, b, t, s=0.5, dt=0.002, sigma=0.5, feedback_scale=1.0,
-                          hyperparameters=HP if adam else None, noise=ng)
+                          hyperparameters=HP if adam else None, **nkw)
         x_ref, x_gpu = (c_ref + 0.5), (outs[0].cpu() + 0.5)
     else:
         fn = O.pumped_langevin_solve_adam if adam else O.pumped_langevin_solve
         args = (q, v, b, t, 0.5, 2.0, 0.002, 0.5, 1.0, src) + ((HP,) if adam else ())
         c_ref = fn(*args)
         outs, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, alg, qg, vg, b, t, s=0.5, pump=2.0, dt=0.002, sigma=0.5,
-                          feedback_scale=1.0, hyperparameters=HP if adam else None, noise=ng)
+                          feedback_scale=1.0, hyperparameters=HP if adam else None, **nkw)
         x_ref, x_gpu = (c_ref + 0.5), (outs[0].cpu() + 0.5)
     assert torch.isfinite(x_gpu).all()
     err = rel_obj_err(x_gpu, x_ref, q, v, sb)
     assert err <= tol, f"{solver} adam={adam} n={n}: objective rel err {err:.3e}"
+    return err
+
+
+@pytest.mark.parametrize("solver,adam,n,b,t,tol", CASES)
+def test_replay_parity_vs_oracle(solver, adam, n, b, t, tol):
+    parity_case(solver, adam, n, b, t, tol)
+
+
+def test_readme_quickstart_full_length():
+    """BASELINE configs[0] at its full length: N = 20, B = 100, T = 15000, pump 2.0,
+    dt 0.005 -- with feedback_scale = 1 the run stays finite, and 15000 rows of the schedule table
+    and 15000 steps of fp32 drift accumulation have to track the oracle."""
+    n, b, t = 20, 100, 15000
+    q, v, sb = instance(n, 1, 0.2)
+    noise = O.make_replay_noise(5, t, 2, n, b)
+    c_ref, _ = O.dl_solve(q, v, b, t, 2.0, 0.005, 10.0, 1.0, O.NoiseSource(n, b, replay=noise))
+    outs, _ = E.solve(nat.SOLVER_DL, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, s=1.0, pump=2.0, dt=0.005,
+                      noise_ratio=10.0, feedback_scale=1.0, g=0.05, noise=noise.cuda())
+    assert torch.isfinite(c_ref).all() and torch.isfinite(outs[0]).all()
+    x_ref, x_gpu = O.change_variables(c_ref, 0, 1, 1.0), O.change_variables(outs[0].cpu(), 0, 1, 1.0)
+    assert rel_obj_err(x_gpu, x_ref, q, v, sb) <= 1e-3
 
 
 def test_nan_for_nan():
@@ -192,11 +224,11 @@ def test_philox_statistical_equivalence(solver):
         assert abs((-e_ref).max().item() - (-e_gpu).max().item()) <= 1e-3 * abs(opt)
 
 
-@pytest.mark.parametrize("env", ["CCVM_NO_TMEM", "CCVM_LEGACY"])
+@pytest.mark.parametrize("env", ["CCVM_NO_TMEM"])
 @pytest.mark.parametrize("solver,adam", [("dl", True), ("mf", False), ("plv", True)])
 def test_alternate_kernel_paths(monkeypatch, env, solver, adam):
-    """The streamed-Q kernel and the first-generation shared-memory kernel stay parity-green at a
-    size the TMEM kernel normally takes (selected through the library's environment switches)."""
+    """The streamed-Q kernel stays parity-green at a size the TMEM kernel normally takes (selected
+    through the library's environment switch)."""
     monkeypatch.setenv(env, "1")
     test_replay_parity_vs_oracle(solver, adam, 70, 100, 200, 2e-3 if (solver == "dl" and adam) else 1e-3)
 

@@ -1,0 +1,84 @@
+"""The PRODUCTION kernel instantiations against the oracle (VERDICT r1 "what's weak" 1).
+
+Noise replay forces the plain variants of the tile kernels (no in-loop noise, run-time column-group
+loop), so the replay tests never run the code a user gets.  Here the engine runs in production mode
+(in-kernel Philox, PIPE / HOIST / VSMEM / compile-time column groups as planned by the library) and
+the ORACLE replays the noise tensor that ``ccvm_dump_noise`` writes for the same (seed, offset): same
+normals on both sides, so the per-trajectory objective must agree to the replay tolerance (1e-3
+relative, 2e-3 for DL-adam; reference loops dl_solver.py:468-769, mf_solver.py:493-764,
+langevin_solver.py:368-561, pumped_langevin_solver.py:232-449)."""
+import pytest
+import torch
+
+from oracle import ccvm_oracle as O
+from ccvm_b200 import engine as E, _native as nat
+from tests.test_gpu_parity import HP, SOLVER_IDS, instance, parity_case
+
+pytestmark = pytest.mark.gpu
+
+TILES = [("dl", False), ("dl", True), ("mf", False), ("mf", True), ("lv", False), ("lv", True), ("plv", False),
+         ("plv", True)]
+
+
+def tol_of(solver, adam):
+    return 2e-3 if (solver == "dl" and adam) else 1e-3
+
+
+def launch_info(solver, adam, n, b, t):
+    d = nat.SolveDesc()
+    d.solver, d.algorithm, d.n, d.batch, d.iterations = SOLVER_IDS[solver], int(adam), n, b, t
+    d.lower, d.upper, d.s = 0.0, 1.0, 1.0
+    d.rng_mode = nat.RNG_PHILOX
+    q = torch.zeros(n, n, device="cuda")
+    d.q, d.v, d.out0, d.out1, d.out2 = (q.data_ptr(),) * 5   # never dereferenced by the query
+    return E.query_launch(d)
+
+
+# compile-time column-group variants: CG = 5, 8, 10, 13, 15, 18 <-> the reference's benchmarking sizes
+@pytest.mark.parametrize("solver,adam", TILES)
+@pytest.mark.parametrize("n", [20, 30, 40, 50, 60, 70])
+def test_compile_time_column_group_variants(solver, adam, n):
+    parity_case(solver, adam, n, 300, 200, tol_of(solver, adam), philox=(1234, 8 * n))
+
+
+# run-time PIPE loop (CG = 9, 17, 32), ragged sizes, the hybrid kernel (n = 129, 250)
+@pytest.mark.parametrize("solver,adam", TILES)
+@pytest.mark.parametrize("n,b,t", [(36, 257, 150), (68, 300, 150), (128, 200, 100), (33, 129, 150), (129, 150, 80),
+                                   (250, 120, 60)])
+def test_run_time_pipe_and_hybrid_variants(solver, adam, n, b, t):
+    parity_case(solver, adam, n, b, t, tol_of(solver, adam), philox=(99, n + b))
+
+
+# the launch geometry of the benchmark: N = 70, B = 4096 -> 147 CTAs of two 7-pair groups
+@pytest.mark.parametrize("solver,adam", TILES)
+@pytest.mark.parametrize("mode", ["replay", "philox"])
+def test_benchmark_geometry(solver, adam, mode):
+    info = launch_info(solver, adam, 70, 4096, 100)
+    assert info["ctas"] == 147 and info["threads"] == 256 and info["traj_per_cta"] == 28
+    parity_case(solver, adam, 70, 4096, 100, tol_of(solver, adam), philox=(7, 3) if mode == "philox" else None)
+
+
+# tcgen05 path in production mode (n = 512: two 256-column output chunks; >= 1024 contraction rows)
+@pytest.mark.parametrize("solver,adam", [("dl", False), ("dl", True), ("mf", False), ("lv", True), ("plv", False)])
+def test_tensor_core_path_production(solver, adam):
+    b = 512 if solver == "dl" else 1024
+    assert launch_info(solver, adam, 512, b, 30)["threads"] == 320   # the tcgen05 kernels (10 warps)
+    parity_case(solver, adam, 512, b, 30, tol_of(solver, adam), philox=(5, 11))
+
+
+def test_dump_noise_is_what_replay_consumes():
+    """Engine in production mode == engine in replay mode on its own dumped noise (same kernel family,
+    different variants): tight agreement, and the dump honours traj_base."""
+    n, b, t = 70, 96, 120
+    q, v, _ = instance(n, 3, 0.05)
+    qg, vg = q.cuda(), v.cuda()
+    kw = dict(s=0.5, pump=2.0, dt=0.002, sigma=0.5, feedback_scale=1.0)
+    prod, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, b, t, seed=21, offset=5, **kw)
+    noise = E.dump_noise(nat.SOLVER_PUMPED_LANGEVIN, n, b, t, 21, 5)
+    rep, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, b, t, noise=noise, **kw)
+    assert (prod[0] - rep[0]).abs().max().item() <= 2e-5
+    part = E.dump_noise(nat.SOLVER_PUMPED_LANGEVIN, n, 40, t, 21, 5, traj_base=56)
+    assert torch.equal(part, noise[..., 56:96])
+    # standard normal
+    x = noise.double().flatten()
+    assert abs(x.mean().item()) < 5 / x.numel() ** 0.5 and abs(x.var().item() - 1) < 5 * (2 / x.numel()) ** 0.5
