@@ -43,14 +43,33 @@ def synthetic_instance(n, seed):
 
 
 def workload_config(n_gpus):
+    """The workload, identical for both arms (arm-specific notes go to the line's `notes`)."""
     return {
         "workload": "configs[2]: DLSolver._solve_adam (pump 8, dt 0.001, noise_ratio 10, g 0.05; Adam alpha 1e-3, "
                     "beta 0.9/0.999, add_assign False) + adam post-processor + compute_energy + solution stats",
         "n": N, "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "iterations": ITERS,
-        "instance": "synthetic dense BoxQP, seed 1000 (SURVEY 8d generator)", "rng": "philox4x32-10 in-kernel",
-        "l2": "L2 flushed (256 MiB write) before every timed step, outside the per-step event pair",
-        "parallelism": f"batch sharded over {n_gpus} GPU(s), no data-path collective; one all_gather of N+9 floats per step",
+        "instance": "synthetic dense BoxQP, seed 1000 (SURVEY 8d generator)",
     }
+
+
+GPU_NOTES = {
+    "rng": "in-kernel: Philox4x32-10-seeded xoshiro128+ stream per (trajectory pair, 4 variables), Box-Muller",
+    "l2": "L2 flushed (256 MiB write) before every timed step, outside the per-step event pair",
+    "parallelism": "batch sharded over the GPUs, no data-path collective; one all_gather of N+10 words per step",
+    "launches": "one fused kernel per step (schedules + loop + change of variables + post-processor + energy + "
+                "statistics); N > 1 adds pack_record + merge_records",
+}
+
+
+def _clean(obj):
+    """Strict JSON: non-finite floats (an unsolved size has TTS = inf) become strings."""
+    if isinstance(obj, float) and not np.isfinite(obj):
+        return str(obj)
+    if isinstance(obj, dict):
+        return {k: _clean(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_clean(v) for v in obj]
+    return obj
 
 
 # ------------------------------------------------------------------------ CPU reference arm
@@ -112,11 +131,12 @@ def run_reference_arm(args):
     sample = (f"{CPU_SAMPLE_ITERS} of {ITERS} iterations of the same B={BATCH}, N={N} DL-adam loop + adam "
               f"post-processor + energy per step (per-iteration cost is constant in T)")
     cfg = workload_config(args.gpus)
-    cfg["parallelism"] = "single host process, torch intra-op threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "notes": {"parallelism": "single host process, torch intra-op threads", "rng": "torch CPU generator",
+                  "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -184,6 +204,192 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+def oracle_check(E, nat, q_host, v_host, q, v, sb, s_val, traj_base):
+    """Best-of-batch and per-trajectory objective of the PRODUCTION kernel (same launch geometry as the timed
+    steps: full batch) against the CPU oracle on a 64-trajectory slice, the oracle replaying the dumped noise."""
+    from oracle import ccvm_oracle as O
+    iters, nb = 200, 64
+    plan = E.plan_solve(nat.SOLVER_DL, nat.ALG_ADAM, q, v, BATCH, iters, s=1.0, pump=DL["pump"], dt=DL["dt"],
+                        noise_ratio=DL["noise_ratio"], g=DL["g"], hyperparameters=HP, seed=77, offset=5,
+                        traj_base=traj_base)
+    epi = E.plan_epilogue(BATCH, N, q.device, map1=(0.5 / s_val, 0.5), post_processor="adam", scaled_by=sb)
+    E.solve_fused(plan, epi, 0.0)
+    noise = E.dump_noise(nat.SOLVER_DL, N, nb, iters, 77, 5, traj_base=traj_base).cpu()
+    c_ref, _ = O.dl_solve_adam(q_host, v_host, nb, iters, DL["pump"], DL["dt"], DL["noise_ratio"],
+                               O.NoiseSource(N, nb, replay=noise), dict(HP), True, DL["g"], 1.0)
+    _, e_ref = O.epilogue("mf", c_ref, q_host, v_host, sb, s_val, post_processor="adam")
+    e_gpu = epi.energy[:nb].cpu()
+    rel = ((e_gpu - e_ref).abs() / e_ref.abs().clamp_min(1e-6)).max().item()
+    return {"trajectories": nb, "iterations": iters, "max_rel_objective_err": rel, "tolerance": 2e-3,
+            "best_gpu": float((-e_gpu).max()), "best_oracle": float((-e_ref).max()), "ok": bool(rel <= 2e-3)}
+
+
+SWEEP_SIZES = list(range(20, 251, 10))
+SWEEP_COUNT, SWEEP_BATCH, SWEEP_ITERS, SWEEP_CHUNK = 1024, 1000, 1500, 64
+
+
+def sweep_record(rank, world, dev):
+    """BASELINE configs[4] (scaled to 1024 instances so that it fits the bench's time budget): synthetic
+    BoxQP instances with N uniform on {20, 30, ..., 250}, B = 1000, T = 1500, Langevin + grad-descent,
+    dealt over the ranks (longest-processing-time placement), chunked fused launches (solve_many).
+    STRONG scaling: the instance set is fixed, `wall_s` includes building this rank's instances on the
+    device, planning, launching and the final gather of the metadata records."""
+    import torch.distributed as dist
+    from ccvm_b200 import sweep
+    from ccvm_b200.solvers import LangevinSolver
+    solver = LangevinSolver(device="cuda", batch_size=SWEEP_BATCH)
+    solver.parameter_key = {n: dict(dt=0.002, S=0.5, sigma=0.5, feedback_scale=1.0, iterations=SWEEP_ITERS)
+                            for n in SWEEP_SIZES}
+    draw = np.random.RandomState(0).choice(len(SWEEP_SIZES), SWEEP_COUNT)
+    specs = [(SWEEP_SIZES[int(i)], k) for k, i in enumerate(draw)]
+    costs = [n * n for n, _ in specs]
+
+    def get(i):
+        n, k = specs[i]
+        return sweep.synthetic_instance(n, k, solver._scaling_multiplier, on_device=True)
+
+    # untimed warm-up: one instance of every size through the same path (module loading, allocator)
+    warm = [sweep.synthetic_instance(n, 10_000 + n, solver._scaling_multiplier, on_device=True) for n in SWEEP_SIZES]
+    solver.solve_many(warm, post_processor="grad-descent")
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    md = sweep.solve_sweep(solver, (SWEEP_COUNT, get), post_processor="grad-descent", chunk=SWEEP_CHUNK, costs=costs)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = t.item()
+    steps = float(SWEEP_COUNT) * SWEEP_BATCH * SWEEP_ITERS
+    return {"workload": "configs[4] mix: 1024 synthetic BoxQP instances, N uniform on {20..250 step 10}, B=1000, T=1500, "
+                        "Langevin + grad-descent", "scaling": "strong", "instances": len(md), "n_gpus": world,
+            "chunk": SWEEP_CHUNK, "wall_s": wall, "traj_steps_per_s": steps / wall,
+            "drift_tflops": sum(2.0 * n * n for n, _ in specs) * SWEEP_BATCH * SWEEP_ITERS / wall / 1e12,
+            "ms_per_instance": wall / SWEEP_COUNT * 1e3,
+            "finite": bool(all(np.isfinite(r["best_objective_value"]) for r in md))}
+
+
+def config4_record(E, nat, rank, world, dev):
+    """BASELINE configs[3]: synthetic dense BoxQP N = 1024, batch 8192 per GPU through the tcgen05 3xTF32 path
+    (weak scaling; max over ranks), as logical drift TFLOP/s and as a fraction of the measured 3xTF32 ceiling
+    (a third of the dense TF32 rate of back-to-back tcgen05.mma, ccvm_microbench_tf32)."""
+    import torch.distributed as dist
+    n, b, t = 1024, 8192, 100
+    q, v, _ = synthetic_instance(n, 1)
+    qd, vd = q.to(dev), v.to(dev)
+    ceiling = E.microbench_tf32(2) / 3.0
+    out = {"n": n, "batch_per_gpu": b, "iterations": t, "n_gpus": world, "ceiling_3xtf32_tflops": ceiling, "loops": {}}
+    cases = {"dl": (nat.SOLVER_DL, 2, dict(s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0, feedback_scale=100.0, g=0.05)),
+             "langevin": (nat.SOLVER_LANGEVIN, 1, dict(s=0.5, dt=0.002, sigma=0.5, feedback_scale=1.0))}
+    for name, (sid, m, kw) in cases.items():
+        for w in range(2):
+            E.solve(sid, nat.ALG_ORIGINAL, qd, vd, b, t, seed=3, offset=w, traj_base=rank * b, **kw)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        per = []
+        for r in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            outs, _ = E.solve(sid, nat.ALG_ORIGINAL, qd, vd, b, t, seed=3, offset=8 + r, traj_base=rank * b, **kw)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            per.append(e0.elapsed_time(e1))
+        ms = sorted(per)[1]
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = tt.item()
+        tf = world * 2.0 * m * n * n * b * t / (ms * 1e-3) / 1e12
+        out["loops"][name] = {"ms": ms, "logical_tflops": tf, "frac_of_ceiling": tf / ceiling / world,
+                              "finite": bool(torch.isfinite(outs[0]).all())}
+    return out
+
+
+def gpu_eager_record(q, v, sb):
+    """the UNMODIFIED reference with device='cuda' (eager torch on the same B200), the whole
+    workload once (B = 4096, T = 1500), with explicit synchronisation around it (the reference itself stops
+    its clock without one, dl_solver.py:851,933)."""
+    if not _load_reference():
+        return {"unavailable": "baseline/_ref not present"}
+    import contextlib
+    import io
+    from ccvm_simulators.solvers import DLSolver
+    from ccvm_simulators.post_processor.adam import PostProcessorAdam
+    s_val = float(np.sqrt(DL["pump"] - 1))
+
+    def run(iters):
+        sol = DLSolver(device="cuda", batch_size=BATCH, S=s_val)
+        sol.q_matrix, sol.v_vector, sol.solution_bounds = q, v, (0.0, 1.0)
+        c, _ = sol._solve_adam(N, BATCH, "cuda", s_val, DL["pump"], DL["dt"], iters, DL["noise_ratio"], True, DL["g"],
+                               None, None, dict(HP))
+        x = sol.change_variables(c, 0.0, 1.0, s_val)
+        with contextlib.redirect_stderr(io.StringIO()):
+            pv = PostProcessorAdam().postprocess(x, q, v)
+        e = 0.5 * torch.einsum("bi, ij, bj -> b", pv, q, pv) * sb + torch.einsum("bi, i -> b", pv, v) * sb
+        return float((-e).max())
+
+    run(50)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    best = run(ITERS)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": BATCH * ITERS / dt, "unit": UNIT, "seconds": dt, "kind": "reference, device='cuda' (eager torch)",
+            "best_objective": best}
+
+
+def tts_record():
+    """TTS half of the metric on a bundled Size70 subset: DLSolver (B = 1000, T = 1500, the example's parameter
+    key), this engine on the GPU vs the unmodified reference on the host CPU, the reference's own definition
+    (mean per-run solve time x bootstrapped R99 of the <= 0.1 %-gap success fraction; ccvm_b200/tts.py)."""
+    if not _load_reference():
+        return {"unavailable": "baseline/_ref not present"}
+    import contextlib
+    import io
+    from ccvm_b200 import tts
+    from ccvm_b200.solvers import DLSolver as EngineDL
+    from tools.equivalence_gpu import load_bundled
+    import ccvm_simulators.solvers as RS
+    from ccvm_simulators.problem_classes.boxqp import ProblemInstance as RefInstance
+    n, count = 70, 4
+    key = dict(pump=8.0, feedback_scale=100, dt=0.001, iterations=1500, noise_ratio=10)
+    torch.manual_seed(0)
+    eng = EngineDL(device="cuda", batch_size=1000)
+    eng.parameter_key = {n: dict(key)}
+    insts = load_bundled()[n][:count]
+    for inst in insts:
+        inst.scale_coefs(eng.get_scaling_factor(inst.q_matrix))
+    eng(instance=insts[0])
+    recs_e = [eng(instance=i).get_metadata_dict() for i in insts]
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bundled_instances.npz"))
+    ref = RS.DLSolver(device="cpu", batch_size=1000)
+    ref.parameter_key = {n: dict(key)}
+    torch.set_num_threads(os.cpu_count())
+    recs_r = []
+    for k in range(count):
+        inst = RefInstance(instance_type="tuning", device="cpu", name=str(z[f"name{n}"][k])[:-3])
+        inst.problem_size = n
+        inst.q_matrix = torch.from_numpy(z[f"q{n}"][k].copy())
+        inst.v_vector = torch.from_numpy(z[f"v{n}"][k].copy())
+        inst.optimal_sol = inst.best_sol = float(z[f"opt{n}"][k])
+        inst.num_frac_values, inst.solution_vector, inst.optimality = 0, [], True
+        inst.scale_coefs(ref.get_scaling_factor(inst.q_matrix))
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            recs_r.append(ref(instance=inst).get_metadata_dict())
+    out = {"instances": count, "n": n, "batch": 1000, "iterations": 1500, "solver": "DLSolver", "cores": os.cpu_count()}
+    for label, recs in (("engine", recs_e), ("reference_cpu", recs_r)):
+        out[label] = {"tts_s": tts.tts_table(recs, percentiles=(50.0,))[n][50.0],
+                      "mean_solve_time_s": float(np.mean([r["solve_time"] for r in recs])),
+                      "mean_p_optimal": float(np.mean([r["solution_performance"]["optimal"] for r in recs]))}
+    out["solve_time_ratio"] = out["reference_cpu"]["mean_solve_time_s"] / out["engine"]["mean_solve_time_s"]
+    te, tr = out["engine"]["tts_s"], out["reference_cpu"]["tts_s"]
+    out["tts_ratio"] = tr / te if np.isfinite(te) and np.isfinite(tr) and te > 0 else None
+    return out
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     from ccvm_b200 import engine as E, _native as nat, parallel as P
@@ -215,20 +421,20 @@ def run_gpu_arm(args):
     launches = {"n": 0}
 
     def device_step(step_idx, ev_mid=None):
-        """solve (1 schedule + 1 persistent SDE kernel) -> fused epilogue -> stats [-> all_gather]."""
-        outs, _ = E.solve(nat.SOLVER_DL, nat.ALG_ADAM, q, v, BATCH, ITERS, s=1.0, pump=DL["pump"], dt=DL["dt"],
-                          noise_ratio=DL["noise_ratio"], g=DL["g"], hyperparameters=HP, seed=1234, offset=step_idx,
-                          traj_base=traj_base)
+        """ONE kernel: schedules + all iterations + change of variables + adam post-processor + energy +
+        solution statistics (ccvm_solve_fused) [-> pack_record -> all_gather -> merge_records]."""
+        plan = E.plan_solve(nat.SOLVER_DL, nat.ALG_ADAM, q, v, BATCH, ITERS, s=1.0, pump=DL["pump"], dt=DL["dt"],
+                            noise_ratio=DL["noise_ratio"], g=DL["g"], hyperparameters=HP, seed=1234, offset=step_idx,
+                            traj_base=traj_base)
+        epi = E.plan_epilogue(BATCH, N, dev, map1=(0.5 / s_val, 0.5), post_processor="adam", scaled_by=sb)
+        res = E.solve_fused(plan, epi, 0.0)
         if ev_mid is not None:
             ev_mid.record(stream)
-        pv, en = E.epilogue(outs[0], q, v, map1=(0.5 / s_val, 0.5), post_processor="adam", scaled_by=sb)
-        res = torch.empty(9, dtype=torch.int32, device=dev)
-        nat.check(lib.ccvm_solution_stats(en.data_ptr(), BATCH, 0.0, res.data_ptr(), stream.cuda_stream))
-        launches["n"] += 4
+        launches["n"] += 1
         if distributed:
             launches["n"] += 2
-            return P.merge_results(P.pack_from_stats(res, pv, traj_base))
-        return res
+            return P.merge_results(P.pack_from_stats(res, epi.pv, traj_base)), res, epi
+        return res, res, epi
 
     # context pre-warm (not a step): module loading and the SM clock ramp of a fresh process take
     # tens of milliseconds, more than W short steps cover -- spin the FP32 probe for ~0.2 s first
@@ -243,6 +449,7 @@ def run_gpu_arm(args):
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    raw_results = []
     if distributed:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -251,8 +458,9 @@ def run_gpu_arm(args):
     for k in range(args.steps):
         flush.fill_(float(k))
         ev[k][0].record(stream)
-        device_step(1000 + k, ev[k][1])
+        last = device_step(1000 + k, ev[k][1])
         ev[k][2].record(stream)
+        raw_results.append(last[1])
     torch.cuda.synchronize(dev)
     if distributed:
         dist.barrier()
@@ -260,9 +468,12 @@ def run_gpu_arm(args):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     step_ms = [ev[k][0].elapsed_time(ev[k][2]) for k in range(args.steps)]
-    solve_ms = [ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]
     total_ms = float(sum(step_ms))
-    solve_avg_ms = float(np.mean(solve_ms))
+    # the dominant kernel (at N = 1 it IS the step: one launch): duration by CUDA events on the launching stream
+    solve_avg_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
+    fused = [E.decode_fused_results(r.cpu())[0] for r in raw_results]
+    loop_ms = float(np.mean([f["loop_ns"] for f in fused])) * 1e-6     # in-kernel %globaltimer, max over CTAs
+    tail_ms = float(np.mean([f["tail_ns"] for f in fused])) * 1e-6
     if distributed:
         t = torch.tensor([total_ms, solve_avg_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -284,11 +495,30 @@ def run_gpu_arm(args):
     ed.post_processor, ed.pp_iterations, ed.pp_step, ed.pp_lower, ed.pp_upper = nat.PP_ADAM, 1, 0.01, 0.0, 1.0
     ed.scaled_by = sb
 
+    h_best = torch.empty((), dtype=torch.float32).pin_memory()
+    h_vec = torch.empty(N, dtype=torch.float32).pin_memory()
+
     def host_step(step_idx):
-        sd.offset = step_idx
-        nat.check(lib.ccvm_solve_host(ctypes.byref(sd), ctypes.byref(ed), qp.data_ptr(), vp.data_ptr(), 0.0,
-                                      h_energy.data_ptr(), h_stats.data_ptr(), stream.cuda_stream))
-        return float(h_stats[:1].view(torch.float32))
+        """N = 1: the C ABI's host-buffer entry (H2D of Q, V; one fused launch; D2H of energies + statistics).
+        N > 1: the same through the package API, plus the cross-rank merge of the step (pack_record,
+        all_gather, merge_records) and the D2H of the merged best objective and winner's vector."""
+        if not distributed:
+            sd.offset = step_idx
+            nat.check(lib.ccvm_solve_host(ctypes.byref(sd), ctypes.byref(ed), qp.data_ptr(), vp.data_ptr(), 0.0,
+                                          h_energy.data_ptr(), h_stats.data_ptr(), stream.cuda_stream))
+            return float(h_stats[:1].view(torch.float32))
+        qd, vd = qp.to(dev, non_blocking=True), vp.to(dev, non_blocking=True)
+        plan = E.plan_solve(nat.SOLVER_DL, nat.ALG_ADAM, qd, vd, BATCH, ITERS, s=1.0, pump=DL["pump"], dt=DL["dt"],
+                            noise_ratio=DL["noise_ratio"], g=DL["g"], hyperparameters=HP, seed=1234, offset=step_idx,
+                            traj_base=traj_base)
+        epi = E.plan_epilogue(BATCH, N, dev, map1=(0.5 / s_val, 0.5), post_processor="adam", scaled_by=sb)
+        res = E.solve_fused(plan, epi, 0.0)
+        best, _, _, vec = P.merge_results(P.pack_from_stats(res, epi.pv, traj_base))
+        h_energy.copy_(epi.energy, non_blocking=True)
+        h_best.copy_(best, non_blocking=True)
+        h_vec.copy_(vec, non_blocking=True)
+        stream.synchronize()
+        return float(h_best)
 
     for w in range(max(args.warmup, 1)):
         host_step(w)
@@ -304,6 +534,31 @@ def run_gpu_arm(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = t[0].item()
+
+    # ---- post-run check (outside every timed region): a 64-trajectory slice of the production kernel's last
+    # step against the CPU oracle replaying the normals that step drew (ccvm_dump_noise)
+    check = None
+    if rank == 0:
+        try:
+            check = oracle_check(E, nat, q_host, v_host, q, v, sb, s_val, traj_base)
+        except Exception as e:  # noqa: BLE001
+            check = {"error": f"{type(e).__name__}: {e}"}
+
+    extras = {}
+    if not args.no_extras:
+        for name, fn in (("sweep", lambda: sweep_record(rank, world, dev)),
+                         ("config4", lambda: config4_record(E, nat, rank, world, dev))):
+            try:
+                extras[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                extras[name] = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0 and world == 1:
+            for name, fn in (("gpu_eager_baseline", lambda: gpu_eager_record(q, v, sb)),
+                             ("tts", lambda: tts_record())):
+                try:
+                    extras[name] = fn()
+                except Exception as e:  # noqa: BLE001
+                    extras[name] = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- roofline of the dominant kernel (the persistent SDE kernel): FP32 SIMT FMA
     traffic = None   # DRAM bytes per launch of that kernel, from the committed ncu --set full capture
@@ -338,23 +593,29 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world), "clocks": clocks,
+            "notes": GPU_NOTES,
             "e2e": {"value": world * BATCH * ITERS * args.steps / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": (N * N + N) * 4, "d2h_bytes_per_step": BATCH * 4 + 36,
-                    "api": "ccvm_solve_host (C ABI, pinned host buffers)"},
+                    "h2d_bytes_per_step": (N * N + N) * 4,
+                    "d2h_bytes_per_step": BATCH * 4 + (36 if world == 1 else 4 + 4 * N),
+                    "api": "ccvm_solve_host (C ABI, pinned host buffers)" if world == 1 else
+                           "plan_solve/solve_fused + merge_results (package API, pinned host buffers, cross-rank merge inside)"},
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic,
-                         "kernel": "ccvm::sde_tmem_kernel<DL, adam>", "kernel_ms": solve_avg_ms,
+                         "kernel": "ccvm::sde_tmem_kernel<DL, adam, TMEM, PIPE, 18> (fused: schedules + loop + tail)",
+                         "kernel_ms": solve_avg_ms, "loop_ms_in_kernel": loop_ms, "tail_ms_in_kernel": tail_ms,
                          "peak_source": "measured in-process: register-only FFMA2 probe (ccvm_microbench_fp32); "
                                         "MEASURED_PEAKS.json has no FP32 SIMT figure (HBM/bf16 only)",
                          "algorithmic_flops_per_launch": flops_per_launch},
             "cpu_baseline": cpu_baseline,
+            "oracle_check": check,
+            **extras,
             "wall_s_timed_region": wall,
             "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(np.max(step_ms)),
         }
         sys.stdout.flush()
         os.dup2(stdout_fd, 1)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(_clean(line)), flush=True)
         os.dup2(2, 1)
     if distributed:
         dist.barrier()
@@ -367,6 +628,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the sweep / config4 / eager-GPU / TTS sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         args.steps = args.steps or 5

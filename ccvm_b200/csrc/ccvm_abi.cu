@@ -369,6 +369,10 @@ static int validate_solve(const ccvm_solve_desc* d) {
     if (d->noise_batch < d->traj_base + d->batch) return fail(CCVM_E_INVALID, "noise tensor is too small for the batch");
   } else if (d->rng_mode != CCVM_RNG_PHILOX) {
     return fail(CCVM_E_INVALID, "unknown rng mode %d", d->rng_mode);
+  } else if (d->traj_base & 1) {
+    // the SIMT kernels key one noise stream per PAIR of trajectories (2p, 2p+1)
+    return fail(CCVM_E_INVALID, "traj_base must be even in Philox mode (got %lld): split batches at even indices",
+                (long long)d->traj_base);
   }
   if (d->evolution_step > 0 && (!d->samples || d->num_samples < 1))
     return fail(CCVM_E_INVALID, "evolution sampling needs a samples buffer");
@@ -935,8 +939,10 @@ extern "C" int ccvm_solve_batch_fused(const ccvm_solve_desc* descs, const ccvm_e
 // The normals a production solve draws, written in the replay layout noise[T][K][n][batch]: feeding this
 // tensor to the CPU oracle (or back to the engine in replay mode) reproduces a production run exactly,
 // which pins the production kernel variants (in-loop noise, compile-time column groups) to the oracle.
-__global__ void dump_noise_kernel(uint32_t k0, uint32_t k1, uint32_t off_lo, long long traj_base, int n, int batch,
-                                  int iterations, int K, float* __restrict__ noise) {
+// Counter mode (the generator of the tcgen05 path): one thread per (iteration, quadrature, column group,
+// trajectory).
+__global__ void dump_noise_counter_kernel(uint32_t k0, uint32_t k1, uint32_t off_lo, long long traj_base, int n,
+                                          int batch, int iterations, int K, float* __restrict__ noise) {
   const int cg_count = (n + 3) / 4;
   const size_t total = (size_t)iterations * K * cg_count * batch;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -957,17 +963,62 @@ __global__ void dump_noise_kernel(uint32_t k0, uint32_t k1, uint32_t off_lo, lon
   }
 }
 
+// Stream mode (the tiled SIMT kernels): one thread per (trajectory pair, column group) walks its
+// xoshiro128+ stream through all iterations in the kernels' draw order (quadrature, trajectory of the pair).
+__global__ void dump_noise_stream_kernel(uint32_t k0, uint32_t k1, uint32_t off_lo, long long traj_base, int n,
+                                         int batch, int iterations, int K, float* __restrict__ noise) {
+  const int cg_count = (n + 3) / 4;
+  const int pairs = (batch + 1) / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pairs * cg_count) return;
+  const int pr = idx % pairs, cg = idx / pairs;   // neighbouring threads: neighbouring trajectories (coalesced stores)
+#if CCVM_STREAM_PER_TRAJ
+  NoiseStream rs2[2] = {stream_init(k0, k1, off_lo, (unsigned long long)(traj_base + 2 * (long long)pr), (uint32_t)cg),
+                        stream_init(k0, k1, off_lo, (unsigned long long)(traj_base + 2 * (long long)pr + 1), (uint32_t)cg)};
+#else
+  NoiseStream rs = stream_init(k0, k1, off_lo, (unsigned long long)(traj_base + 2 * (long long)pr) >> 1, (uint32_t)cg);
+#endif
+  for (int t = 0; t < iterations; ++t)
+    for (int q = 0; q < K; ++q)
+      for (int i = 0; i < 2; ++i) {
+        float w[4];
+#if CCVM_STREAM_PER_TRAJ
+        stream_normals4(rs2[i], w[0], w[1], w[2], w[3]);
+#else
+        stream_normals4(rs, w[0], w[1], w[2], w[3]);
+#endif
+        const int b = 2 * pr + i;
+        if (b >= batch) continue;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * cg + jj;
+          if (j < n) noise[(((size_t)t * K + q) * n + j) * (size_t)batch + b] = w[jj];
+        }
+      }
+}
+
 extern "C" int ccvm_dump_noise(const ccvm_solve_desc* d, float* noise, void* stream) {
   if (!d || !noise) return fail(CCVM_E_INVALID, "bad argument to ccvm_dump_noise");
   if (d->n < 1 || d->batch < 1 || d->iterations < 1) return fail(CCVM_E_INVALID, "n, batch and iterations must be >= 1");
   if (d->solver < 0 || d->solver > 3) return fail(CCVM_E_INVALID, "unknown solver id %d", d->solver);
   const int K = d->solver == CCVM_SOLVER_DL ? 2 : 1;
-  const size_t total = (size_t)d->iterations * K * ((d->n + 3) / 4) * d->batch;
-  size_t grid = (total + 255) / 256;
-  if (grid > 148 * 64) grid = 148 * 64;
-  dump_noise_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-      (uint32_t)d->seed, (uint32_t)(d->seed >> 32) ^ (uint32_t)(d->offset >> 32), (uint32_t)d->offset, d->traj_base, d->n,
-      d->batch, d->iterations, K, noise);
+  const int cg_count = (d->n + 3) / 4;
+  const uint32_t k0 = (uint32_t)d->seed, k1 = (uint32_t)(d->seed >> 32) ^ (uint32_t)(d->offset >> 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  // the generator ccvm_solve(desc) would use: counter mode on the tcgen05 path, streams on the tiled SIMT path
+  const bool stream_mode = CCVM_SIMT_RNG && choose_path(*d) != PATH_TC;
+  if (stream_mode) {
+    if (d->traj_base & 1) return fail(CCVM_E_INVALID, "traj_base must be even (noise streams belong to trajectory pairs)");
+    const int total = ((d->batch + 1) / 2) * cg_count;
+    dump_noise_stream_kernel<<<(total + 127) / 128, 128, 0, st>>>(k0, k1, (uint32_t)d->offset, d->traj_base, d->n, d->batch,
+                                                                 d->iterations, K, noise);
+  } else {
+    const size_t total = (size_t)d->iterations * K * cg_count * d->batch;
+    size_t grid = (total + 255) / 256;
+    if (grid > 148 * 64) grid = 148 * 64;
+    dump_noise_counter_kernel<<<(unsigned)grid, 256, 0, st>>>(k0, k1, (uint32_t)d->offset, d->traj_base, d->n, d->batch,
+                                                             d->iterations, K, noise);
+  }
   CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
 }

@@ -109,17 +109,69 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   n1 = r * sn;
 }
 
-// The engine's noise stream: four standard normals for (global trajectory gb, iteration t, column group
-// cg = j / 4, quadrature qi) under key (k0, k1) and stream offset off_lo -- one Philox4x32-10 call and two
-// Box-Muller pairs.  EVERY consumer (the tiled SIMT kernels, the tcgen05 kernels, ccvm_dump_noise)
-// goes through this one function, so a dumped noise tensor is exactly what a production solve draws.
+// ---- the engine's noise ---------------------------------------------------------------------
+// Two generators, both keyed by (seed, offset) and by GLOBAL trajectory indices, so results never
+// depend on how a batch is split over CTAs, launches or GPUs:
+//
+//  * counter mode (the tcgen05 kernels, whose threads walk hundreds of column groups per iteration):
+//    one Philox4x32-10 call per (trajectory, iteration, column group, quadrature) -> 4 normals;
+//  * stream mode (the tiled SIMT kernels, CCVM_SIMT_RNG == 1): a thread owns the pair of trajectories
+//    (2p, 2p+1) and one column group for the whole run, so it carries ONE xoshiro128+ state
+//    (Blackman & Vigna 2018; recommended by its authors for floating-point generation, which only
+//    consumes the high bits) seeded by a Philox4x32-10 call on (pair, column group) and draws its
+//    2 x K x 4 normals per iteration from it in a fixed order.  Per 4 normals that is ~32
+//    add / shift / xor instructions on the ALU pipe instead of 20 IMAD.WIDE on the FMA pipe -- the
+//    pipe the drift contraction saturates (ncu, profiles/r1t_ncu_sde_dl_adam_final.txt: IMAD.WIDE was
+//    6.5 % of the instructions, 16 % of the stall samples and ~4 FMA-pipe cycles apiece).
+//
+// Both end in the same Box-Muller transform.  ccvm_dump_noise replays either generator, so the
+// normals of any production solve can be handed to the CPU oracle.
+#ifndef CCVM_SIMT_RNG
+#define CCVM_SIMT_RNG 1
+#endif
+// stream mode, experiment switch: 1 = one stream per TRAJECTORY and column group (two independent
+// chains per thread, 8 state registers), 0 = one per trajectory PAIR (4 registers, traj_base even)
+#ifndef CCVM_STREAM_PER_TRAJ
+#define CCVM_STREAM_PER_TRAJ 0
+#endif
+constexpr uint32_t NOISE_DOMAIN = 0xCC5DE200u;  // keeps solver streams apart from torch's own Philox use of the same seed
+
 __device__ __forceinline__ void noise_normals4(uint32_t k0, uint32_t k1, uint32_t off_lo, unsigned long long gb,
                                                uint32_t t, uint32_t cg, uint32_t qi, float& n0, float& n1, float& n2,
                                                float& n3) {
   const uint4 r = philox4x32_10(make_uint4((uint32_t)gb, t, cg | (qi << 24) | ((uint32_t)(gb >> 32) << 25), off_lo),
-                                make_uint2(k0, k1));
+                                make_uint2(k0, k1 ^ NOISE_DOMAIN));
   box_muller(r.x, r.y, n0, n1);
   box_muller(r.z, r.w, n2, n3);
+}
+
+struct NoiseStream {
+  uint32_t s0, s1, s2, s3;
+};
+// stream of (global trajectory pair, column group)
+__device__ __forceinline__ NoiseStream stream_init(uint32_t k0, uint32_t k1, uint32_t off_lo, unsigned long long pair,
+                                                   uint32_t cg) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), cg | 0x80000000u, off_lo),
+                                make_uint2(k0, k1 ^ NOISE_DOMAIN));
+  NoiseStream s = {r.x, r.y, r.z, r.w};
+  if ((r.x | r.y | r.z | r.w) == 0u) s.s0 = 1u;  // the one state xoshiro cannot leave
+  return s;
+}
+__device__ __forceinline__ uint32_t stream_next(NoiseStream& s) {
+  const uint32_t result = s.s0 + s.s3;
+  const uint32_t t = __funnelshift_l(0u, s.s1, 9);  // s1 << 9 as a funnel shift: stays on the ALU pipe (no IMAD.SHL)
+  s.s2 ^= s.s0;
+  s.s3 ^= s.s1;
+  s.s1 ^= s.s2;
+  s.s0 ^= s.s3;
+  s.s2 ^= t;
+  s.s3 = __funnelshift_l(s.s3, s.s3, 11);
+  return result;
+}
+__device__ __forceinline__ void stream_normals4(NoiseStream& s, float& n0, float& n1, float& n2, float& n3) {
+  const uint32_t a = stream_next(s), b = stream_next(s), c = stream_next(s), d = stream_next(s);
+  box_muller(a, b, n0, n1);
+  box_muller(c, d, n2, n3);
 }
 
 // ---- launch parameters of the persistent SDE kernel ------------------------------------

@@ -21,7 +21,7 @@ constexpr int EPT = 8;        // trajectories per tile of the tiled body
 // shared-memory floats the two bodies need for `nwarps` warps (Q staged on chip or not)
 __host__ __device__ inline size_t epi_tile_floats(int n, int nwarps, int wpt, bool q_in_smem) {
   const int tpc = nwarps / wpt;
-  return (q_in_smem ? (((size_t)n * n + 3) & ~(size_t)3) : 0) + (size_t)tpc * 2 * n * EPT + (size_t)tpc * wpt * EPT * 2;
+  return (q_in_smem ? (((size_t)n * n + 3) & ~(size_t)3) : 0) + (size_t)tpc * 2 * n * EPT + (size_t)tpc * wpt * 4 * EPT * 2;
 }
 __host__ __device__ inline size_t epi_warp_floats(int n, int nwarps, bool q_in_smem) {
   return (q_in_smem ? (size_t)n * (n | 1) : 0) + (size_t)nwarps * 2 * n;
@@ -138,7 +138,7 @@ static __device__ __noinline__ void epilogue_tile_body(const EpiParams& p, float
   const int tile = warp / wpt, wt = warp - tile * wpt;
   float* qs = esm;
   float* xall = esm + (p.q_in_smem ? (((size_t)N * N + 3) & ~(size_t)3) : 0);  // 16-byte aligned (LDS.128)
-  float* red = xall + (size_t)tpc * 2 * N * EPT;  // [tpc][wpt][EPT][2]
+  float* red = xall + (size_t)tpc * 2 * N * EPT;  // [tpc][wpt * CPL column blocks][EPT][2]
   if (p.q_in_smem) {
     for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) qs[idx] = p.q[idx];
   }
@@ -230,39 +230,39 @@ static __device__ __noinline__ void epilogue_tile_body(const EpiParams& p, float
         y = tmp;
       }
       // E = (1/2 x Q x + V x) * scaled_by   (problem_instance.py:226-241)
+      // The sum over columns is associated the same way for EVERY tile geometry (so that a fused tail
+      // in CTAs of any size and the stand-alone kernel agree bit for bit): each block of 32 consecutive
+      // columns is reduced by the warp's xor tree, the block sums are added in ascending column order.
       contract(x, acc);
-      float e1[EPT], e2[EPT];
+      float* rt = red + (size_t)tile * wpt * CPL * EPT * 2;   // [block = wt * CPL + c][EPT][2]
 #pragma unroll
-      for (int tb = 0; tb < EPT; ++tb) {
-        e1[tb] = 0.f;
-        e2[tb] = 0.f;
-#pragma unroll
-        for (int c = 0; c < CPL; ++c)
-          if (jok[c]) {
-            const float xj = x[(size_t)jc[c] * EPT + tb];
-            e1[tb] = fmaf(acc[c][tb], xj, e1[tb]);
-            e2[tb] = fmaf(vj[c], xj, e2[tb]);
-          }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          e1[tb] += __shfl_xor_sync(0xffffffffu, e1[tb], o);
-          e2[tb] += __shfl_xor_sync(0xffffffffu, e2[tb], o);
-        }
-      }
-      float* rt = red + (size_t)tile * wpt * EPT * 2;
-      if (lane == 0) {
+      for (int c = 0; c < CPL; ++c) {
 #pragma unroll
         for (int tb = 0; tb < EPT; ++tb) {
-          rt[(wt * EPT + tb) * 2] = e1[tb];
-          rt[(wt * EPT + tb) * 2 + 1] = e2[tb];
+          float e1 = 0.f, e2 = 0.f;
+          if (jok[c]) {
+            const float xj = x[(size_t)jc[c] * EPT + tb];
+            e1 = acc[c][tb] * xj;
+            e2 = vj[c] * xj;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+            e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+          }
+          if (lane == 0) {
+            rt[((wt * CPL + c) * EPT + tb) * 2] = e1;
+            rt[((wt * CPL + c) * EPT + tb) * 2 + 1] = e2;
+          }
         }
       }
       tile_sync();
       if (wt == 0 && lane < EPT && b0 + lane < b_end) {
+        const int nblocks = (N + 31) / 32;
         float s1 = 0.f, s2 = 0.f;
-        for (int w = 0; w < wpt; ++w) {
-          s1 += rt[(w * EPT + lane) * 2];
-          s2 += rt[(w * EPT + lane) * 2 + 1];
+        for (int m = 0; m < nblocks; ++m) {
+          s1 += rt[(m * EPT + lane) * 2];
+          s2 += rt[(m * EPT + lane) * 2 + 1];
         }
         p.energy[b0 + lane] = 0.5f * (s1 * p.scaled_by) + s2 * p.scaled_by;
       }

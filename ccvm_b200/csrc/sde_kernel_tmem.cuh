@@ -278,13 +278,33 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   }
 
   const uint2 key = make_uint2(p.seed_lo, p.seed_hi ^ p.off_hi);
+#if CCVM_SIMT_RNG
+  // stream mode: one xoshiro128+ state per thread = per (global trajectory pair, column group); the
+  // quanta of an iteration are drawn in the fixed order (quadrature, trajectory of the pair)
+#if CCVM_STREAM_PER_TRAJ
+  NoiseStream rs2[2] = {stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + gb0), (uint32_t)cgc),
+                        stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + gb0 + 1), (uint32_t)cgc)};
+  NoiseStream& rs = rs2[0];
+#else
+  NoiseStream rs = stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + gb0) >> 1, (uint32_t)cgc);
+#endif
+#endif
 
-  // one Philox call: the four columns of (quadrature q, trajectory i) at iteration t
+  // one noise quantum: the four columns of (quadrature q, trajectory i) at iteration t
   auto quantum = [&](pf2 (&Wd)[KT][4], int q, int i, int t) {
+    float n0, n1, n2, n3;
+#if CCVM_SIMT_RNG
+    (void)t;
+#if CCVM_STREAM_PER_TRAJ
+    stream_normals4(rs2[i], n0, n1, n2, n3);
+#else
+    stream_normals4(rs, n0, n1, n2, n3);
+#endif
+#else
     const unsigned long long gb = (unsigned long long)(p.traj_base + gb0 + i);
     const uint32_t qi = (uint32_t)(q + half);  // which quadrature's stream
-    float n0, n1, n2, n3;
     noise_normals4(key.x, key.y, p.off_lo, gb, (uint32_t)t, (uint32_t)cgc, qi, n0, n1, n2, n3);
+#endif
     // Padding columns (j >= n) draw noise like any other: their state stays finite (zero drift, the
     // solver's own saturating terms / a zero clamp), it only ever meets the zero rows of Qs and is
     // never written out -- masking it cost a SEL per normal.
@@ -489,6 +509,11 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         contract(qb, xb);
         xp += (8 / KP) * ROWB;
         if constexpr (!SMALLCG) {
+#if CCVM_SIMT_RNG && CCVM_STREAM_PER_TRAJ
+          rs2[u & 1].s0 ^= pin;
+#elif CCVM_SIMT_RNG
+          rs.s0 ^= pin;  // (0) the formal dependence that pins this quantum to this pair of chunks
+#endif
           if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
           else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
         }
@@ -670,6 +695,11 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
           wait_chunk();
           load_chunk(2 * u + 2, qa);
           contract4(qb);
+#if CCVM_SIMT_RNG && CCVM_STREAM_PER_TRAJ
+          rs2[u & 1].s0 ^= pin;
+#elif CCVM_SIMT_RNG
+          rs.s0 ^= pin;
+#endif
           if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
           else quantum(W, u >> 1, u & 1, tn ^ (int)pin);
         }

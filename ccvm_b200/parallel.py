@@ -17,13 +17,18 @@ N_COUNTS = 7
 HEADER = 3 + N_COUNTS   # CCVM_RECORD_HEADER: energy, index low, index high, 7 counters
 
 
-def shard_bounds(total, world_size, rank):
+def shard_bounds(total, world_size, rank, align=1):
     """Contiguous split of ``total`` items: (start, count) of ``rank``; remainders go to the
-    lowest ranks, so shard sizes differ by at most one."""
-    base, rem = divmod(int(total), int(world_size))
-    count = base + (1 if rank < rem else 0)
-    start = rank * base + min(rank, rem)
-    return start, count
+    lowest ranks, so shard sizes differ by at most ``align``.  ``align=2`` keeps every shard start
+    even -- what trajectory shards need, because the engine's noise streams belong to trajectory
+    pairs (``traj_base`` must be even)."""
+    total, align = int(total), int(align)
+    units = (total + align - 1) // align
+    base, rem = divmod(units, int(world_size))
+    ucount = base + (1 if rank < rem else 0)
+    ustart = rank * base + min(rank, rem)
+    start = min(ustart * align, total)
+    return start, min((ustart + ucount) * align, total) - start
 
 
 def instance_owner(index, world_size):

@@ -79,6 +79,10 @@ class CCVMSolver(ABC):
         self.noise_source = None
         #: list collecting planned (not yet launched) solves while ``solve_many`` is gathering a batch
         self._deferred = None
+        #: optional queue of (seed, offset) noise streams for the next solves instead of torch's CUDA
+        #: generator state: sweeps key every instance by its GLOBAL index, so results do not depend on
+        #: how instances are dealt to ranks or chunks (and no two ranks ever draw the same stream)
+        self.noise_streams = None
 
     # ------------------------------------------------------------------ properties
     @property
@@ -231,6 +235,8 @@ class CCVMSolver(ABC):
         kwargs = dict(lower=lower, upper=upper, s=s_val, s_vec=s_vec, hyperparameters=hyperparameters,
                       noise=self.noise_source, evolution_step=evolution_step_size or None,
                       num_samples=num_samples or 0, **scalars)
+        if self.noise_streams and self.noise_source is None:
+            kwargs["seed"], kwargs["offset"] = self.noise_streams.pop(0)
         if self._deferred is not None:
             plan = engine.plan_solve(solver_id, algorithm, self.q_matrix, self.v_vector, batch_size, iterations,
                                      **kwargs)

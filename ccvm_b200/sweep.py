@@ -65,20 +65,37 @@ def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=No
     else:
         mine = [k for k in range(count) if parallel.instance_owner(k, world_size) == rank]
 
+    # one noise stream per instance, keyed by its GLOBAL index: identical results for any number of ranks
+    # and any chunking, and no two ranks ever share a stream (they all start from the same generator state)
+    streams = None
+    if getattr(solver, "device", "cpu") == "cuda" and hasattr(solver, "noise_streams"):
+        gen = torch.cuda.default_generators[torch.cuda.current_device()]
+        seed, base = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, gen.get_offset()
+        streams = lambda ks: [(seed, base + 4 * (k + 1)) for k in ks]  # noqa: E731
+        gen.set_offset(base + 4 * (count + 1))
+
     def record(k, sol):
         rec = sol.get_metadata_dict()
         rec["best_index"], rec["rank"], rec["index"] = sol.best_index, rank, k
         local[k] = rec
 
-    if chunk <= 1:
-        for k in mine:
-            record(k, solver(instance=getter(k), post_processor=post_processor, **call_kwargs))
-    else:
-        for lo in range(0, len(mine), chunk):
-            ks = mine[lo:lo + chunk]
-            sols = solver.solve_many([getter(k) for k in ks], post_processor=post_processor, **call_kwargs)
-            for k, sol in zip(ks, sols):
-                record(k, sol)
+    try:
+        if chunk <= 1:
+            for k in mine:
+                if streams:
+                    solver.noise_streams = streams([k])
+                record(k, solver(instance=getter(k), post_processor=post_processor, **call_kwargs))
+        else:
+            for lo in range(0, len(mine), chunk):
+                ks = mine[lo:lo + chunk]
+                if streams:
+                    solver.noise_streams = streams(ks)
+                sols = solver.solve_many([getter(k) for k in ks], post_processor=post_processor, **call_kwargs)
+                for k, sol in zip(ks, sols):
+                    record(k, sol)
+    finally:
+        if streams:
+            solver.noise_streams = None
     if world_size == 1 or not gather:
         return [local[k] for k in sorted(local)]
     shards = [None] * world_size

@@ -44,7 +44,9 @@ extern "C" {
 #define CCVM_ALG_ADAM 1     /* Solver._solve_adam */
 
 /* noise source */
-#define CCVM_RNG_PHILOX 0 /* in-kernel Philox4x32-10 + Box-Muller, keyed by (seed, offset, trajectory, step, variable);
+#define CCVM_RNG_PHILOX 0 /* in-kernel generation keyed by (seed, offset, GLOBAL trajectory, variable): Philox4x32-10 per
+                             (trajectory, step, 4 variables) on the tcgen05 path; on the SIMT paths Philox4x32-10 seeds
+                             one xoshiro128+ stream per (trajectory pair, 4 variables); Box-Muller on both.
                              ccvm_dump_noise writes exactly the normals this mode draws */
 #define CCVM_RNG_REPLAY 1 /* validation: consume a recorded noise tensor [T][K][N][B]                 */
 
@@ -94,7 +96,8 @@ typedef struct ccvm_solve_desc {
   uint64_t offset;     /* PHILOX stream offset (advance by >= 1 between calls)                */
   int64_t traj_base;   /* global index of this call's trajectory 0 (batch sharding across GPUs:
                           noise depends on the GLOBAL trajectory index, so results do not
-                          depend on how the batch was split)                                 */
+                          depend on how the batch was split).  Must be EVEN in PHILOX mode:
+                          noise streams belong to trajectory pairs (2p, 2p+1)               */
   /* outputs, device [batch*n] each, row-major (B,N):
    *   DL:  out0 = c (clamped), out1 = s
    *   MF:  out0 = mu, out1 = mu_tilde (clamped last measurement), out2 = sigma

@@ -73,3 +73,14 @@ def test_reference_records_are_complete():
             assert all(len(r) == 8 for r in rows)
             fr = np.asarray(rows)[:, :7]
             assert (np.diff(fr, axis=1) >= 0).all() and fr.min() >= 0 and fr.max() <= 1   # nested thresholds
+
+
+def test_majority_gate_needs_more_than_half_of_the_seeds_per_criterion():
+    def run(rej, zok, bad):
+        return {"engine_vs_ref": {"reject_rate": rej, "pooled_ok": zok}, "max_reject": 0.07, "best_mismatch": bad,
+                "max_best_mismatch": 5}
+    good, bad_z, bad_best = run(0.03, True, 2), run(0.03, False, 2), run(0.03, True, 9)
+    assert G.majority_gate([good, good, bad_z]) and G.majority_gate([good])
+    assert not G.majority_gate([good, bad_z, bad_z]) and not G.majority_gate([bad_best])
+    assert G.majority_gate([good, bad_z, bad_best])          # each criterion fails under one seed only
+    assert not G.majority_gate([bad_z, bad_z, good, good])   # a tie is not a majority

@@ -16,20 +16,27 @@ REF = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "equivale
 SOLVERS = [s for s in G.ALL_LOOPS if f"{s}/seed0/70" in REF]
 
 
+ENGINE_SEEDS = (0, 1, 2)
+
+
 @pytest.mark.parametrize("route", ["many", "single"])
 @pytest.mark.parametrize("name", SOLVERS)
 def test_statistically_equivalent_on_bundled_instances(name, route):
     """All eight loops (the _solve_adam ones on the first 10 instances of every size, with the
     AdamParameters of the reference's examples), through batched launches (solve_many) AND through
-    one Solver.__call__ per instance (the single-launch kernel instantiations)."""
+    one Solver.__call__ per instance (the single-launch kernel instantiations).
+
+    Every criterion of the gate is a 95 % test, so a correct implementation fails a single-seed run of one
+    loop about 4 % of the time (measured: tools/equivalence_null.py, engine vs engine).  The test runs three
+    independent engine seeds and applies the criteria by majority (tools/equivalence_gpu.py::majority_gate)."""
     meta = REF["_meta"]
     if route == "single" and not name.endswith("_adam"):
-        pytest.skip("300 single calls per solver: run with tools/equivalence_gpu.py --route single")
-    rows = G.run_engine(name, meta["keys"][name], meta["post_processor"][name], seed=0, batch=meta["batch"],
-                        adam=meta.get("adam"), per_size=meta.get("adam_per_size"), route=route)
-    g = G.gate(REF, name, rows, meta["batch"])
-    e = g["engine_vs_ref"]
-    assert e["reject_rate"] <= g["max_reject"], (name, e["rejects"], e["cells"], g["max_reject"])
-    assert e["pooled_ok"], (name, e["pooled_worst_z"], e["pooled"])
-    assert g["best_mismatch"] <= g["max_best_mismatch"], (name, g["best_mismatch"], g["max_best_mismatch"])
-    assert g["pass"]
+        pytest.skip("300 single calls per solver and seed: run with tools/equivalence_gpu.py --route single")
+    runs = []
+    for seed in ENGINE_SEEDS:
+        rows = G.run_engine(name, meta["keys"][name], meta["post_processor"][name], seed=seed, batch=meta["batch"],
+                            adam=meta.get("adam"), per_size=meta.get("adam_per_size"), route=route)
+        runs.append(G.gate(REF, name, rows, meta["batch"]))
+    summary = [(round(r["engine_vs_ref"]["reject_rate"], 4), round(r["engine_vs_ref"]["pooled_worst_z"], 2),
+                r["best_mismatch"], r["max_best_mismatch"]) for r in runs]
+    assert G.majority_gate(runs), (name, route, "per seed (reject rate, pooled worst z, best mismatches, allowed)", summary)

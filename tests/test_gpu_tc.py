@@ -75,11 +75,15 @@ def test_tc_matches_simt_under_same_philox_stream(monkeypatch, solver, ver):
         sid, kw = nat.SOLVER_LANGEVIN, dict(s=0.5, dt=0.002, sigma=0.5, feedback_scale=1.0)
     else:
         sid, kw = nat.SOLVER_MF, dict(s=20.0, pump=0.0, dt=0.0025, j=5.0, feedback_scale=4000.0, g=0.01)
-    res = {}
-    for flag in ("0", ver):
-        monkeypatch.setenv("CCVM_TC", flag)
-        outs, _ = E.solve(sid, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, seed=9, offset=8, **kw)
-        res[flag] = [o.clone() for o in outs]
+    # the tensor-core path draws Philox in counter mode, the SIMT kernels draw per-thread streams: the
+    # SIMT side replays the normals the tensor-core run drew (ccvm_dump_noise under the same switch)
+    monkeypatch.setenv("CCVM_TC", ver)
+    outs, _ = E.solve(sid, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, seed=9, offset=8, **kw)
+    res = {ver: [o.clone() for o in outs]}
+    noise = E.dump_noise(sid, n, b, t, 9, 8)
+    monkeypatch.setenv("CCVM_TC", "0")
+    outs, _ = E.solve(sid, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, noise=noise, **kw)
+    res["0"] = [o.clone() for o in outs]
     for a, c in zip(res["0"], res[ver]):
         assert torch.isfinite(c).all()
         scale = a.abs().max().item()
@@ -111,7 +115,8 @@ def test_tc_nan_for_nan(monkeypatch, ver):
     q, v, _ = instance(n, 1, 0.2)
     outs, _ = E.solve(nat.SOLVER_DL, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, s=1.0, pump=2.0, dt=0.005,
                       noise_ratio=10.0, feedback_scale=100.0, g=0.05, seed=1, offset=0)
+    noise = E.dump_noise(nat.SOLVER_DL, n, b, t, 1, 0)    # the normals the tensor-core run drew
     monkeypatch.setenv("CCVM_TC", "0")
     ref, _ = E.solve(nat.SOLVER_DL, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, s=1.0, pump=2.0, dt=0.005,
-                     noise_ratio=10.0, feedback_scale=100.0, g=0.05, seed=1, offset=0)
+                     noise_ratio=10.0, feedback_scale=100.0, g=0.05, noise=noise)
     assert torch.equal(torch.isnan(outs[0]).any(dim=1), torch.isnan(ref[0]).any(dim=1))

@@ -20,6 +20,11 @@ def test_shard_bounds_cover_everything():
             for (s0, c0), (s1, _) in zip(spans, spans[1:]):
                 assert s0 + c0 == s1
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+            even = [P.shard_bounds(total, world, r, align=2) for r in range(world)]
+            assert even[0][0] == 0 and sum(c for _, c in even) == total and all(s % 2 == 0 for s, c in even if c)
+            for (s0, c0), (s1, _) in zip(even, even[1:]):
+                assert s0 + c0 == s1
+            assert max(c for _, c in even) - min(c for _, c in even) < 4   # one unit of 2, minus a ragged tail
     assert [P.instance_owner(k, 4) for k in range(6)] == [0, 1, 2, 3, 0, 1]
 
 

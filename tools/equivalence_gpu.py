@@ -19,6 +19,15 @@ Gate (per solver):
     vertices); the engine is compared with each reference seed and the closer one counts.
 With two reference seeds on record the reference side is their union (2 x B trajectories); seed 0
 vs seed 1 goes through the same tests: that is the calibration.
+
+How often does a CORRECT implementation fail this gate?  The pooled criterion is a 95 % test per loop:
+tools/equivalence_null.py measures the statistic between independent runs of the engine itself (12 seeds,
+same design) and finds worst |z| > 3.24 in 2 of 48 cases (4 %) -- and the same frequency for engine vs
+reference (profiles/r2_equivalence_null.json).  A single-seed run of all eight loops therefore fails
+somewhere about one time in three by chance alone.  `--seeds a,b,c` runs independent engine seeds and
+applies every criterion by MAJORITY (a loop passes when it passes under more than half of the seeds):
+a chance failure rate of ~0.7 % per loop with three seeds, while a real bias -- which shows under every
+seed -- is still caught.  tools/noise_bias.py isolates the generator from the arithmetic.
 """
 import argparse
 import json
@@ -159,9 +168,19 @@ def gate(ref, name, engine_rows, batch):
     return out
 
 
+def majority_gate(runs):
+    """A loop passes when EACH criterion holds under more than half of the independent engine seeds."""
+    need = len(runs) // 2 + 1
+    crit = [sum(r["engine_vs_ref"]["reject_rate"] <= r["max_reject"] for r in runs),
+            sum(bool(r["engine_vs_ref"]["pooled_ok"]) for r in runs),
+            sum(r["best_mismatch"] <= r["max_best_mismatch"] for r in runs)]
+    return all(c >= need for c in crit)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--seeds", default="", help="comma list of engine seeds: majority gate over independent runs")
     ap.add_argument("--solvers", default=",".join(ALL_LOOPS))
     ap.add_argument("--route", default="many", choices=["many", "single"])
     ap.add_argument("--out", default="")
@@ -171,20 +190,29 @@ def main():
     report = {"batch": meta["batch"], "iterations": meta["iterations"], "engine_seed": args.seed, "route": args.route,
               "z_pooled_max": Z_BONF42,
               "reference": {"torch": meta["torch"], "device": meta["device"]}}
+    seeds = [int(x) for x in args.seeds.split(",")] if args.seeds else [args.seed]
+    report["engine_seeds"] = seeds
     ok = True
     for name in args.solvers.split(","):
         if f"{name}/seed0/{SIZES[-1]}" not in ref:
             print(f"{name}: no reference record, skipped")
             continue
-        rows = run_engine(name, meta["keys"][name], meta["post_processor"][name], args.seed, meta["batch"],
-                          adam=meta.get("adam"), per_size=meta.get("adam_per_size"), route=args.route)
-        g = gate(ref, name, rows, meta["batch"])
-        report[name] = g
-        e, c = g["engine_vs_ref"], g.get("ref_seed0_vs_seed1")
-        print(f"{name}: pass={g['pass']} cell rejections {e['rejects']}/{e['cells']} ({100 * e['reject_rate']:.2f} %)"
-              f" pooled worst z {e['pooled_worst_z']:.2f}; best mismatches {g['best_mismatch']} (allowed {g['max_best_mismatch']})"
-              + (f" | reference seed0 vs seed1: {100 * c['reject_rate']:.2f} %, worst z {c['pooled_worst_z']:.2f}" if c else ""))
-        ok = ok and g["pass"]
+        runs = []
+        for seed in seeds:
+            rows = run_engine(name, meta["keys"][name], meta["post_processor"][name], seed, meta["batch"],
+                              adam=meta.get("adam"), per_size=meta.get("adam_per_size"), route=args.route)
+            g = gate(ref, name, rows, meta["batch"])
+            g["engine_seed"] = seed
+            runs.append(g)
+            e, c = g["engine_vs_ref"], g.get("ref_seed0_vs_seed1")
+            print(f"{name} seed {seed}: pass={g['pass']} cell rejections {e['rejects']}/{e['cells']} ({100 * e['reject_rate']:.2f} %)"
+                  f" pooled worst z {e['pooled_worst_z']:.2f}; best mismatches {g['best_mismatch']} (allowed {g['max_best_mismatch']})"
+                  + (f" | reference seed0 vs seed1: {100 * c['reject_rate']:.2f} %, worst z {c['pooled_worst_z']:.2f}" if c else ""))
+        verdict = majority_gate(runs)
+        report[name] = {"pass": verdict, "runs": runs} if len(runs) > 1 else runs[0]
+        if len(runs) > 1:
+            print(f"{name}: majority over seeds {seeds}: pass={verdict}")
+        ok = ok and verdict
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         json.dump(report, open(args.out, "w"), indent=1)
