@@ -327,7 +327,7 @@ def gpu_eager_record(q, v, sb):
                                None, None, dict(HP))
         x = sol.change_variables(c, 0.0, 1.0, s_val)
         with contextlib.redirect_stderr(io.StringIO()):
-            pv = PostProcessorAdam().postprocess(x, q, v)
+            pv = PostProcessorAdam().postprocess(x, q, v, device="cuda")
         e = 0.5 * torch.einsum("bi, ij, bj -> b", pv, q, pv) * sb + torch.einsum("bi, i -> b", pv, v) * sb
         return float((-e).max())
 

@@ -35,6 +35,16 @@
 #include "epilogue.cuh"
 #include "sde_launch.h"
 
+// Per-tile code-shape choices made by measurement (bit = 2 * solver + adam; solvers DL, MF, LV, PLV):
+//   CCVM_HOIST_MASK  tiles whose drift-independent update math is evaluated inside the contraction
+//   CCVM_UNPIN_MASK  tiles whose noise quanta are left unpinned in the compile-time variants at CG = 15, 18
+#ifndef CCVM_HOIST_MASK
+#define CCVM_HOIST_MASK 0xA3
+#endif
+#ifndef CCVM_UNPIN_MASK
+#define CCVM_UNPIN_MASK 0xF3
+#endif
+
 namespace ccvm {
 
 constexpr int HYB_TMEM_CHUNKS = 32;  // chunks of 4 rows held in TMEM (128 rows x 4 columns = 512 TMEM columns)
@@ -160,7 +170,8 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   // chosen by measurement at N = 70 / 128 / 250 -- DL 3.23 -> 3.15 ms, Langevin + Adam 2.12 -> 2.02,
   // PumpedLangevin + Adam 2.17 -> 2.10; neutral or slower for the others (ptxas gives up FFMA2
   // overlap elsewhere), which keep the whole step after the contraction.
-  constexpr bool HOIST = PIPE && ((SOLVER == SOLVER_DL && !ADAM) || ((SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV) && ADAM) || VSMEM);
+  constexpr int TILE_BIT = 1 << (SOLVER * 2 + (ADAM ? 1 : 0));
+  constexpr bool HOIST = PIPE && (((CCVM_HOIST_MASK & TILE_BIT) != 0 && !DL_ADAM) || (VSMEM && (CCVM_HOIST_MASK & TILE_BIT) != 0));
   // compile-time panel stride (0: run time)
   constexpr int XSC = !PIPE ? 0
                       : QSRC == QSRC_TMEM ? TMEM_PIPE_XS
@@ -479,7 +490,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       // The same holds, measured, for every larger compile-time variant (N = 40 ... 70: DL + Adam 3.57 ->
       // 3.39 ms at N = 70 and +12-15 % at N = 40 ... 60, Langevin +4-15 %, its Adam variant +6 %) except
       // MF at CG = 15, 18, which keeps one pinned quantum per chunk pair (MF + Adam loses 12 % unpinned).
-      constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV || SOLVER == SOLVER_DL);
+      constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || (CCVM_UNPIN_MASK & TILE_BIT) != 0);
       constexpr int NQ = SMALLCG ? 2 : 2 * KT;
       const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
       tmem_ld16(tlane, qa);

@@ -342,13 +342,21 @@ class CCVMSolver(ABC):
         files, examples/ccvm_boxqp_dl.py:27-52), except that ``solve_time`` / ``pp_time`` are the
         measured device times of the shared launches apportioned by each instance's share of the
         drift work (batch x iterations x N^2) -- a batch-1000 solve fills a fraction of the GPU, so
-        concurrent instances are how the machine is kept busy."""
+        concurrent instances are how the machine is kept busy.
+
+        ``launch_many`` / ``collect_many`` are the two halves: a sweep launches chunk k+1 before it
+        collects chunk k, so that planning and result handling on the host overlap the kernels."""
+        return self.collect_many(self.launch_many(instances, post_processor, algorithm_parameters, **call_kwargs))
+
+    def launch_many(self, instances, post_processor=None, algorithm_parameters=None, **call_kwargs):
+        """Plan and enqueue one chunk (kernels + the asynchronous read-back of its result blocks into
+        pinned memory); returns a handle for ``collect_many``.  Does not synchronise."""
         if self.device != "cuda":
             raise engine.nat.NativeError(
                 "ccvm_b200 solves on CUDA only (device='cuda'); there is no CPU implementation.")
         instances = list(instances)
         if not instances:
-            return []
+            return None
         if call_kwargs.get("evolution_step_size"):
             raise ValueError("solve_many does not support evolution sampling.")
         self._deferred = []
@@ -374,8 +382,19 @@ class CCVMSolver(ABC):
             raw = engine.solve_batch_fused(plans, [p.epilogue for p in pending],
                                            [_as_float(p.instance.optimal_sol) for p in pending])
         ev[1].record(stream)
-        stats = engine.decode_fused_results(raw.cpu())   # ONE device->host copy for the whole chunk
-        ev[1].synchronize()
+        host = torch.empty(raw.shape, dtype=torch.uint8).pin_memory()
+        host.copy_(raw, non_blocking=True)           # ONE device->host copy for the whole chunk
+        done = torch.cuda.Event()
+        done.record(stream)
+        return (pending, plans, ev, host, done, raw, bool(post_processor))
+
+    def collect_many(self, handle):
+        """Wait for a chunk launched by ``launch_many`` and build its ``Solution`` objects."""
+        if handle is None:
+            return []
+        pending, plans, ev, host, done, _raw, has_pp = handle
+        done.synchronize()
+        stats = engine.decode_fused_results(host)
         t_total = ev[0].elapsed_time(ev[1]) * 1e-3
         work = [p.batch_size * p.iterations * p.instance.problem_size ** 2 for p in pending]
         total = float(sum(work)) or 1.0
@@ -386,7 +405,7 @@ class CCVMSolver(ABC):
             loop_share = r["loop_ns"] / device_ns if device_ns else 1.0
             t_inst = t_total * work[i] / total
             out.append(p.make_solution(p.epilogue.pv, p.epilogue.energy, t_inst * loop_share / p.batch_size,
-                                       (t_inst * (1.0 - loop_share) / p.batch_size) if post_processor else 0.0,
+                                       (t_inst * (1.0 - loop_share) / p.batch_size) if has_pp else 0.0,
                                        (r["best"], r["arg_best"], r["counts"])))
         return out
 

@@ -85,11 +85,25 @@ def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=No
                 if streams:
                     solver.noise_streams = streams([k])
                 record(k, solver(instance=getter(k), post_processor=post_processor, **call_kwargs))
-        else:
+        elif hasattr(solver, "launch_many"):
+            # software pipeline over chunks: chunk c+1 is built, planned and enqueued while chunk c runs;
+            # its results are collected (one event wait, no device-wide synchronisation) afterwards
+            in_flight = None
             for lo in range(0, len(mine), chunk):
                 ks = mine[lo:lo + chunk]
                 if streams:
                     solver.noise_streams = streams(ks)
+                handle = solver.launch_many([getter(k) for k in ks], post_processor=post_processor, **call_kwargs)
+                if in_flight is not None:
+                    for k, sol in zip(in_flight[0], solver.collect_many(in_flight[1])):
+                        record(k, sol)
+                in_flight = (ks, handle)
+            if in_flight is not None:
+                for k, sol in zip(in_flight[0], solver.collect_many(in_flight[1])):
+                    record(k, sol)
+        else:
+            for lo in range(0, len(mine), chunk):
+                ks = mine[lo:lo + chunk]
                 sols = solver.solve_many([getter(k) for k in ks], post_processor=post_processor, **call_kwargs)
                 for k, sol in zip(ks, sols):
                     record(k, sol)
