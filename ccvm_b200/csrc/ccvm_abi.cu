@@ -972,21 +972,12 @@ __global__ void dump_noise_stream_kernel(uint32_t k0, uint32_t k1, uint32_t off_
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= pairs * cg_count) return;
   const int pr = idx % pairs, cg = idx / pairs;   // neighbouring threads: neighbouring trajectories (coalesced stores)
-#if CCVM_STREAM_PER_TRAJ
-  NoiseStream rs2[2] = {stream_init(k0, k1, off_lo, (unsigned long long)(traj_base + 2 * (long long)pr), (uint32_t)cg),
-                        stream_init(k0, k1, off_lo, (unsigned long long)(traj_base + 2 * (long long)pr + 1), (uint32_t)cg)};
-#else
   NoiseStream rs = stream_init(k0, k1, off_lo, (unsigned long long)(traj_base + 2 * (long long)pr) >> 1, (uint32_t)cg);
-#endif
   for (int t = 0; t < iterations; ++t)
     for (int q = 0; q < K; ++q)
       for (int i = 0; i < 2; ++i) {
         float w[4];
-#if CCVM_STREAM_PER_TRAJ
-        stream_normals4(rs2[i], w[0], w[1], w[2], w[3]);
-#else
         stream_normals4(rs, w[0], w[1], w[2], w[3]);
-#endif
         const int b = 2 * pr + i;
         if (b >= batch) continue;
 #pragma unroll

@@ -129,11 +129,9 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 #ifndef CCVM_SIMT_RNG
 #define CCVM_SIMT_RNG 1
 #endif
-// stream mode, experiment switch: 1 = one stream per TRAJECTORY and column group (two independent
-// chains per thread, 8 state registers), 0 = one per trajectory PAIR (4 registers, traj_base even)
-#ifndef CCVM_STREAM_PER_TRAJ
-#define CCVM_STREAM_PER_TRAJ 0
-#endif
+// (One stream per TRAJECTORY -- two independent chains per thread, 8 state registers, no alignment
+// rule for traj_base -- was measured and dropped: no gain at N = 70, DL + Adam 5 % slower,
+// profiles/r2b_quick_bench_n70_per_trajectory_streams.jsonl.)
 constexpr uint32_t NOISE_DOMAIN = 0xCC5DE200u;  // keeps solver streams apart from torch's own Philox use of the same seed
 
 __device__ __forceinline__ void noise_normals4(uint32_t k0, uint32_t k1, uint32_t off_lo, unsigned long long gb,

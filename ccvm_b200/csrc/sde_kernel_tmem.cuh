@@ -35,14 +35,16 @@
 #include "epilogue.cuh"
 #include "sde_launch.h"
 
-// Per-tile code-shape choices made by measurement (bit = 2 * solver + adam; solvers DL, MF, LV, PLV):
+// Per-tile code-shape choices made by measurement (bit = 2 * solver + adam; solvers DL, MF, LV, PLV;
+// profiles/r2f_tuning_masks_n70.txt):
 //   CCVM_HOIST_MASK  tiles whose drift-independent update math is evaluated inside the contraction
 //   CCVM_UNPIN_MASK  tiles whose noise quanta are left unpinned in the compile-time variants at CG = 15, 18
+//                    (all but PumpedLangevin + Adam: pinned 0.45 vs unpinned 0.40 of FP32 peak at N = 70)
 #ifndef CCVM_HOIST_MASK
 #define CCVM_HOIST_MASK 0xA3
 #endif
 #ifndef CCVM_UNPIN_MASK
-#define CCVM_UNPIN_MASK 0xF3
+#define CCVM_UNPIN_MASK 0x7F
 #endif
 
 namespace ccvm {
@@ -292,13 +294,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
 #if CCVM_SIMT_RNG
   // stream mode: one xoshiro128+ state per thread = per (global trajectory pair, column group); the
   // quanta of an iteration are drawn in the fixed order (quadrature, trajectory of the pair)
-#if CCVM_STREAM_PER_TRAJ
-  NoiseStream rs2[2] = {stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + gb0), (uint32_t)cgc),
-                        stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + gb0 + 1), (uint32_t)cgc)};
-  NoiseStream& rs = rs2[0];
-#else
   NoiseStream rs = stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + gb0) >> 1, (uint32_t)cgc);
-#endif
 #endif
 
   // one noise quantum: the four columns of (quadrature q, trajectory i) at iteration t
@@ -306,11 +302,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     float n0, n1, n2, n3;
 #if CCVM_SIMT_RNG
     (void)t;
-#if CCVM_STREAM_PER_TRAJ
-    stream_normals4(rs2[i], n0, n1, n2, n3);
-#else
     stream_normals4(rs, n0, n1, n2, n3);
-#endif
 #else
     const unsigned long long gb = (unsigned long long)(p.traj_base + gb0 + i);
     const uint32_t qi = (uint32_t)(q + half);  // which quadrature's stream
@@ -520,9 +512,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         contract(qb, xb);
         xp += (8 / KP) * ROWB;
         if constexpr (!SMALLCG) {
-#if CCVM_SIMT_RNG && CCVM_STREAM_PER_TRAJ
-          rs2[u & 1].s0 ^= pin;
-#elif CCVM_SIMT_RNG
+#if CCVM_SIMT_RNG
           rs.s0 ^= pin;  // (0) the formal dependence that pins this quantum to this pair of chunks
 #endif
           if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
@@ -706,9 +696,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
           wait_chunk();
           load_chunk(2 * u + 2, qa);
           contract4(qb);
-#if CCVM_SIMT_RNG && CCVM_STREAM_PER_TRAJ
-          rs2[u & 1].s0 ^= pin;
-#elif CCVM_SIMT_RNG
+#if CCVM_SIMT_RNG
           rs.s0 ^= pin;
 #endif
           if constexpr (SOLVER == SOLVER_MF) quantum(Wn, u >> 1, u & 1, tn ^ (int)pin);
