@@ -242,7 +242,7 @@ def sweep_record(rank, world, dev):
                             for n in SWEEP_SIZES}
     draw = np.random.RandomState(0).choice(len(SWEEP_SIZES), SWEEP_COUNT)
     specs = [(SWEEP_SIZES[int(i)], k) for k, i in enumerate(draw)]
-    costs = [n * n for n, _ in specs]
+    costs = [n * n + 1000 for n, _ in specs]   # measured: solve time ~ a + b n^2 with a / b ~ 1000 (profiles/r2g_quick_bench_sizes_20_250.jsonl)
 
     def get(i):
         n, k = specs[i]
@@ -252,6 +252,7 @@ def sweep_record(rank, world, dev):
     warm = [sweep.synthetic_instance(n, 10_000 + n, solver._scaling_multiplier, on_device=True) for n in SWEEP_SIZES]
     solver.solve_many(warm, post_processor="grad-descent")
     torch.cuda.synchronize(dev)
+    solver.host_seconds = {"launch": 0.0, "collect": 0.0}
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -268,6 +269,7 @@ def sweep_record(rank, world, dev):
             "chunk": SWEEP_CHUNK, "wall_s": wall, "traj_steps_per_s": steps / wall,
             "drift_tflops": sum(2.0 * n * n for n, _ in specs) * SWEEP_BATCH * SWEEP_ITERS / wall / 1e12,
             "ms_per_instance": wall / SWEEP_COUNT * 1e3,
+            "host_seconds_rank0": {k: round(v, 4) for k, v in solver.host_seconds.items()},
             "finite": bool(all(np.isfinite(r["best_objective_value"]) for r in md))}
 
 

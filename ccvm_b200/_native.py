@@ -62,7 +62,7 @@ class EpilogueDesc(C.Structure):
         ("apply_map2", C.c_int32), ("map2_scale", C.c_double), ("map2_shift", C.c_double),
         ("map2_scale_vec", _fp),
         ("scaled_by", C.c_double),
-        ("problem_variables", _fp), ("energy", _fp),
+        ("problem_variables", _fp), ("energy", _fp), ("scaled_by_dev", _fp),
     ]
 
 

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/ccvm_b200.h"
@@ -524,6 +525,7 @@ static int epi_params_from_desc(const ccvm_epilogue_desc* d, EpiParams& p) {
   p.lo = (float)d->pp_lower;
   p.hi = (float)d->pp_upper;
   p.scaled_by = (float)d->scaled_by;
+  p.scaled_by_ptr = d->scaled_by_dev;
   return CCVM_OK;
 }
 
@@ -778,6 +780,23 @@ extern "C" int ccvm_solve_fused(const ccvm_solve_desc* d, const ccvm_epilogue_de
 }
 
 // ------------------------------------------------------------------ batched instances
+// side streams of the library (per device, created once): the buckets of a batched launch run concurrently
+struct SideStreams {
+  static constexpr int N = 8;
+  cudaStream_t s[N];
+  bool ok = false;
+};
+static int side_streams(int device, SideStreams*& out) {
+  static SideStreams pools[64];
+  SideStreams& p = pools[device];
+  if (!p.ok) {
+    for (int i = 0; i < SideStreams::N; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking));
+    p.ok = true;
+  }
+  out = &p;
+  return CCVM_OK;
+}
+
 struct SchedJob {
   SchedArgs a;
   long long offset;  // first row of this problem in the shared schedule table
@@ -876,6 +895,10 @@ static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_de
     for (int c = 0; c < plans[b].ctas; ++c) B.map.push_back(make_int2((int)b, c));
     if (smem > B.smem) B.smem = smem;
   }
+  // largest buckets first: the long kernels start early, the small ones fill the gaps
+  std::sort(buckets.begin(), buckets.end(), [](const Bucket& a, const Bucket& b) {
+    return (size_t)a.threads * a.map.size() > (size_t)b.threads * b.map.size();
+  });
   size_t total_ctas = 0;
   for (const Bucket& B : buckets) total_ctas += B.map.size();
   CUDA_TRY(items_buf.alloc(items.size() * sizeof(BatchItem)));
@@ -890,8 +913,21 @@ static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_de
     CUDA_TRY(cudaMemcpyAsync(d_map, all.data(), total_ctas * sizeof(int2), cudaMemcpyHostToDevice, st));
     // `all` is pageable host memory: the copy is staged before cudaMemcpyAsync returns
   }
-  size_t off = 0;
+  // The buckets of a chunk are independent kernels of very different sizes (a bucket may hold a single
+  // small instance: a dozen CTAs): on ONE stream they would run one after the other and leave most SMs idle.
+  // They are forked onto side streams of the library (after an event that orders them behind the copies and
+  // the schedule kernel above) and joined back into the caller's stream.
   const bool adam = alg == CCVM_ALG_ADAM;
+  const bool fork = buckets.size() > 1 && getenv("CCVM_NO_FORK") == nullptr;
+  SideStreams* side = nullptr;
+  cudaEvent_t ready = nullptr;
+  if (fork) {
+    if ((rc = side_streams(di.device, side))) return rc;
+    CUDA_TRY(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ready, st));
+  }
+  size_t off = 0;
+  int launched = 0;
   for (const Bucket& B : buckets) {
     BatchBucket bb;
     bb.items = d_items;
@@ -901,12 +937,31 @@ static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_de
     bb.qsrc = B.qsrc;
     bb.cgc = B.cgc;
     bb.smem = B.smem;
-#define LAUNCH_BATCH(S, A) rc = launch_tmem_batch<S, A>(bb, st)
+    cudaStream_t ls = st;
+    if (fork) {
+      ls = side->s[launched % SideStreams::N];
+      if (launched < SideStreams::N) cudaStreamWaitEvent(ls, ready, 0);  // later buckets follow on the same side stream
+    }
+#define LAUNCH_BATCH(S, A) rc = launch_tmem_batch<S, A>(bb, ls)
     CCVM_DISPATCH_TILE(solver, adam, LAUNCH_BATCH)
 #undef LAUNCH_BATCH
-    if (rc) return rc;
+    if (rc) break;
     off += B.map.size();
+    ++launched;
   }
+  if (fork) {
+    // join: the caller's stream continues (and the scratch is freed) only after every side stream is done
+    const int used = launched < SideStreams::N ? launched : SideStreams::N;
+    for (int i = 0; i < used; ++i) {
+      cudaEvent_t done;
+      if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess) continue;
+      cudaEventRecord(done, side->s[i]);
+      cudaStreamWaitEvent(st, done, 0);
+      cudaEventDestroy(done);   // released by the runtime once the wait has been satisfied
+    }
+    cudaEventDestroy(ready);
+  }
+  if (rc) return rc;
   if (epis && !fuse) {
     for (int i : batched) {
       ccvm_epilogue_desc ed = epis[i];

@@ -254,6 +254,7 @@ struct EpiParams {
   const float* state;
   const float* m1vec;
   const float* m2vec;
+  const float* scaled_by_ptr;  // optional device scalar overriding scaled_by (a scaling factor still on the device)
   float* pv;
   float* energy;
   int n, batch, ld, q_in_smem;

@@ -114,7 +114,10 @@ static __device__ __noinline__ void epilogue_warp_body(const EpiParams& p, float
         e1 += __shfl_xor_sync(0xffffffffu, e1, o);
         e2 += __shfl_xor_sync(0xffffffffu, e2, o);
       }
-      if (lane == 0) p.energy[b] = 0.5f * (e1 * p.scaled_by) + e2 * p.scaled_by;
+      if (lane == 0) {
+        const float sb = p.scaled_by_ptr ? *p.scaled_by_ptr : p.scaled_by;
+        p.energy[b] = 0.5f * (e1 * sb) + e2 * sb;
+      }
     }
     __syncwarp();
   }
@@ -264,7 +267,8 @@ static __device__ __noinline__ void epilogue_tile_body(const EpiParams& p, float
           s1 += rt[(m * EPT + lane) * 2];
           s2 += rt[(m * EPT + lane) * 2 + 1];
         }
-        p.energy[b0 + lane] = 0.5f * (s1 * p.scaled_by) + s2 * p.scaled_by;
+        const float sb = p.scaled_by_ptr ? *p.scaled_by_ptr : p.scaled_by;
+        p.energy[b0 + lane] = 0.5f * (s1 * sb) + s2 * sb;
       }
     }
     tile_sync();

@@ -172,6 +172,17 @@ def _vec_or_scalar(val, n, dev):
     return float(val), None
 
 
+def _set_scaled_by(desc, scaled_by, dev, keep):
+    """``instance.scaled_by`` as a host scalar, or -- when it is a one-element CUDA tensor (the product of
+    scaling factors reduced on the device) -- as a device pointer: no ``.item()`` synchronisation."""
+    if torch.is_tensor(scaled_by) and scaled_by.is_cuda and scaled_by.numel() == 1:
+        t = nat.as_f32(scaled_by, dev).reshape(1)
+        keep.append(t)
+        desc.scaled_by, desc.scaled_by_dev = 1.0, nat.ptr(t)
+    else:
+        desc.scaled_by = float(scaled_by.item()) if torch.is_tensor(scaled_by) else float(scaled_by)
+
+
 class PlannedEpilogue:
     """A filled ``ccvm_epilogue_desc`` with its output tensors (pv, energy)."""
 
@@ -203,7 +214,7 @@ def plan_epilogue(b, n, dev, *, map1=None, post_processor=None, pp_iterations=10
     if pp_step is None:
         pp_step = 0.1 if post_processor == "grad-descent" else 0.01
     d.pp_step, d.pp_lower, d.pp_upper = float(pp_step), float(pp_lower), float(pp_upper)
-    d.scaled_by = float(scaled_by)
+    _set_scaled_by(d, scaled_by, dev, keep)
     pv = torch.empty((b, n), dtype=torch.float32, device=dev) if want_pv else None
     en = energy_out if energy_out is not None else torch.empty((b,), dtype=torch.float32, device=dev)
     if en.numel() != b or en.dtype != torch.float32 or not en.is_contiguous() or en.device != dev:
@@ -280,7 +291,7 @@ def epilogue(state, q, v, *, map1=None, post_processor=None, pp_iterations=10, p
     if pp_step is None:
         pp_step = 0.1 if post_processor == "grad-descent" else 0.01
     d.pp_step, d.pp_lower, d.pp_upper = float(pp_step), float(pp_lower), float(pp_upper)
-    d.scaled_by = float(scaled_by)
+    _set_scaled_by(d, scaled_by, dev, keep)
     pv = torch.empty((b, n), dtype=torch.float32, device=dev) if want_pv else None
     en = None
     if want_energy:

@@ -83,6 +83,9 @@ class CCVMSolver(ABC):
         #: generator state: sweeps key every instance by its GLOBAL index, so results do not depend on
         #: how instances are dealt to ranks or chunks (and no two ranks ever draw the same stream)
         self.noise_streams = None
+        #: cumulative host seconds spent planning + enqueueing (launch_many) and building Solutions
+        #: (collect_many, after its event wait): what a sweep has to hide behind the kernels
+        self.host_seconds = {"launch": 0.0, "collect": 0.0}
 
     # ------------------------------------------------------------------ properties
     @property
@@ -285,7 +288,7 @@ class CCVMSolver(ABC):
         state, map1, map2, make_variables = finish(outs)
         epi = engine.plan_epilogue(batch_size, instance.problem_size, plan.device, map1=map1,
                                    post_processor=post_processor, pp_iterations=10, map2=map2,
-                                   scaled_by=_as_float(instance.scaled_by))
+                                   scaled_by=instance.scaled_by)   # stays on the device if it is there
 
         def make_solution(pv, objval, solve_time, pp_time, stats=None):
             return Solution(
@@ -354,6 +357,7 @@ class CCVMSolver(ABC):
         if self.device != "cuda":
             raise engine.nat.NativeError(
                 "ccvm_b200 solves on CUDA only (device='cuda'); there is no CPU implementation.")
+        t_host = time.perf_counter()
         instances = list(instances)
         if not instances:
             return None
@@ -386,6 +390,7 @@ class CCVMSolver(ABC):
         host.copy_(raw, non_blocking=True)           # ONE device->host copy for the whole chunk
         done = torch.cuda.Event()
         done.record(stream)
+        self.host_seconds["launch"] += time.perf_counter() - t_host
         return (pending, plans, ev, host, done, raw, bool(post_processor))
 
     def collect_many(self, handle):
@@ -394,6 +399,7 @@ class CCVMSolver(ABC):
             return []
         pending, plans, ev, host, done, _raw, has_pp = handle
         done.synchronize()
+        t_host = time.perf_counter()
         stats = engine.decode_fused_results(host)
         t_total = ev[0].elapsed_time(ev[1]) * 1e-3
         work = [p.batch_size * p.iterations * p.instance.problem_size ** 2 for p in pending]
@@ -407,6 +413,7 @@ class CCVMSolver(ABC):
             out.append(p.make_solution(p.epilogue.pv, p.epilogue.energy, t_inst * loop_share / p.batch_size,
                                        (t_inst * (1.0 - loop_share) / p.batch_size) if has_pp else 0.0,
                                        (r["best"], r["arg_best"], r["counts"])))
+        self.host_seconds["collect"] += time.perf_counter() - t_host
         return out
 
     # ----------------------------------------------------------- evolution sampling

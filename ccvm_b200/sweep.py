@@ -88,9 +88,17 @@ def solve_sweep(solver, instances, post_processor=None, rank=None, world_size=No
         elif hasattr(solver, "launch_many"):
             # software pipeline over chunks: chunk c+1 is built, planned and enqueued while chunk c runs;
             # its results are collected (one event wait, no device-wide synchronisation) afterwards
+            # the first chunks are small and double up to `chunk`: the GPU starts working after a handful of
+            # instances have been planned instead of after a whole chunk (what is not hidden behind kernels
+            # is what limits the strong scaling of a sweep over many GPUs)
             in_flight = None
-            for lo in range(0, len(mine), chunk):
-                ks = mine[lo:lo + chunk]
+            bounds, lo, size = [], 0, max(1, chunk // 8)
+            while lo < len(mine):
+                bounds.append((lo, min(lo + size, len(mine))))
+                lo += size
+                size = min(chunk, size * 2)
+            for lo, hi in bounds:
+                ks = mine[lo:hi]
                 if streams:
                     solver.noise_streams = streams(ks)
                 handle = solver.launch_many([getter(k) for k in ks], post_processor=post_processor, **call_kwargs)

@@ -172,6 +172,9 @@ typedef struct ccvm_epilogue_desc {
   double scaled_by;            /* instance.scaled_by                                   */
   float* problem_variables;    /* out, device [batch*n] (pv); may be NULL              */
   float* energy;               /* out, device [batch]; may be NULL                     */
+  const float* scaled_by_dev;  /* optional DEVICE scalar that overrides scaled_by: the factor written by
+                                  ccvm_scaling_factor can stay on the device (no host read-back, so a sweep
+                                  never synchronises while it plans the next chunk); NULL: use scaled_by */
 } ccvm_epilogue_desc;
 
 int ccvm_epilogue(const ccvm_epilogue_desc* desc, void* stream);
