@@ -186,8 +186,7 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   // fixed-stride panels of the K = 1 solvers in the hybrid kernel hold two k rows per panel row
   // (sde_kernel_tmem.cuh, KP)
   const bool cgc_variant = fixed_xs && path == PATH_TMEM && !cgc_off && (cg == 10 || cg == 13 || cg == 15 || cg == 18);
-  const bool kp2_tmem = CCVM_KP2_TMEM_MINCG > 0 && path == PATH_TMEM && cg >= CCVM_KP2_TMEM_MINCG && (cgc_variant || small_cgc);
-  const int kp = (fixed_xs && K == 1 && (path == PATH_HYB || kp2_tmem)) ? 2 : 1;
+  const int kp = (fixed_xs && K == 1 && path == PATH_HYB) ? 2 : 1;
   // DL + Adam parks its second moments in shared memory (sde_kernel_tmem.cuh, VSMEM): 64 B per thread
   const size_t vsm = (fixed_xs && path == PATH_TMEM && d.solver == CCVM_SOLVER_DL && d.algorithm == CCVM_ALG_ADAM)
                          ? (size_t)256 * 16 : 0;  // floats

@@ -40,18 +40,11 @@
 //   CCVM_HOIST_MASK  tiles whose drift-independent update math is evaluated inside the contraction
 //   CCVM_UNPIN_MASK  tiles whose noise quanta are left unpinned in the compile-time variants at CG = 15, 18
 //                    (all but PumpedLangevin + Adam: pinned 0.45 vs unpinned 0.40 of FP32 peak at N = 70)
+// Measured and dropped in round 2 (profiles/r2m_tuning_x32_kp2_padstage.txt): tcgen05.ld.x32 for the K = 1
+// tiles (half the LDTM / R2UR / wait instructions) and two k rows per panel row for n <= 128 (one LDS.128
+// per two k) -- within +-3 % either way, no consistent sign over the loops and sizes.
 #ifndef CCVM_HOIST_MASK
 #define CCVM_HOIST_MASK 0xA3
-#endif
-// K = 1 tiles of the TMEM kernel with a compile-time column-group count >= this pack two k rows per panel
-// row like the hybrid kernel does (one LDS.128 per two k instead of two LDS.64); 0: never
-#ifndef CCVM_KP2_TMEM_MINCG
-#define CCVM_KP2_TMEM_MINCG 0
-#endif
-// K = 1 tiles of the TMEM kernel with compile-time column groups and unpinned noise read their Q slice
-// with tcgen05.ld.x32 (8 k rows per load: half the LDTM / R2UR / wait instructions); 0: x16 everywhere
-#ifndef CCVM_TMEM_X32
-#define CCVM_TMEM_X32 0
 #endif
 #ifndef CCVM_UNPIN_MASK
 #define CCVM_UNPIN_MASK 0x7F
@@ -89,30 +82,6 @@ __device__ __forceinline__ void tmem_st4(uint32_t addr, float a, float b, float 
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t addr, float (&r)[16]) {
-  uint32_t u[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
-      : "r"(addr));
-#pragma unroll
-  for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
-}
-// 32 columns (8 k rows of a 4-column Q slice) in one instruction; `n16` = false loads only the first 16
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, float (&r)[32]) {
-  uint32_t u[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
-        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
-        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
-        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
-      : "r"(addr));
-#pragma unroll
-  for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
-}
-__device__ __forceinline__ void tmem_ld16_lo(uint32_t addr, float (&r)[32]) {
   uint32_t u[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -212,8 +181,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   constexpr int XSC = !PIPE ? 0
                       : QSRC == QSRC_TMEM ? TMEM_PIPE_XS
                       : QSRC == QSRC_HYB ? HYB_PIPE_XS : 0;
-  constexpr bool KP2_TMEM = CCVM_KP2_TMEM_MINCG > 0 && QSRC == QSRC_TMEM && CGC >= CCVM_KP2_TMEM_MINCG;
-  constexpr int KP = (XSC != 0 && KT == 1 && (QSRC == QSRC_HYB || KP2_TMEM)) ? 2 : 1;  // k rows per panel row (see HYB_PIPE_XS)
+  constexpr int KP = (XSC != 0 && KT == 1 && QSRC == QSRC_HYB) ? 2 : 1;  // k rows per panel row (see HYB_PIPE_XS)
   const int N = p.n, CG = CGC ? CGC : p.cg, NP = 4 * CG, RG = L.rg, XS = XSC ? XSC : L.xs, T = p.iterations;
   const int PR = NP / KP;                            // panel rows per buffer
   const bool idle = tid >= L.ng * L.gt;
@@ -344,7 +312,7 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
     noise_normals4(key.x, key.y, p.off_lo, gb, (uint32_t)t, (uint32_t)cgc, qi, n0, n1, n2, n3);
 #endif
     // Padding columns (j >= n) draw noise like any other -- masking it cost a SEL per normal; their
-    // state is never staged into the panel (see `stage`) and never written out.
+    // state stays finite (see `stage`) and is never written out.
     const float nn[4] = {n0, n1, n2, n3};
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -385,18 +353,17 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
 #pragma unroll
       for (int jp = 0; jp < 2; ++jp) {
         float* dst = X + ((size_t)buf * PR + (j0 >> 1) + jp) * XS + 4 * rg;
-        const bool ok0 = colok[2 * jp], ok1 = colok[2 * jp + 1];
-        *reinterpret_cast<float4*>(dst) = make_float4(ok0 ? a[2 * jp].x : 0.f, ok0 ? a[2 * jp].y : 0.f,
-                                                      ok1 ? a[2 * jp + 1].x : 0.f, ok1 ? a[2 * jp + 1].y : 0.f);
+        *reinterpret_cast<float4*>(dst) = make_float4(a[2 * jp].x, a[2 * jp].y, a[2 * jp + 1].x, a[2 * jp + 1].y);
       }
       return;
     }
-    // Padding columns (j >= n) are never staged: their panel rows keep the zeros of the prologue, so
-    // whatever the padded state does (it sees no drift and is never written out) it cannot reach a real
-    // column through the contraction -- not even as Inf * 0.
+    // Padding columns (j >= n) are staged like any other: their state only ever meets the zero rows of Qs.
+    // That needs it to stay FINITE (Inf * 0 would poison the pair): it sees no drift, only the solver's own
+    // saturating terms (DL, MF: the cubic -- a step size that blows it up blows up the real columns as well)
+    // or a zero clamp (Langevin, PumpedLangevin).  Staging it behind a predicate was measured: 1-5 % slower
+    // on every loop (profiles/r2m_tuning_x32_kp2_padstage.txt).
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      if (!colok[jj]) continue;
       float* dst = X + ((size_t)buf * NP + (j0 + jj)) * XS + xoff + RW * rg + 2 * half;
       if constexpr (K == 2 && !SPLIT) *reinterpret_cast<float4*>(dst) = make_float4(a[jj].x, a[jj].y, b[jj].x, b[jj].y);
       else *reinterpret_cast<float2*>(dst) = make_float2(a[jj].x, a[jj].y);
@@ -525,52 +492,6 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
       constexpr bool SMALLCG = CGC != 0 && (CGC <= 13 || (CCVM_UNPIN_MASK & TILE_BIT) != 0);
       constexpr int NQ = SMALLCG ? 2 : 2 * KT;
       const int tn = SOLVER == SOLVER_MF ? t + 1 : t;
-      constexpr bool X32 = CCVM_TMEM_X32 != 0 && SMALLCG && QSRC == QSRC_TMEM && KT == 1 && CGC >= 5;
-      if constexpr (X32) {
-        // eight k rows of the Q slice per tcgen05.ld (two ping-pong sets of 32 registers), state rows one
-        // chunk of four ahead as below; everything is unrolled at compile time
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if constexpr (SOLVER == SOLVER_MF) quantum(Wn, 0, i, tn);
-          else quantum(W, 0, i, tn);
-        }
-        constexpr int NPAIR = (CGC + 1) / 2;
-        float q0[32], q1[32];
-        auto ld_pair = [&](int pr, float (&dst)[32]) {
-          if (2 * pr + 1 < CGC) tmem_ld32(tlane + 32 * pr, dst);
-          else tmem_ld16_lo(tlane + 32 * pr, dst);
-        };
-        auto contract_h = [&](const float (&qq)[32], int off, const XV (&xx)[XR]) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            pf2 xv;
-            if constexpr (KP == 2) xv = (kk & 1) ? pk(xx[kk / 2].z, xx[kk / 2].w) : pk(xx[kk / 2].x, xx[kk / 2].y);
-            else xv = pk(xx[kk].x, xx[kk].y);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) acc[0][jj] = fma2(xv, dup(qq[off + 4 * kk + jj]), acc[0][jj]);
-          }
-        };
-        ld_pair(0, q0);
-        load_x(0, xa);
-#pragma unroll
-        for (int pr = 0; pr < NPAIR; ++pr) {
-          float(&cur)[32] = (pr & 1) ? q1 : q0;
-          float(&nxt)[32] = (pr & 1) ? q0 : q1;
-          const bool two = 2 * pr + 1 < CGC, more = pr + 1 < NPAIR;
-          tmem_wait_ld();
-          if (more) ld_pair(pr + 1, nxt);
-          if (two) load_x(4, xb);
-          contract_h(cur, 0, xa);
-          if (two) {
-            if (more) load_x(8, xa);
-            contract_h(cur, 16, xb);
-          }
-          xp += (8 / KP) * ROWB;
-          if (pr == 1) {
-            if constexpr (HOIST) precompute();
-          }
-        }
-      } else {
       tmem_ld16(tlane, qa);
       load_x(0, xa);
       int kc = 0;
@@ -707,7 +628,6 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         }
         }
       }
-      }  // !X32
     } else {
       // four k's against one 16-column TMEM chunk; two chunk buffers ping-pong so that the next
       // tcgen05.ld is in flight while the current chunk is consumed (no register copies)
