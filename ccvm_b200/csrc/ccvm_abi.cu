@@ -301,6 +301,22 @@ static void plan_tc(const ccvm_solve_desc& d, TcPlan& P) {
   const bool adam = d.algorithm == CCVM_ALG_ADAM;
   P.n_aux = (d.solver == CCVM_SOLVER_MF ? 2 : 0) + (adam ? 2 : 0);
   P.ctas = P.rows_p / TC_BM;
+  // Few row blocks (Langevin-type loops have one row per trajectory: 64 CTAs at B = 8192): two or four CTA pairs
+  // share a block of 256 rows and split its output chunks, exchanging the new state through L2 with per-chunk
+  // flags.  They wait for each other, so every CTA must be resident: col_split x ctas <= the SM count.
+  P.col_split = 1;
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int nc = P.np / TC_BN;
+    if (P.version == 2 && getenv("CCVM_TC_NO_SPLIT") == nullptr)
+      for (int cs = 4; cs >= 2; cs >>= 1)
+        if (nc % cs == 0 && cs * P.ctas <= sms) {
+          P.col_split = cs;
+          break;
+        }
+  }
+  P.ctas *= P.col_split;
   P.smem = P.version == 2 ? (size_t)T2_SMEM_BYTES
                           : 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)2 * P.np * sizeof(float);
 }
@@ -310,11 +326,15 @@ static int solve_tc(const ccvm_solve_desc* d, SdeParams& p, cudaStream_t st) {
   TcPlan P;
   plan_tc(*d, P);
   const size_t plane = (size_t)P.rows_p * P.np;
-  const size_t floats = 4 * plane + (size_t)P.n_aux * plane + 2 * (size_t)P.np * P.np + 2 * (size_t)P.np;
+  const size_t n_flags = (size_t)(P.rows_p / TC_BM) * (P.np / TC_BN);
+  const size_t floats = 4 * plane + (size_t)P.n_aux * plane + 2 * (size_t)P.np * P.np + 2 * (size_t)P.np + n_flags;
   StreamBuf scratch_buf(st);
   CUDA_TRY(scratch_buf.alloc(floats * sizeof(float)));
   float* scratch = scratch_buf.as<float>();
   TcParams tc;
+  tc.col_split = P.col_split;
+  tc.chunk_flags = reinterpret_cast<unsigned int*>(scratch + floats - n_flags);
+  CUDA_TRY(cudaMemsetAsync(tc.chunk_flags, 0, n_flags * sizeof(unsigned int), st));
   tc.xh = scratch;
   tc.xl = tc.xh + 2 * plane;
   tc.aux = tc.xl + 2 * plane;
@@ -471,7 +491,7 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
     plan_tc(*d, P);
     info5[0] = TC_THREADS;
     info5[1] = P.ctas;
-    info5[2] = TC_BM / (d->solver == CCVM_SOLVER_DL ? 2 : 1);
+    info5[2] = TC_BM / (d->solver == CCVM_SOLVER_DL ? 2 : 1) / P.col_split;
     info5[3] = (int)P.smem;
 #define REGS_TC(S, A) regs = regs_tc<S, A>(P.version)
     CCVM_DISPATCH_TILE(d->solver, adam, REGS_TC)

@@ -17,6 +17,7 @@ namespace ccvm {
 
 constexpr int EPI_WARPS = 8;  // warps per CTA of the stand-alone epilogue kernels
 constexpr int EPT = 8;        // trajectories per tile of the tiled body
+constexpr int EPW = 4;        // trajectories a warp of the per-warp body walks at once (one LDS.128 per row)
 
 // shared-memory floats the two bodies need for `nwarps` warps (Q staged on chip or not)
 __host__ __device__ inline size_t epi_tile_floats(int n, int nwarps, int wpt, bool q_in_smem) {
@@ -24,7 +25,7 @@ __host__ __device__ inline size_t epi_tile_floats(int n, int nwarps, int wpt, bo
   return (q_in_smem ? (((size_t)n * n + 3) & ~(size_t)3) : 0) + (size_t)tpc * 2 * n * EPT + (size_t)tpc * wpt * 4 * EPT * 2;
 }
 __host__ __device__ inline size_t epi_warp_floats(int n, int nwarps, bool q_in_smem) {
-  return (q_in_smem ? (size_t)n * (n | 1) : 0) + (size_t)nwarps * 2 * n;
+  return (q_in_smem ? (((size_t)n * (n | 1) + 3) & ~(size_t)3) : 0) + (size_t)nwarps * 2 * n * EPW;
 }
 
 // ------------------------------------------------------------------------- warp per trajectory
@@ -38,36 +39,56 @@ static __device__ __noinline__ void epilogue_warp_body(const EpiParams& p, float
   const int N = p.n, LD = p.ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   float* qs = esm;
-  float* xbuf = esm + (p.q_in_smem ? (size_t)N * LD : 0) + (size_t)warp * 2 * N;
+  float* xbuf = esm + (p.q_in_smem ? (((size_t)N * LD + 3) & ~(size_t)3) : 0) + (size_t)warp * 2 * N * EPW;  // 16-byte aligned
   const float* Q = p.q;
   int ld = N;
   if (p.q_in_smem) {
-    for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
-      const int i = idx / N, j = idx - i * N;
-      qs[i * LD + j] = p.q[idx];
-    }
+    for (int i = warp; i < N; i += nwarps)
+      for (int j = lane; j < N; j += 32) qs[i * LD + j] = p.q[(size_t)i * N + j];
     Q = qs;
     ld = LD;
   }
   __syncthreads();
 
-  for (long long b = b_begin + (long long)cta_slot * nwarps + warp; b < b_end; b += (long long)n_slots * nwarps) {
+  // a warp walks EPW trajectories AT ONCE (element [j][u] of the working vectors belongs to trajectory u): every
+  // Q element it loads serves all of them and the EPW dot products are independent FMA chains -- the
+  // one-trajectory-at-a-time version was latency-bound (36 us of tail behind a 3.2 ms loop at N = 70).  Each
+  // trajectory still sees exactly the arithmetic below in exactly this order.
+  const long long wslot = (long long)cta_slot * nwarps + warp, nslot = (long long)n_slots * nwarps;
+  for (long long b0 = b_begin + wslot * EPW; b0 < b_end; b0 += nslot * EPW) {
     float* x = xbuf;
-    float* y = xbuf + N;
+    float* y = xbuf + (size_t)N * EPW;
+    bool ok[EPW];
+#pragma unroll
+    for (int u = 0; u < EPW; ++u) ok[u] = b0 + u < b_end;
     for (int j = lane; j < N; j += 32) {
-      float val = p.state[(size_t)b * N + j];
-      if (p.map1) val = val * (p.m1vec ? p.m1vec[j] : p.m1s) + p.m1o;
-      x[j] = val;
+#pragma unroll
+      for (int u = 0; u < EPW; ++u) {
+        float val = ok[u] ? p.state[(size_t)(b0 + u) * N + j] : 0.f;
+        if (p.map1) val = val * (p.m1vec ? p.m1vec[j] : p.m1s) + p.m1o;
+        x[j * EPW + u] = val;
+      }
     }
     __syncwarp();
     if (p.pp == CCVM_PP_GRAD_DESCENT) {
       // x <- clamp(x - step (xQ + V), lo, hi), all variables from the OLD x (grad_descent.py:61-64)
       for (int it = 0; it < p.pp_iters; ++it) {
         for (int j = lane; j < N; j += 32) {
-          float acc = 0.f;
-          for (int i = 0; i < N; ++i) acc = fmaf(x[i], Q[i * ld + j], acc);
-          const float g = acc + p.v[j];
-          y[j] = clampf(x[j] + (-p.step) * g, p.lo, p.hi);
+          float acc[EPW];
+#pragma unroll
+          for (int u = 0; u < EPW; ++u) acc[u] = 0.f;
+          for (int i = 0; i < N; ++i) {
+            const float q = Q[i * ld + j];
+            const float4 x4 = *reinterpret_cast<const float4*>(x + i * EPW);
+            const float xi[EPW] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int u = 0; u < EPW; ++u) acc[u] = fmaf(xi[u], q, acc[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < EPW; ++u) {
+            const float g = acc[u] + p.v[j];
+            y[j * EPW + u] = clampf(x[j * EPW + u] + (-p.step) * g, p.lo, p.hi);
+          }
         }
         __syncwarp();
         float* tmp = x;
@@ -78,15 +99,26 @@ static __device__ __noinline__ void epilogue_warp_body(const EpiParams& p, float
       // one torch.optim.Adam step on 1/2 xQx + Vx then clamp (adam.py:58-66):
       // g = 1/2 (xQ + x Q^T) + V ; x <- clamp(x - lr * (m/(1-b1)) / (sqrt(v/(1-b2)) + eps))
       for (int j = lane; j < N; j += 32) {
-        float a1 = 0.f, a2 = 0.f;
+        float a1[EPW], a2[EPW];
+#pragma unroll
+        for (int u = 0; u < EPW; ++u) a1[u] = a2[u] = 0.f;
         for (int i = 0; i < N; ++i) {
-          a1 = fmaf(x[i], Q[i * ld + j], a1);
-          a2 = fmaf(x[i], Q[j * ld + i], a2);
+          const float qc = Q[i * ld + j], qr = Q[j * ld + i];
+          const float4 x4 = *reinterpret_cast<const float4*>(x + i * EPW);
+          const float xi[EPW] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int u = 0; u < EPW; ++u) {
+            a1[u] = fmaf(xi[u], qc, a1[u]);
+            a2[u] = fmaf(xi[u], qr, a2[u]);
+          }
         }
-        const float g = 0.5f * (a1 + a2) + p.v[j];
-        const float m = (1.f - 0.9f) * g, vv = (1.f - 0.99f) * g * g;
-        const float den = sqrtf(vv) / sqrtf(1.f - 0.99f) + 1e-8f;
-        y[j] = clampf(x[j] - (p.step / (1.f - 0.9f)) * (m / den), p.lo, p.hi);
+#pragma unroll
+        for (int u = 0; u < EPW; ++u) {
+          const float g = 0.5f * (a1[u] + a2[u]) + p.v[j];
+          const float m = (1.f - 0.9f) * g, vv = (1.f - 0.99f) * g * g;
+          const float den = sqrtf(vv) / sqrtf(1.f - 0.99f) + 1e-8f;
+          y[j * EPW + u] = clampf(x[j * EPW + u] - (p.step / (1.f - 0.9f)) * (m / den), p.lo, p.hi);
+        }
       }
       __syncwarp();
       float* tmp = x;
@@ -94,29 +126,50 @@ static __device__ __noinline__ void epilogue_warp_body(const EpiParams& p, float
       y = tmp;
     }
     if (p.pv)
-      for (int j = lane; j < N; j += 32) p.pv[(size_t)b * N + j] = x[j];
+      for (int j = lane; j < N; j += 32) {
+#pragma unroll
+        for (int u = 0; u < EPW; ++u)
+          if (ok[u]) p.pv[(size_t)(b0 + u) * N + j] = x[j * EPW + u];
+      }
     if (p.energy) {
       if (p.map2) {
-        for (int j = lane; j < N; j += 32) y[j] = x[j] * (p.m2vec ? p.m2vec[j] : p.m2s) + p.m2o;
+        for (int j = lane; j < N; j += 32) {
+#pragma unroll
+          for (int u = 0; u < EPW; ++u) y[j * EPW + u] = x[j * EPW + u] * (p.m2vec ? p.m2vec[j] : p.m2s) + p.m2o;
+        }
         __syncwarp();
         x = y;
       }
       // E = (1/2 x Q x + V x) * scaled_by   (problem_instance.py:226-241)
-      float e1 = 0.f, e2 = 0.f;
-      for (int j = lane; j < N; j += 32) {
-        float acc = 0.f;
-        for (int i = 0; i < N; ++i) acc = fmaf(x[i], Q[i * ld + j], acc);
-        e1 = fmaf(acc, x[j], e1);
-        e2 = fmaf(p.v[j], x[j], e2);
-      }
+      float e1[EPW], e2[EPW];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        e1 += __shfl_xor_sync(0xffffffffu, e1, o);
-        e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+      for (int u = 0; u < EPW; ++u) e1[u] = e2[u] = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        float acc[EPW];
+#pragma unroll
+        for (int u = 0; u < EPW; ++u) acc[u] = 0.f;
+        for (int i = 0; i < N; ++i) {
+          const float q = Q[i * ld + j];
+          const float4 x4 = *reinterpret_cast<const float4*>(x + i * EPW);
+          const float xi[EPW] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int u = 0; u < EPW; ++u) acc[u] = fmaf(xi[u], q, acc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < EPW; ++u) {
+          e1[u] = fmaf(acc[u], x[j * EPW + u], e1[u]);
+          e2[u] = fmaf(p.v[j], x[j * EPW + u], e2[u]);
+        }
       }
-      if (lane == 0) {
-        const float sb = p.scaled_by_ptr ? *p.scaled_by_ptr : p.scaled_by;
-        p.energy[b] = 0.5f * (e1 * sb) + e2 * sb;
+      const float sb = p.scaled_by_ptr ? *p.scaled_by_ptr : p.scaled_by;
+#pragma unroll
+      for (int u = 0; u < EPW; ++u) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          e1[u] += __shfl_xor_sync(0xffffffffu, e1[u], o);
+          e2[u] += __shfl_xor_sync(0xffffffffu, e2[u], o);
+        }
+        if (lane == 0 && ok[u]) p.energy[b0 + u] = 0.5f * (e1[u] * sb) + e2[u] * sb;
       }
     }
     __syncwarp();

@@ -656,6 +656,23 @@ __device__ __forceinline__ void ld_cg_256(const float* src, float* r) {
                : "memory");
 }
 
+// Waits until a global chunk counter has reached `need` (acquire at GPU scope), then orders the TMA loads
+// that follow behind it.  Bounded like mbar_wait: a protocol bug traps instead of hanging the device.
+__device__ __forceinline__ void flag_wait(const unsigned int* flag, uint32_t need) {
+  long long start = 0;
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= need) break;
+    if ((spins & 0xff) == 0xff) {
+      const long long now = clock64();
+      if (start == 0) start = now;
+      else if (now - start > 4000000000ll) __trap();
+    }
+  }
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 template <int SOLVER, bool ADAM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     sde_tc2_kernel(const SdeParams p, const TcParams tc, const __grid_constant__ CUtensorMap map_xh,
@@ -675,7 +692,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const int NC = NP / TC_BN;
   const int KB = NP / T2_BK;
   constexpr int KB_PER_CHUNK = TC_BN / T2_BK;
-  const int row0 = blockIdx.x * TC_BM;
+  // column split (TcParams::col_split): CS pairs share one block of 256 rows, pair `cs` owns output chunks
+  // [nc_lo, nc_hi); the chunks of the others reach it through global memory, published by chunk_flags
+  const int CS = tc.col_split;
+  const int pair_idx = (int)(blockIdx.x >> 1);
+  const int cs = pair_idx % CS;
+  const int row_cta = (pair_idx / CS) * 2 + (int)rank;   // index of this CTA's block of 128 rows
+  const int row0 = row_cta * TC_BM;
+  const int nc_lo = cs * (NC / CS), nc_hi = nc_lo + NC / CS;
+  unsigned int* my_flags = tc.chunk_flags + (size_t)row_cta * NC;
   const size_t plane = (size_t)tc.rows_p * NP;
 
   const uint32_t smem_base = (smem_u32(tc_smem) + 1023u) & ~1023u;
@@ -718,11 +743,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       uint32_t phase = 0;
       for (int t = 0; t < T; ++t) {
         const int arow = (t & 1) * tc.rows_p + row0;
-        for (int nc = 0; nc < NC; ++nc) {
+        for (int nc = nc_lo; nc < nc_hi; ++nc) {
           const int brow = nc * TC_BN + (int)rank * TC_BM;  // this CTA's half of the Qs^T tile
-          for (int kb = 0; kb < KB; ++kb) {
-            if (t > 0 && nc == 0 && (kb % KB_PER_CHUNK) == 0)
-              mbar_wait(ready_bar(kb / KB_PER_CHUNK), (uint32_t)((t - 1) & 1));
+          for (int kbi = 0; kbi < KB; ++kbi) {
+            // k-blocks are consumed in the order their columns become ready: with a column split the h-th chunks
+            // of all owners come first, own one leading (every pair finishes its h-th chunk at about the same
+            // time), so the contraction of iteration t+1 starts under the last epilogues of iteration t
+            const int ci = kbi / KB_PER_CHUNK;
+            const int c = ((cs + ci % CS) % CS) * (NC / CS) + ci / CS;   // CS = 1: ci
+            const int kb = c * KB_PER_CHUNK + kbi % KB_PER_CHUNK;
+            if (t > 0 && nc == nc_lo && (kbi % KB_PER_CHUNK) == 0) {
+              // the columns of this k-block were written by the epilogue of iteration t-1: this CTA's own
+              // (shared-memory barrier) or the partner pair's (global counter, +2 per iteration)
+              if (c >= nc_lo && c < nc_hi) mbar_wait(ready_bar(c), (uint32_t)((t - 1) & 1));
+              else flag_wait(my_flags + c, 2u * (uint32_t)t);
+            }
             mbar_wait(empty_bar(stage), phase ^ 1u);
             const uint32_t sa = smem_base + stage * T2_STAGE_BYTES;
             const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
@@ -749,7 +784,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       uint32_t phase = 0;
       uint32_t it = 0;
       for (int t = 0; t < T; ++t) {
-        for (int nc = 0; nc < NC; ++nc, ++it) {
+        for (int nc = nc_lo; nc < nc_hi; ++nc, ++it) {
           const uint32_t ab = it & 1u;
           mbar_wait(acce_bar(ab), ((it >> 1) & 1u) ^ 1u);
           tc_fence_after();
@@ -801,7 +836,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       const float* xh_cur = tc.xh + (size_t)(t & 1) * plane + (size_t)row * NP;
       const float* xl_cur = tc.xl + (size_t)(t & 1) * plane + (size_t)row * NP;
       const int nrow0 = ((t + 1) & 1) * tc.rows_p + row0;  // first row of this CTA in the next state half
-      for (int nc = 0; nc < NC; ++nc, ++it) {
+      for (int nc = nc_lo; nc < nc_hi; ++nc, ++it) {
         const uint32_t ab = it & 1u;
         mbar_wait(accf_bar(ab), (it >> 1) & 1u);
         tc_fence_after();
@@ -863,6 +898,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           // this warpgroup's half of the chunk is in global memory: the producer may fetch it
           asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
           mbar_arrive(ready_bar(nc));
+          if (CS > 1) {
+            // ... and so may the partner pair's: publish at GPU scope (the TMA stores above are complete)
+            __threadfence();
+            atomicAdd(my_flags + nc, 1u);
+          }
         }
       }
     }

@@ -90,11 +90,14 @@ struct TcParams {
   int np;           // n rounded up to a multiple of TC_BN
   int rows;         // valid rows = K * batch
   int rows_p;       // rows rounded up to a multiple of TC_BM
+  int col_split;    // CTA pairs (1, 2 or 4) that share one block of 256 rows, each owning np / 256 / col_split output chunks
+  unsigned int* chunk_flags;  // col_split > 1: [rows_p / TC_BM][np / 256] counters, +2 per iteration and chunk written
 };
 
 struct TcPlan {
   int version;  // 1: single-CTA kernel (sde_tc_kernel), 2: CTA-pair kernel (sde_tc2_kernel)
   int np, rows, rows_p, n_aux, ctas;
+  int col_split;  // see TcParams
   size_t smem;
 };
 

@@ -29,6 +29,13 @@ def test_path_selection(monkeypatch):
     monkeypatch.delenv("CCVM_TC", raising=False)
     assert _launch_info(nat.SOLVER_DL, 1024, 8192)["threads"] == TC_THREADS      # config 4
     assert _launch_info(nat.SOLVER_DL, 1024, 8192)["ctas"] == 128
+    # Langevin-type loops have one row per trajectory: 64 row blocks at B = 8192 -> two CTA pairs per block of
+    # 256 rows split its four output chunks (128 CTAs); small batches split four ways
+    assert _launch_info(nat.SOLVER_LANGEVIN, 1024, 8192)["ctas"] == 128
+    assert _launch_info(nat.SOLVER_LANGEVIN, 1024, 2048)["ctas"] == 64
+    monkeypatch.setenv("CCVM_TC_NO_SPLIT", "1")
+    assert _launch_info(nat.SOLVER_LANGEVIN, 1024, 8192)["ctas"] == 64
+    monkeypatch.delenv("CCVM_TC_NO_SPLIT")
     assert _launch_info(nat.SOLVER_LANGEVIN, 320, 1024)["threads"] == TC_THREADS
     assert _launch_info(nat.SOLVER_DL, 320, 512)["threads"] == TC_THREADS        # 1024 rows
     assert _launch_info(nat.SOLVER_LANGEVIN, 320, 512)["threads"] != TC_THREADS  # too few rows: SIMT
@@ -92,6 +99,28 @@ def test_tc_matches_simt_under_same_philox_stream(monkeypatch, solver, ver):
     monkeypatch.setenv("CCVM_TC", ver)
     outs, _ = E.solve(sid, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, seed=9, offset=8, **kw)
     assert all(torch.equal(o, r) for o, r in zip(outs, res[ver]))
+
+
+@pytest.mark.parametrize("solver,n,b", [("lv", 1024, 2048), ("mf", 512, 1024), ("plv", 1024, 4096), ("dl", 512, 512)])
+def test_tc_column_split_matches_unsplit(monkeypatch, solver, n, b):
+    """Two / four CTA pairs per row block exchanging the state through L2 (chunk flags) against one pair per
+    block: same noise, same arithmetic up to the order of the k-blocks inside the tensor-core accumulation."""
+    t = 25
+    q, v, _ = instance(n, 9, 0.2 if solver == "dl" else 0.05)
+    sid, kw = {"dl": (nat.SOLVER_DL, dict(s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0, feedback_scale=100.0, g=0.05)),
+               "lv": (nat.SOLVER_LANGEVIN, dict(s=0.5, dt=0.002, sigma=0.5, feedback_scale=1.0)),
+               "plv": (nat.SOLVER_PUMPED_LANGEVIN, dict(s=0.5, pump=2.0, dt=0.002, sigma=0.5, feedback_scale=1.0)),
+               "mf": (nat.SOLVER_MF, dict(s=20.0, pump=0.0, dt=0.0025, j=5.0, feedback_scale=4000.0, g=0.01))}[solver]
+    monkeypatch.delenv("CCVM_TC_NO_SPLIT", raising=False)
+    split, _ = E.solve(sid, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, seed=2, offset=6, **kw)
+    split = [o.clone() for o in split]
+    again, _ = E.solve(sid, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, seed=2, offset=6, **kw)
+    assert all(torch.equal(a, c) for a, c in zip(split, again))       # the exchange is race-free: bit-reproducible
+    monkeypatch.setenv("CCVM_TC_NO_SPLIT", "1")
+    one, _ = E.solve(sid, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, seed=2, offset=6, **kw)
+    for a, c in zip(one, split):
+        assert torch.isfinite(c).all()
+        assert (a - c).abs().max().item() <= 2e-4 * max(a.abs().max().item(), 1.0)
 
 
 @pytest.mark.parametrize("ver", ["2", "1"])
