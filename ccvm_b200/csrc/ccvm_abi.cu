@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ccvm_b200.h"
 #include "epilogue.cuh"
 #include "sde_kernel_tc.cuh"
@@ -30,6 +32,12 @@ int ccvm::set_error(int code, const char* fmt, ...) {
   return code;
 }
 #define fail(...) ::ccvm::set_error(__VA_ARGS__)
+
+// NVTX range around an entry point (tracing hooks); header-only NVTX3, a no-op without a tool attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 extern "C" const char* ccvm_last_error(void) { return g_err; }
 extern "C" int ccvm_abi_version(void) { return CCVM_ABI_VERSION; }
@@ -566,6 +574,7 @@ static int plan_epilogue(EpiParams& p, int nwarps, int max_smem, size_t& smem) {
 }
 
 static int run_epilogue(const EpiParams& p0, cudaStream_t st) {
+  NvtxRange range("ccvm_epilogue");
   EpiParams p = p0;
   DeviceInfo di;
   int rc = device_info(di);
@@ -719,6 +728,7 @@ static int plan_fused_tail(const ccvm_solve_desc& d, const ccvm_epilogue_desc* e
 
 static int solve_impl(const ccvm_solve_desc* d, const ccvm_epilogue_desc* epi, double optimal, FusedOut* result,
                       cudaStream_t st) {
+  NvtxRange range(epi ? "ccvm_solve_fused" : "ccvm_solve");
   int rc = validate_solve(d);
   if (rc) return rc;
   DeviceInfo di;
@@ -830,6 +840,7 @@ __global__ void build_schedule_batch_kernel(const SchedJob* __restrict__ jobs, f
 
 static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_desc* epis, const double* optimal,
                             int32_t count, FusedOut* results, cudaStream_t st) {
+  NvtxRange range(epis ? "ccvm_solve_batch_fused" : "ccvm_solve_batch");
   if (!descs || count < 1) return fail(CCVM_E_INVALID, "ccvm_solve_batch needs at least one descriptor");
   if (results && (!epis || !optimal)) return fail(CCVM_E_INVALID, "statistics need epilogue descriptors and optimal values");
   DeviceInfo di;
