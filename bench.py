@@ -224,6 +224,45 @@ def oracle_check(E, nat, q_host, v_host, q, v, sb, s_val, traj_base):
             "best_gpu": float((-e_gpu).max()), "best_oracle": float((-e_ref).max()), "ok": bool(rel <= 2e-3)}
 
 
+def strong_record(E, nat, P, rank, world, dev, q, v, sb, s_val):
+    """STRONG scaling of the headline workload: ONE batch of 4096 trajectories split over the GPUs (even shard
+    starts), same fused step + cross-rank merge, device-timed, max over ranks.  With 512 trajectories per GPU at
+    N = 8 an SM owns 3-4 trajectories: the loop is latency-bound there, this record says by how much."""
+    import torch.distributed as dist
+    start, count = P.shard_bounds(BATCH, world, rank, align=2)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(k):
+        plan = E.plan_solve(nat.SOLVER_DL, nat.ALG_ADAM, q, v, count, ITERS, s=1.0, pump=DL["pump"], dt=DL["dt"],
+                            noise_ratio=DL["noise_ratio"], g=DL["g"], hyperparameters=HP, seed=4321, offset=k,
+                            traj_base=start)
+        epi = E.plan_epilogue(count, N, dev, map1=(0.5 / s_val, 0.5), post_processor="adam", scaled_by=sb)
+        res = E.solve_fused(plan, epi, 0.0)
+        if world > 1:
+            return P.merge_results(P.pack_from_stats(res, epi.pv, start))
+        return res
+
+    for k in range(3):
+        step(k)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    steps = 10
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record(stream)
+    for k in range(steps):
+        step(10 + k)
+    ev[1].record(stream)
+    torch.cuda.synchronize(dev)
+    ms = ev[0].elapsed_time(ev[1]) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    return {"workload": "the headline step on ONE batch of 4096 trajectories sharded over the GPUs", "scaling": "strong",
+            "n_gpus": world, "batch_per_gpu": count, "ms_per_step": ms, "traj_steps_per_s": BATCH * ITERS / (ms * 1e-3)}
+
+
 SWEEP_SIZES = list(range(20, 251, 10))
 SWEEP_COUNT, SWEEP_BATCH, SWEEP_ITERS, SWEEP_CHUNK = 1024, 1000, 1500, 64
 
@@ -548,6 +587,10 @@ def run_gpu_arm(args):
 
     extras = {}
     if not args.no_extras:
+        try:
+            extras["strong"] = strong_record(E, nat, P, rank, world, dev, q, v, sb, s_val)
+        except Exception as e:  # noqa: BLE001
+            extras["strong"] = {"error": f"{type(e).__name__}: {e}"}
         for name, fn in (("sweep", lambda: sweep_record(rank, world, dev)),
                          ("config4", lambda: config4_record(E, nat, rank, world, dev))):
             try:
