@@ -237,6 +237,8 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   P.qsrc = path == PATH_TMEM ? QSRC_TMEM : path == PATH_HYB ? QSRC_HYB : QSRC_GMEM;
   P.cg = cg;
   P.cgc = (cgc_variant || (small_cgc && pipe)) ? cg : 0;
+  // N = 30, 50, 70: the variant that leaves out the two padding rows of the last chunk of four
+  P.ktail = (P.cgc == 8 || P.cgc == 13 || P.cgc == 18) && d.n == 4 * cg - 2 && getenv("CCVM_NO_KTAIL") == nullptr ? 2 : 0;
   P.threads = ng * P.L.gt;
   P.ctas = (d.batch + ng * 2 * rg - 1) / (ng * 2 * rg);
   P.smem = smem_of(xs);
@@ -896,7 +898,7 @@ static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_de
   // items + CTA maps, bucketed by (Q source, block size, compiled-in column-group count) so that small
   // instances do not pay for big blocks and the benchmarking sizes get the fully unrolled kernels
   struct Bucket {
-    int threads, qsrc, cgc;
+    int threads, qsrc, cgc, ktail;
     size_t smem;
     std::vector<int2> map;
   };
@@ -919,9 +921,11 @@ static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_de
     }
     size_t which = buckets.size();
     for (size_t u = 0; u < buckets.size(); ++u)
-      if (buckets[u].threads == bucket_threads[k] && buckets[u].qsrc == plans[b].qsrc && buckets[u].cgc == plans[b].cgc)
+      if (buckets[u].threads == bucket_threads[k] && buckets[u].qsrc == plans[b].qsrc && buckets[u].cgc == plans[b].cgc &&
+          buckets[u].ktail == plans[b].ktail)
         which = u;
-    if (which == buckets.size()) buckets.push_back(Bucket{bucket_threads[k], plans[b].qsrc, plans[b].cgc, 0, {}});
+    if (which == buckets.size())
+      buckets.push_back(Bucket{bucket_threads[k], plans[b].qsrc, plans[b].cgc, plans[b].ktail, 0, {}});
     Bucket& B = buckets[which];
     for (int c = 0; c < plans[b].ctas; ++c) B.map.push_back(make_int2((int)b, c));
     if (smem > B.smem) B.smem = smem;
@@ -967,6 +971,7 @@ static int solve_batch_impl(const ccvm_solve_desc* descs, const ccvm_epilogue_de
     bb.threads = B.threads;
     bb.qsrc = B.qsrc;
     bb.cgc = B.cgc;
+    bb.ktail = B.ktail;
     bb.smem = B.smem;
     cudaStream_t ls = st;
     if (fork) {

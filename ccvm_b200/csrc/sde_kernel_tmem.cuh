@@ -43,8 +43,14 @@
 // Measured and dropped in round 2 (profiles/r2m_tuning_x32_kp2_padstage.txt): tcgen05.ld.x32 for the K = 1
 // tiles (half the LDTM / R2UR / wait instructions) and two k rows per panel row for n <= 128 (one LDS.128
 // per two k) -- within +-3 % either way, no consistent sign over the loops and sizes.
+//   CCVM_KTAIL_MASK  tiles whose N = 30 / 50 / 70 variants leave out the two padding rows of the last chunk
+//                    (+1-2 % for DL, MF, Langevin(+Adam), PumpedLangevin; -1-4 % for the other Adam tiles:
+//                    profiles/r2t_ktail_n30_50_70.txt)
 #ifndef CCVM_HOIST_MASK
 #define CCVM_HOIST_MASK 0xA3
+#endif
+#ifndef CCVM_KTAIL_MASK
+#define CCVM_KTAIL_MASK 0x75
 #endif
 #ifndef CCVM_UNPIN_MASK
 #define CCVM_UNPIN_MASK 0x7F
@@ -146,7 +152,9 @@ __device__ __forceinline__ void adam_tile4(pf2 (&g)[4], pf2 (&m)[4], pf2 (&v)[4]
 // issue slot free); the ALU / MUFU work and the dependent IMAD.WIDE chain of the generator fill
 // those slots, and the latency-bound phase between contraction and barrier shrinks to the SDE
 // update itself (profiles/r1_ncu_sde_dl_tmem_v3.txt: FMA pipe 73 % busy, 27 % bubbles, before).
-template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
+// KTAIL (compile-time column-group variants only): real rows in the LAST chunk of four k -- 2 for N = 30, 50,
+// 70, whose padding rows 4 CG - 2, 4 CG - 1 (zero rows of Qs) are then neither loaded nor multiplied; 0: all four.
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0, int KTAIL = 0>
 __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaunch& L, const FusedTail& f, const int cta,
                                               float* smem, uint32_t* tmem_slot_p) {
   constexpr int K = SolverTraits<SOLVER>::K;
@@ -482,6 +490,28 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         }
         return __float_as_uint(xx[XR - 1].x);
       };
+      // the last chunk of the contraction without its padding rows (KTAIL)
+      constexpr int LASTK = (KTAIL > 0 && KP == 1 && CGC != 0) ? KTAIL : 4;
+      auto load_x_last = [&](int row, XV (&dst)[XR]) {
+#pragma unroll
+        for (int kk = 0; kk < (LASTK < XR ? LASTK : XR); ++kk) dst[kk] = *reinterpret_cast<const XV*>(xp + (row / KP + kk) * ROWB);
+      };
+      auto contract_last = [&](const float (&qq)[16], const XV (&xx)[XR]) {
+        if constexpr (LASTK == 4) {
+          contract(qq, xx);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < LASTK; ++kk) {
+            pf2 xv[KT];
+            xv[0] = pk(xx[kk].x, xx[kk].y);
+            if constexpr (KT == 2) xv[1] = pk(xx[kk].z, xx[kk].w);
+#pragma unroll
+            for (int q = 0; q < KT; ++q)
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) acc[q][jj] = fma2(xv[q], dup(qq[4 * kk + jj]), acc[q][jj]);
+          }
+        }
+      };
       // Small compile-time column-group counts (CG = 5, 8 <-> N = 20, 30): the contraction is too short
       // to hide a noise quantum per chunk pair -- pinned there, the quanta ran one after the other and
       // their ~250-cycle dependent chains WERE the iteration.  All of them start at the top instead,
@@ -619,12 +649,12 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
         tmem_wait_ld();
         if (kc + 2 == CG) {
           tmem_ld16(tlane + 16 * (kc + 1), qb);
-          load_x(4, xb);
+          load_x_last(4, xb);
           contract(qa, xa);
           tmem_wait_ld();
-          contract(qb, xb);
+          contract_last(qb, xb);
         } else {
-          contract(qa, xa);
+          contract_last(qa, xa);
         }
         }
       }
@@ -904,12 +934,12 @@ __device__ __forceinline__ void sde_tile_body(const SdeParams& p, const TmemLaun
   }
 }
 
-template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0>
+template <int SOLVER, bool ADAM, int QSRC, bool PIPE, int CGC = 0, int KTAIL = 0>
 __global__ void __launch_bounds__(QSRC == QSRC_GMEM ? 512 : 256, 1)
     sde_tmem_kernel(const SdeParams p, const TmemLaunch L, const FusedTail f) {
   extern __shared__ __align__(16) float smem[];
   __shared__ uint32_t tmem_slot;
-  sde_tile_body<SOLVER, ADAM, QSRC, PIPE, CGC>(p, L, f, blockIdx.x, smem, &tmem_slot);
+  sde_tile_body<SOLVER, ADAM, QSRC, PIPE, CGC, KTAIL>(p, L, f, blockIdx.x, smem, &tmem_slot);
 }
 
 // PIPE needs Philox noise and more than 4*K chunks of four Q rows (DL: n >= 33, others: n >= 17).
@@ -921,7 +951,7 @@ __host__ __device__ __forceinline__ bool pipe_ok(int cg, bool philox) {
 // One launch over MANY problem instances (BatchItem, sde_launch.h): each CTA looks up (instance, CTA
 // index inside the instance) and runs the same body with that instance's parameters.  CGC != 0: every
 // instance of the bucket has that column-group count (compile-time variants of the PIPE kernels).
-template <int SOLVER, bool ADAM, int QSRC, int CGC = 0>
+template <int SOLVER, bool ADAM, int QSRC, int CGC = 0, int KTAIL = 0>
 __global__ void __launch_bounds__(256, 1)
     sde_tmem_batch_kernel(const BatchItem* __restrict__ items, const int2* __restrict__ cta_map) {
   extern __shared__ __align__(16) float smem[];
@@ -937,7 +967,7 @@ __global__ void __launch_bounds__(256, 1)
   const SdeParams p = s_item.p;
   const TmemLaunch L = s_item.L;
   if constexpr (CGC != 0) {
-    sde_tile_body<SOLVER, ADAM, QSRC, true, CGC>(p, L, s_item.f, m.y, smem, &tmem_slot);
+    sde_tile_body<SOLVER, ADAM, QSRC, true, CGC, KTAIL>(p, L, s_item.f, m.y, smem, &tmem_slot);
   } else {
     if (L.pipe)
       sde_tile_body<SOLVER, ADAM, QSRC, true>(p, L, s_item.f, m.y, smem, &tmem_slot);

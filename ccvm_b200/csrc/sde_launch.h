@@ -51,6 +51,7 @@ struct TmemPlan {
   TmemLaunch L;
   int cg, threads, ctas, qsrc;
   int cgc;  // column-group count compiled into the kernel variant to launch (0: run-time loop)
+  int ktail;  // 2: the variant that skips the two padding rows of the last chunk (n = 4 cgc - 2: N = 30, 50, 70); 0: none
   size_t smem;
 };
 
@@ -69,7 +70,7 @@ struct BatchBucket {
   const BatchItem* items;
   const int2* map;
   unsigned ctas;
-  int threads, qsrc, cgc;
+  int threads, qsrc, cgc, ktail;
   size_t smem;
 };
 
