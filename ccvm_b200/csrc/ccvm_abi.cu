@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>
@@ -64,6 +65,8 @@ static int device_info(DeviceInfo& di) {
     if (major != 10)
       return fail(CCVM_E_CUDA, "ccvm_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
     static cudaMemPool_t pools[64];  // one per device for the whole process
+    static std::mutex pools_mutex;
+    std::lock_guard<std::mutex> lock(pools_mutex);
     if (!pools[dev]) {
       cudaMemPoolProps props;
       memset(&props, 0, sizeof(props));
@@ -753,12 +756,18 @@ static int solve_impl(const ccvm_solve_desc* d, const ccvm_epilogue_desc* epi, d
     if ((rc = plan_tmem(*d, di, path, TP))) return rc;
     FusedTail f;
     memset(&f, 0, sizeof(f));
-    // the schedule table is evaluated by every CTA in its prologue (one launch per solve)
-    CUDA_TRY(sched_buf.alloc(sched_row_bytes * TP.ctas));
-    f.sched_inline = 1;
+    // the schedule table is evaluated by every CTA in its prologue (one launch per solve) -- unless the per-CTA
+    // copies would add up (very large batches x very long runs): then ONE table from a kernel of its own
+    const bool inline_sched = sched_row_bytes * (size_t)TP.ctas <= ((size_t)64 << 20) && getenv("CCVM_NO_SCHED_INLINE") == nullptr;
+    CUDA_TRY(sched_buf.alloc(inline_sched ? sched_row_bytes * TP.ctas : sched_row_bytes));
+    f.sched_inline = inline_sched ? 1 : 0;
     f.sa = sched_args(d);
     f.sched_scratch = sched_buf.as<float>();
-    fill_params(d, nullptr, TP.cg, p);
+    if (!inline_sched) {
+      build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(f.sa, sched_buf.as<float>());
+      CUDA_TRY(cudaGetLastError());
+    }
+    fill_params(d, inline_sched ? nullptr : sched_buf.as<float>(), TP.cg, p);
     if (TP.qsrc == QSRC_GMEM) {
       const int np = 4 * TP.cg;
       CUDA_TRY(qs_buf.alloc((size_t)np * np * sizeof(float)));
@@ -820,6 +829,8 @@ struct SideStreams {
 };
 static int side_streams(int device, SideStreams*& out) {
   static SideStreams pools[64];
+  static std::mutex pools_mutex;
+  std::lock_guard<std::mutex> lock(pools_mutex);
   SideStreams& p = pools[device];
   if (!p.ok) {
     for (int i = 0; i < SideStreams::N; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&p.s[i], cudaStreamNonBlocking));

@@ -388,3 +388,19 @@ def test_tiled_epilogue_matches_per_trajectory_kernel(monkeypatch, n, b, pp):
     pv_l, e_l = E.epilogue(state, q, v, **kw)
     assert torch.equal(pv_t, pv_l)
     assert torch.allclose(e_t, e_l, rtol=2e-6, atol=1e-5 * float(e_l.abs().max()))
+
+
+def test_schedule_table_from_its_own_kernel_matches_the_inline_one(monkeypatch):
+    """Very large batch x iteration counts fall back to ONE schedule table built by a kernel of its own (the
+    per-CTA copies of the in-kernel prologue would add up): same table, bit-identical results."""
+    q0, v0 = O.synthetic_boxqp(33, 5)
+    f = O.scaling_factor(q0, 0.2)
+    q, v = (q0 / f).cuda(), (v0 / f).cuda()
+    kw = dict(s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0, g=0.05, seed=3, offset=8,
+              hyperparameters=dict(alpha=0.001, beta1=0.9, beta2=0.999, add_assign=True))
+    monkeypatch.delenv("CCVM_NO_SCHED_INLINE", raising=False)
+    a, _ = E.solve(nat.SOLVER_DL, nat.ALG_ADAM, q, v, 130, 77, **kw)
+    a = [t.clone() for t in a]
+    monkeypatch.setenv("CCVM_NO_SCHED_INLINE", "1")
+    b, _ = E.solve(nat.SOLVER_DL, nat.ALG_ADAM, q, v, 130, 77, **kw)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
