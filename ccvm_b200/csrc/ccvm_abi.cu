@@ -324,7 +324,8 @@ static void plan_tc(const ccvm_solve_desc& d, TcPlan& P) {
     const int nc = P.np / TC_BN;
     if (P.version == 2 && getenv("CCVM_TC_NO_SPLIT") == nullptr)
       for (int cs = 4; cs >= 2; cs >>= 1)
-        if (nc % cs == 0 && cs * P.ctas <= sms) {
+        // (2-CTA clusters cannot use the odd SM of a GPC: leave a margin so that ALL clusters are resident)
+        if (nc % cs == 0 && cs * P.ctas <= sms - 12) {
           P.col_split = cs;
           break;
         }

@@ -664,10 +664,11 @@ __device__ __forceinline__ void flag_wait(const unsigned int* flag, uint32_t nee
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     if (v >= need) break;
+    __nanosleep(64);
     if ((spins & 0xff) == 0xff) {
       const long long now = clock64();
       if (start == 0) start = now;
-      else if (now - start > 4000000000ll) __trap();
+      else if (now - start > 60000000000ll) __trap();   // ~30 s: the partner may be held up by other streams' kernels
     }
   }
   asm volatile("fence.proxy.async;" ::: "memory");
