@@ -399,6 +399,7 @@ def test_schedule_table_from_its_own_kernel_matches_the_inline_one(monkeypatch):
     kw = dict(s=1.0, pump=8.0, dt=0.001, noise_ratio=10.0, g=0.05, seed=3, offset=8,
               hyperparameters=dict(alpha=0.001, beta1=0.9, beta2=0.999, add_assign=True))
     monkeypatch.delenv("CCVM_NO_SCHED_INLINE", raising=False)
+    from ccvm_b200 import _native as nat
     a, _ = E.solve(nat.SOLVER_DL, nat.ALG_ADAM, q, v, 130, 77, **kw)
     a = [t.clone() for t in a]
     monkeypatch.setenv("CCVM_NO_SCHED_INLINE", "1")
