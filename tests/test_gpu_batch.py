@@ -97,3 +97,23 @@ def test_sweep_chunked_equals_unchunked():
     b = sweep.solve_sweep(solver, insts, post_processor=pp, rank=0, world_size=1, chunk=3)
     strip = lambda r: {k: v for k, v in r.items() if k not in ("solve_time", "pp_time")}  # noqa: E731
     assert [strip(r) for r in a] == [strip(r) for r in b]
+
+
+def test_sweep_results_do_not_depend_on_rank_count_or_chunking():
+    """Every instance's noise stream is keyed by its GLOBAL index in the sweep (sweep.solve_sweep), so the shards of
+    a 2-rank or 3-rank sweep (emulated here rank by rank, no process group) reproduce the 1-rank results exactly,
+    whatever the chunk size."""
+    solver, pp = _solver("lv", 64, 30)
+    insts = _instances(solver)
+    torch.manual_seed(5)
+    one = sweep.solve_sweep(solver, insts, post_processor=pp, rank=0, world_size=1, chunk=4)
+    strip = lambda r: {k: v for k, v in r.items() if k not in ("solve_time", "pp_time", "rank")}  # noqa: E731
+    for world, chunk in ((2, 1), (3, 8)):
+        merged = {}
+        for rank in range(world):
+            torch.manual_seed(5)          # every rank starts from the same generator state, as under torchrun
+            for rec in sweep.solve_sweep(solver, insts, post_processor=pp, rank=rank, world_size=world, chunk=chunk,
+                                         gather=False):
+                merged[rec["index"]] = rec
+        assert sorted(merged) == list(range(len(insts)))
+        assert [strip(merged[k]) for k in sorted(merged)] == [strip(r) for r in one]
