@@ -16,6 +16,7 @@
 
 #include "../../include/ccvm_b200.h"
 #include "epilogue.cuh"
+#include "sde_kernel_mma.cuh"
 #include "sde_kernel_tc.cuh"
 #include "sde_kernel_tmem.cuh"
 #include "sde_launch.h"
@@ -116,7 +117,7 @@ __global__ void build_schedule_kernel(SchedArgs a, float* __restrict__ out) {
 }
 
 // ---- tiled paths (sde_kernel_tmem.cuh): Q slice from TMEM (n <= 128) or streamed from L2 (any n)
-enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_TC = 3, PATH_HYB = 4 };
+enum { PATH_TMEM = 0, PATH_GMEM = 1, PATH_TC = 3, PATH_HYB = 4, PATH_MMA = 5 };
 
 // tcgen05 3xTF32 drift (sde_kernel_tc.cuh) where batch x N x N is a genuine dense GEMM:
 // n > 256 and at least 1024 contraction rows (8 CTAs of 128 rows).  n = 256 itself is also served by
@@ -139,8 +140,22 @@ static bool tc_eligible(const ccvm_solve_desc& d) {
   return tc_size_rule(d);
 }
 
-static int choose_path(const ccvm_solve_desc& d) {
+// Small-n tensor-core kernel (sde_kernel_mma.cuh): single-instance launches in production (Philox) mode whose
+// batch fills the SMs with 28-32 trajectories each -- there the register-tile kernels are issue-bound on the
+// contraction's FFMA2 stream and the tensor core takes it off the SIMT pipes.  Below ~48 variables most TMEM
+// lanes of the 128-row MMA idle and the tiled kernel wins; noise replay, evolution sampling and batched
+// (many-instance) launches stay on the tiled kernels.  CCVM_MMA=0 / 1 overrides the size rule.
+static bool mma_eligible(const ccvm_solve_desc& d) {
+  if (d.n > 128 || d.rng_mode != CCVM_RNG_PHILOX || d.evolution_step > 0) return false;
+  if (const char* e = getenv("CCVM_MMA")) {
+    if (e[0] != 'a') return atoi(e) != 0;
+  }
+  return false;   // (being tuned: opt-in)
+}
+
+static int choose_path(const ccvm_solve_desc& d, bool single_launch = false) {
   if (tc_eligible(d)) return PATH_TC;
+  if (single_launch && mma_eligible(d)) return PATH_MMA;
   if (d.n <= 128 && getenv("CCVM_NO_TMEM") == nullptr) return PATH_TMEM;
   // 128 < n <= 256: first 128 rows of every Q slice in TMEM, the rest in shared memory
   if (d.n <= 4 * 64 && getenv("CCVM_NO_TMEM") == nullptr && getenv("CCVM_NO_HYB") == nullptr) return PATH_HYB;
@@ -246,6 +261,25 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   P.ctas = (d.batch + ng * 2 * rg - 1) / (ng * 2 * rg);
   P.smem = smem_of(xs);
   return CCVM_OK;
+}
+
+// Launch geometry of the small-n tensor-core kernel: a CTA advances 4 nbp trajectories (two warpgroups of nbp
+// pairs); nbp = 7 or 8, whichever needs fewer waves of CTAs (ties: 7, less work per thread).
+static void plan_mma(const ccvm_solve_desc& d, const DeviceInfo& di, MmaPlan& P) {
+  auto waves = [&](int nbp) {
+    const long long ctas = ((long long)d.batch + 4 * nbp - 1) / (4 * nbp);
+    return (ctas + di.sms - 1) / di.sms;
+  };
+  P.nbp = waves(8) < waves(7) ? 8 : 7;
+  if (const char* e = getenv("CCVM_MMA_NBP")) {
+    const int v = atoi(e);
+    if (v == 7 || v == 8) P.nbp = v;
+  }
+  P.kd = ((d.n + 1 + 7) / 8) * 8;
+  P.tcols = 512;
+  P.threads = MMA_THREADS;
+  P.ctas = (int)(((long long)d.batch + 4 * P.nbp - 1) / (4 * P.nbp));
+  P.smem = mma_loop_smem_bytes();
 }
 
 // Qs[k][j] = -alpha_k alpha_j Q_kj, zero padded to NP x NP (QSRC_GMEM operand)
@@ -497,9 +531,22 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
   if (rc) return rc;
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
-  const int path = choose_path(*d);
+  const int path = choose_path(*d, true);
   const bool adam = d->algorithm == CCVM_ALG_ADAM;
   int regs = -1;
+  if (path == PATH_MMA) {
+    MmaPlan P;
+    plan_mma(*d, di, P);
+    info5[0] = P.threads;
+    info5[1] = P.ctas;
+    info5[2] = 4 * P.nbp;
+    info5[3] = (int)P.smem;
+#define REGS_MMA(S, A) regs = regs_mma<S, A>(P.nbp)
+    CCVM_DISPATCH_TILE(d->solver, adam, REGS_MMA)
+#undef REGS_MMA
+    info5[4] = regs;
+    return CCVM_OK;
+  }
   if (path == PATH_TC) {
     TcPlan P;
     plan_tc(*d, P);
@@ -739,14 +786,45 @@ static int solve_impl(const ccvm_solve_desc* d, const ccvm_epilogue_desc* epi, d
   if (rc) return rc;
   DeviceInfo di;
   if ((rc = device_info(di))) return rc;
-  const int path = choose_path(*d);
+  const int path = choose_path(*d, true);
   const bool adam = d->algorithm == CCVM_ALG_ADAM;
   const size_t sched_row_bytes = (size_t)d->iterations * SCHED_W * sizeof(float);
   StreamBuf sched_buf(st), qs_buf(st), accum_buf(st);
   SdeParams p;
   bool fused = false;
 
-  if (path == PATH_TC) {
+  if (path == PATH_MMA) {
+    MmaPlan MP;
+    plan_mma(*d, di, MP);
+    FusedTail f;
+    memset(&f, 0, sizeof(f));
+    const bool inline_sched = sched_row_bytes * (size_t)MP.ctas <= ((size_t)64 << 20) && getenv("CCVM_NO_SCHED_INLINE") == nullptr;
+    CUDA_TRY(sched_buf.alloc(inline_sched ? sched_row_bytes * MP.ctas : sched_row_bytes));
+    f.sched_inline = inline_sched ? 1 : 0;
+    f.sa = sched_args(d);
+    f.sched_scratch = sched_buf.as<float>();
+    if (!inline_sched) {
+      build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(f.sa, sched_buf.as<float>());
+      CUDA_TRY(cudaGetLastError());
+    }
+    fill_params(d, inline_sched ? nullptr : sched_buf.as<float>(), (d->n + 3) / 4, p);
+    if (epi && getenv("CCVM_NO_FUSE") == nullptr) {
+      StatsAccum* accum = nullptr;
+      if (result) {
+        CUDA_TRY(accum_buf.alloc(sizeof(StatsAccum)));
+        accum = accum_buf.as<StatsAccum>();
+        CUDA_TRY(cudaMemsetAsync(accum, 0, sizeof(StatsAccum), st));
+      }
+      if ((rc = plan_fused_tail(*d, epi, optimal, MP.threads, MP.smem, di.max_smem, (unsigned)MP.ctas, accum, result, f,
+                                MP.smem)))
+        return rc;
+      fused = true;
+    }
+#define LAUNCH_MMA(S, A) rc = launch_mma<S, A>(p, MP, f, st)
+    CCVM_DISPATCH_TILE(d->solver, adam, LAUNCH_MMA)
+#undef LAUNCH_MMA
+    if (rc) return rc;
+  } else if (path == PATH_TC) {
     CUDA_TRY(sched_buf.alloc(sched_row_bytes));
     build_schedule_kernel<<<(d->iterations + 127) / 128, 128, 0, st>>>(sched_args(d), sched_buf.as<float>());
     CUDA_TRY(cudaGetLastError());
@@ -1091,6 +1169,25 @@ __global__ void dump_noise_stream_kernel(uint32_t k0, uint32_t k1, uint32_t off_
       }
 }
 
+// Streams of the small-n tensor-core kernel (sde_kernel_mma.cuh): one thread per (trajectory pair, variable);
+// a Box-Muller pair per iteration and quadrature serves the two trajectories of the pair.
+__global__ void dump_noise_mma_kernel(uint32_t k0, uint32_t k1, uint32_t off_lo, long long traj_base, int n, int batch,
+                                      int iterations, int K, float* __restrict__ noise) {
+  const int pairs = (batch + 1) / 2;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= pairs * n) return;
+  const int pr = idx % pairs, v = idx / pairs;
+  NoiseStream rs = stream_init(k0, k1, off_lo, (unsigned long long)(traj_base + 2 * (long long)pr) >> 1,
+                               (uint32_t)v | MMA_STREAM_TAG);
+  for (int t = 0; t < iterations; ++t)
+    for (int q = 0; q < K; ++q) {
+      const pf2 w = stream_normal_pair(rs);
+      float* dst = noise + (((size_t)t * K + q) * n + v) * (size_t)batch + 2 * pr;
+      dst[0] = w.x;
+      if (2 * pr + 1 < batch) dst[1] = w.y;
+    }
+}
+
 extern "C" int ccvm_dump_noise(const ccvm_solve_desc* d, float* noise, void* stream) {
   if (!d || !noise) return fail(CCVM_E_INVALID, "bad argument to ccvm_dump_noise");
   if (d->n < 1 || d->batch < 1 || d->iterations < 1) return fail(CCVM_E_INVALID, "n, batch and iterations must be >= 1");
@@ -1100,8 +1197,14 @@ extern "C" int ccvm_dump_noise(const ccvm_solve_desc* d, float* noise, void* str
   const uint32_t k0 = (uint32_t)d->seed, k1 = (uint32_t)(d->seed >> 32) ^ (uint32_t)(d->offset >> 32);
   cudaStream_t st = (cudaStream_t)stream;
   // the generator ccvm_solve(desc) would use: counter mode on the tcgen05 path, streams on the tiled SIMT path
-  const bool stream_mode = CCVM_SIMT_RNG && choose_path(*d) != PATH_TC;
-  if (stream_mode) {
+  const int path = choose_path(*d, true);
+  const bool stream_mode = CCVM_SIMT_RNG && path != PATH_TC;
+  if (path == PATH_MMA) {
+    if (d->traj_base & 1) return fail(CCVM_E_INVALID, "traj_base must be even (noise streams belong to trajectory pairs)");
+    const int total = ((d->batch + 1) / 2) * d->n;
+    dump_noise_mma_kernel<<<(total + 127) / 128, 128, 0, st>>>(k0, k1, (uint32_t)d->offset, d->traj_base, d->n, d->batch,
+                                                              d->iterations, K, noise);
+  } else if (stream_mode) {
     if (d->traj_base & 1) return fail(CCVM_E_INVALID, "traj_base must be even (noise streams belong to trajectory pairs)");
     const int total = ((d->batch + 1) / 2) * cg_count;
     dump_noise_stream_kernel<<<(total + 127) / 128, 128, 0, st>>>(k0, k1, (uint32_t)d->offset, d->traj_base, d->n, d->batch,

@@ -111,6 +111,18 @@ int launch_tc(const SdeParams& p, const TcParams& tc, const TcPlan& P, const TcM
 template <int SOLVER, bool ADAM>
 int regs_tc(int version);
 
+// ---- small-n tensor-core kernel (sde_kernel_mma.cuh): contraction on tcgen05 with Qs^T resident in TMEM
+struct MmaPlan {
+  int nbp;     // trajectory pairs per warpgroup (7 or 8): a CTA advances 4 nbp trajectories
+  int kd, tcols;       // MmaLaunch
+  int ctas, threads;
+  size_t smem;
+};
+template <int SOLVER, bool ADAM>
+int launch_mma(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStream_t st);
+template <int SOLVER, bool ADAM>
+int regs_mma(int nbp);
+
 // dispatch on run-time (solver, algorithm): `CALL` is a macro taking (SOLVER, ADAM)
 #define CCVM_DISPATCH_TILE(solver, adam, CALL)                 \
   switch ((solver) * 2 + ((adam) ? 1 : 0)) {                   \
