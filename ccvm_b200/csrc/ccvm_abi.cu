@@ -140,17 +140,19 @@ static bool tc_eligible(const ccvm_solve_desc& d) {
   return tc_size_rule(d);
 }
 
-// Small-n tensor-core kernel (sde_kernel_mma.cuh): single-instance launches in production (Philox) mode whose
-// batch fills the SMs with 28-32 trajectories each -- there the register-tile kernels are issue-bound on the
-// contraction's FFMA2 stream and the tensor core takes it off the SIMT pipes.  Below ~48 variables most TMEM
-// lanes of the 128-row MMA idle and the tiled kernel wins; noise replay, evolution sampling and batched
-// (many-instance) launches stay on the tiled kernels.  CCVM_MMA=0 / 1 overrides the size rule.
+// Small-n tensor-core kernel (sde_kernel_mma.cuh): single-instance launches in production (Philox) mode whose batch
+// gives every SM a few dozen trajectories.  There the register-tile kernels are issue-bound on the contraction's
+// FFMA2 stream; the tensor core takes it off the SIMT pipes: measured at B = 4096 (profiles/r2y_*): 1.2-1.5x at
+// n = 40, 1.5-1.7x at n = 70, 3.0-3.7x at n = 100 ... 128; below ~40 variables the ~0.6 us handshake per iteration
+// (mbarrier -> MMA -> commit -> tcgen05.ld) is longer than the whole tiled iteration and the tiled kernel wins.
+// Noise replay, evolution sampling and batched (many-instance) launches stay on the tiled kernels.
+// CCVM_MMA=0 / 1 overrides the size rule ("1": whenever the kernel can run).
 static bool mma_eligible(const ccvm_solve_desc& d) {
   if (d.n > 128 || d.rng_mode != CCVM_RNG_PHILOX || d.evolution_step > 0) return false;
   if (const char* e = getenv("CCVM_MMA")) {
     if (e[0] != 'a') return atoi(e) != 0;
   }
-  return false;   // (being tuned: opt-in)
+  return d.n >= 40 && d.batch >= 2048;
 }
 
 static int choose_path(const ccvm_solve_desc& d, bool single_launch = false) {
@@ -263,20 +265,24 @@ static int plan_tmem(const ccvm_solve_desc& d, const DeviceInfo& di, int path, T
   return CCVM_OK;
 }
 
-// Launch geometry of the small-n tensor-core kernel: a CTA advances 4 nbp trajectories (two warpgroups of nbp
-// pairs); nbp = 7 or 8, whichever needs fewer waves of CTAs (ties: 7, less work per thread).
+// Launch geometry of the small-n tensor-core kernel: a CTA advances 4 nbp trajectories (two warpgroups of nbp pairs,
+// nbp <= 8): the smallest nbp that needs the fewest waves of CTAs (B = 4096 on 148 SMs: nbp = 7, 147 CTAs).
 static void plan_mma(const ccvm_solve_desc& d, const DeviceInfo& di, MmaPlan& P) {
   auto waves = [&](int nbp) {
     const long long ctas = ((long long)d.batch + 4 * nbp - 1) / (4 * nbp);
     return (ctas + di.sms - 1) / di.sms;
   };
-  P.nbp = waves(8) < waves(7) ? 8 : 7;
+  P.nbp = 8;
+  for (int nbp = 7; nbp >= 1; --nbp)
+    if (waves(nbp) <= waves(P.nbp)) P.nbp = nbp;
   if (const char* e = getenv("CCVM_MMA_NBP")) {
     const int v = atoi(e);
-    if (v == 7 || v == 8) P.nbp = v;
+    if (v >= 1 && v <= 8) P.nbp = v;
   }
-  P.kd = ((d.n + 1 + 7) / 8) * 8;
-  P.tcols = 512;
+  P.kd = ((d.n + 15) / 16) * 16;
+  P.tcols = 256;
+  P.ipl = (((d.n + 3) / 4) * P.nbp + 31) / 32;
+  if (P.ipl < 2) P.ipl = 2;
   P.threads = MMA_THREADS;
   P.ctas = (int)(((long long)d.batch + 4 * P.nbp - 1) / (4 * P.nbp));
   P.smem = mma_loop_smem_bytes();
@@ -541,7 +547,7 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
     info5[1] = P.ctas;
     info5[2] = 4 * P.nbp;
     info5[3] = (int)P.smem;
-#define REGS_MMA(S, A) regs = regs_mma<S, A>(P.nbp)
+#define REGS_MMA(S, A) regs = regs_mma<S, A>(P.ipl)
     CCVM_DISPATCH_TILE(d->solver, adam, REGS_MMA)
 #undef REGS_MMA
     info5[4] = regs;
@@ -1197,7 +1203,10 @@ extern "C" int ccvm_dump_noise(const ccvm_solve_desc* d, float* noise, void* str
   const uint32_t k0 = (uint32_t)d->seed, k1 = (uint32_t)(d->seed >> 32) ^ (uint32_t)(d->offset >> 32);
   cudaStream_t st = (cudaStream_t)stream;
   // the generator ccvm_solve(desc) would use: counter mode on the tcgen05 path, streams on the tiled SIMT path
-  const int path = choose_path(*d, true);
+  ccvm_solve_desc launch = *d;   // the launch whose draws are wanted (noise_batch: its batch, when this is a slice)
+  launch.rng_mode = CCVM_RNG_PHILOX;
+  if (d->noise_batch > 0 && d->noise_batch <= 0x7fffffff) launch.batch = (int32_t)d->noise_batch;
+  const int path = choose_path(launch, true);
   const bool stream_mode = CCVM_SIMT_RNG && path != PATH_TC;
   if (path == PATH_MMA) {
     if (d->traj_base & 1) return fail(CCVM_E_INVALID, "traj_base must be even (noise streams belong to trajectory pairs)");

@@ -9,21 +9,25 @@
 // instructions (636 of 1154 per warp-iteration for DL + Adam at N = 70), so no code shape gets it far
 // beyond ~0.5 of the FP32 FMA peak.  Here the contraction leaves the SIMT pipes altogether:
 //
-//   D[v][b] = sum_k Qs[k][v] x_b[k] + h_v        (v: variable = MMA row, b: trajectory = MMA column)
+//   D[v][b] = sum_k Qs[k][v] x_b[k]        (v: variable = MMA row, b: trajectory = MMA column)
 //
-//   * A = Qs^T (hi, lo) with the affine term h as one extra K column -- CONSTANT for the whole run -- is written
-//     ONCE into tensor memory and stays there (tcgen05.mma with the A operand in TMEM: no shared-memory read of
-//     the 128 x K operand per MMA, which is what a 16-column MMA would otherwise be bound by);
+//   * operands are FP16 PAIRS: x sigma = hi + lo, Qs tau = hi + lo with hi = fp16(.), lo = fp16(. - hi) and sigma, tau
+//     powers of two that put the largest magnitude of each operand near 2^13 (x: the clamp bound S, or 2^5
+//     headroom above it for the unclamped DL amplitudes, saturating); D = Alo.Bhi + Ahi.Blo + Ahi.Bhi keeps
+//     ~22 bits of every product like 3xTF32 does, but an FP16 MMA contracts K = 16 per instruction: half the
+//     instructions (every tcgen05.mma costs ~20 cycles at these tiny N, measured, and the loop was bound by them);
+//   * A = Qs^T (hi | lo) -- CONSTANT for the whole run -- is written ONCE into tensor memory and stays there
+//     (tcgen05.mma with the A operand in TMEM: no shared-memory read of the 128 x K operand per MMA);
 //   * B = the contraction input of 16 trajectories per warpgroup (hi, lo; K-major, no swizzle, 144-byte
 //     K stride so that a warp's stores are conflict-free), rewritten by the update threads every iteration:
 //     a few KB of shared memory;
-//   * per warpgroup and iteration one lane of warp 8 issues  D = Alo.Bhi + Ahi.Blo + Ahi.Bhi  (3 x K/8
-//     tcgen05.mma kind::tf32, M = 128, N = 16 or 32) and commits to an mbarrier;
+//   * per warpgroup and iteration one elected lane of warp 8 issues 3 x K/16 tcgen05.mma kind::f16 (M = 128,
+//     N = 16 or 32) and commits to an mbarrier;
 //   * thread (warpgroup g, TMEM lane m) owns ONE variable for the 14-16 trajectories of its warpgroup: it
 //     draws their noise and the drift-independent part of the step while the MMAs run, reads its row of D
-//     with one tcgen05.ld, finishes the step, splits the new contraction input into (hi, lo) and stores it
-//     into B; an mbarrier (128 arrivals) hands the tile back to the issuer.  Two warpgroups per CTA run out
-//     of phase on the same four schedulers.
+//     with one tcgen05.ld, rescales it and adds the affine term h_v, finishes the step, splits the new contraction
+//     input into (hi, lo) and stores it into B; an mbarrier (128 arrivals) hands the tile back to the issuer.
+//     Two warpgroups per CTA run out of phase on the same four schedulers.
 //
 // Variables are dealt to the four TMEM lane quadrants round-robin (v = 4 lane + quadrant), so that the four
 // warps of a warpgroup carry the same load; 70 variables occupy 18 lanes of every warp.
@@ -42,30 +46,26 @@ namespace ccvm {
 #endif
 constexpr int MMA_ISSUERS = CCVM_MMA_ISSUERS;   // 1: warp 8 serves both warpgroups; 2: warp 8 + g serves warpgroup g
 constexpr int MMA_THREADS = 256 + 32 * MMA_ISSUERS;   // warps 0-3, 4-7: two update warpgroups; then the MMA issuer(s)
-constexpr int MMA_KD_MAX = 136;           // K extent: n + 1 (affine column), rounded up to 8
+constexpr int MMA_KD_MAX = 128;           // K extent: n rounded up to 16 (one FP16 MMA contracts 16)
 constexpr int MMA_LBO = 144;              // bytes between the two 16-byte K chunks of a core matrix pair (128 + 16:
-                                          // 32 consecutive K positions land in 32 different banks)
-constexpr int MMA_SBO = (MMA_KD_MAX / 4) * MMA_LBO;   // bytes between 8-row groups (compile-time: immediates)
-constexpr int MMA_TILE_BYTES = 4 * MMA_SBO;           // one B tile: up to 32 rows (DL: 16 c rows + 16 s rows)
-#ifndef CCVM_MMA_NACC
-#define CCVM_MMA_NACC 1
-#endif
-constexpr int MMA_NACC = CCVM_MMA_NACC;   // independent accumulators per warpgroup: consecutive MMAs of a chain into ONE
-                                          // accumulator serialise on its read-modify-write (~21 cycles per 16-column
-                                          // MMA measured, against a floor of 8), so the MMAs rotate over NACC of them
-                                          // and the update thread adds the partial sums
-constexpr int MMA_D_COLS = 2 * 3 * 32;    // TMEM columns [0, 192): [warpgroup][accumulator][32]
+                                          // 32 consecutive K positions land in different banks)
+constexpr int MMA_SBO = (MMA_KD_MAX / 8) * MMA_LBO;   // bytes between 8-row groups (compile-time: immediates)
+constexpr int MMA_TILE_BYTES = 8 * MMA_SBO;           // one warpgroup's B tile: rows [hi | lo], up to 2 x 32 (DL: 16 c + 16 s)
+constexpr int MMA_D_COLS = 64;            // TMEM columns [0, 64): the two warpgroups' accumulators (32 each)
+constexpr int MMA_SCRATCH_ITEMS = 256;    // per warp and quadrature: float2 slots of the row -> item redistribution
 constexpr uint32_t MMA_STREAM_TAG = 0x40000000u;      // keeps these noise streams apart from the column-group streams
 
-__host__ __device__ inline size_t mma_loop_smem_bytes() { return 128 * sizeof(float) + 128 + 4 * (size_t)MMA_TILE_BYTES; }
+__host__ __device__ inline size_t mma_loop_smem_bytes() {
+  return 256 * sizeof(float) + 128 + 2 * (size_t)MMA_TILE_BYTES + (size_t)8 * 2 * MMA_SCRATCH_ITEMS * 8;
+}
 
-// D[tmem] (+)= A[tmem] . B[smem]^T, A = 128 x 8 TF32 in tensor memory (lane = row, column = k)
-__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[tmem] . B[smem]^T, A = 128 x 16 FP16 in tensor memory (lane = row, 32-bit column = two k)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -91,6 +91,32 @@ __device__ __forceinline__ void tmem_ld_row32(uint32_t addr, float (&r)[32]) {
       : "r"(addr));
 #pragma unroll
   for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(u[i]);
+}
+
+// FP16 split of a scaled value pair: hi = fp16(x) (saturating: an unclamped amplitude beyond the headroom must not
+// become Inf), lo = fp16(x - hi); both halves of a register: .x in the low 16 bits
+__device__ __forceinline__ uint32_t f16x2_sat(float lo_half, float hi_half) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+  return r;
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t h2) {
+  float r;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(r) : "r"(h2));
+  return r;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t h2) {
+  float r;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(r) : "r"(h2));
+  return r;
+}
+// largest power of two p with v p < 2^(e + 1)  (v > 0 finite; 1 for v = 0)
+__device__ __forceinline__ float pow2_scale(float v, int e) {
+  if (!(v > 0.f)) return 1.f;
+  const int ev = (int)((__float_as_uint(v) >> 23) & 0xffu) - 127;
+  int k = e - ev;
+  k = k < -60 ? -60 : k > 60 ? 60 : k;
+  return __uint_as_float((uint32_t)(k + 127) << 23);
 }
 
 // Adam transform of one gradient pair (dl_solver.py:699-727 and siblings): adam_tile4 of sde_kernel_tmem.cuh
@@ -159,8 +185,9 @@ __device__ long long g_mma_trace[32 * 8];
 #endif
 
 struct MmaLaunch {
-  int kd;      // K extent of the contraction: n + 1 rounded up to a multiple of 8
-  int tcols;   // TMEM columns to allocate (power of two >= MMA_D_COLS + 2 kd)
+  int kd;      // K extent of the contraction: n rounded up to a multiple of 16
+  int tcols;   // TMEM columns to allocate (power of two >= MMA_D_COLS + kd)
+  int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
 };
 
 // Variables are dealt to the four TMEM lane quadrants round-robin: v = 4 i + q sits in lane i of quadrant q and at
@@ -172,22 +199,28 @@ __device__ __forceinline__ int mma_koff(int n, int q) {
   return o;
 }
 
-// NBP: trajectory pairs per warpgroup (7 or 8; a CTA advances 4 NBP trajectories)
-template <int SOLVER, bool ADAM, int NBP>
+// IPL: (variable, trajectory pair) items per lane.  A warp reads the rows of its TMEM lane quadrant (one variable per
+// lane, 18 of 32 lanes at n = 70) and deals the values out again through shared memory, so that EVERY lane owns
+// IPL items for the whole run (n = 70, 7 pairs: 126 items on 32 x 4 slots) -- the elementwise work, two thirds of it
+// the noise, is the bound of this kernel and would otherwise run at 56 % lane occupancy.
+template <int SOLVER, bool ADAM, int IPL>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
     sde_mma_kernel(const SdeParams p, const MmaLaunch L, const FusedTail f) {
   constexpr int K = SolverTraits<SOLVER>::K;
-  constexpr int NR = 16 * K;   // B rows = D columns per warpgroup (DL: c rows 0-15, s rows 16-31)
+  constexpr int NR = 16 * K;   // B rows per half (hi | lo) and warpgroup (DL: c rows 0-15, s rows 16-31)
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) unsigned long long bars[4];
   __shared__ uint32_t tmem_slot;
+  __shared__ unsigned int s_max[2];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int N = p.n, T = p.iterations, KD = L.kd;
+  const int N = p.n, T = p.iterations, KD = L.kd, NBP = L.nbp;
   const int cta = blockIdx.x;
   float* av = smem;                                                    // [128] alpha_v
-  const uint32_t tiles = (smem_u32(smem) + 128 * 4 + 127u) & ~127u;    // [warpgroup][hi | lo] B tiles
+  float* hv = smem + 128;                                              // [128] affine term h_v
+  const uint32_t tiles = (smem_u32(smem) + 256 * 4 + 127u) & ~127u;    // [warpgroup] B tiles, rows [hi | lo]
   uint8_t* tiles_g = reinterpret_cast<uint8_t*>(smem) + (tiles - smem_u32(smem));
+  float2* scratch = reinterpret_cast<float2*>(tiles_g + 2 * MMA_TILE_BYTES);   // [warp][K][MMA_SCRATCH_ITEMS]
   const uint32_t bar0 = smem_u32(bars);
   auto ready_bar = [&](int g) { return bar0 + 8u * g; };       // B tile of warpgroup g written (128 arrivals)
   auto done_bar = [&](int g) { return bar0 + 8u * (2 + g); };  // accumulator of warpgroup g complete (tcgen05.commit)
@@ -200,6 +233,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     mbar_init(done_bar(0), 1);
     mbar_init(done_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_max[0] = s_max[1] = 0u;
   }
   if (warp == 8) tmem_alloc(&tmem_slot, L.tcols);
   const float* sched = p.sched;
@@ -210,58 +244,74 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   }
   for (int j = tid; j < 128; j += MMA_THREADS)
     av[j] = j < N ? p.a_half / (p.drift_s_vec ? p.drift_s_vec[j] : p.drift_s) : 0.f;
-  for (int i = tid; i < 4 * MMA_TILE_BYTES / 16; i += MMA_THREADS)
+  for (int i = tid; i < 2 * MMA_TILE_BYTES / 16; i += MMA_THREADS)
     reinterpret_cast<float4*>(tiles_g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  {
+    // operand scales: max |Qs| and max clamp bound (positive floats order like their bit patterns)
+    float mq = 0.f, ms = 0.f;
+    for (int idx = tid; idx < N * N; idx += MMA_THREADS) {
+      const int k = idx / N, j = idx - k * N;
+      mq = fmaxf(mq, fabsf(av[k] * av[j] * p.q[idx]));
+    }
+    for (int j = tid; j < N; j += MMA_THREADS) ms = fmaxf(ms, fabsf(p.clamp_s_vec ? p.clamp_s_vec[j] : p.clamp_s));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mq = fmaxf(mq, __shfl_xor_sync(0xffffffffu, mq, o));
+      ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, o));
+    }
+    if (lane == 0) {
+      atomicMax(&s_max[0], __float_as_uint(mq));
+      atomicMax(&s_max[1], __float_as_uint(ms));
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  const int PB = N;   // K position of the affine column
+  // Qs tau < 2^14; x sigma < 2^14 for the clamped inputs (Langevin, PumpedLangevin, MF: |x| <= S), S sigma < 2^9 for
+  // the unclamped DL amplitudes (FP16 saturates at 65504: 2^7 S, far outside the dynamics)
+  const float tau = pow2_scale(__uint_as_float(s_max[0]), 13);
+  const float sigma = pow2_scale(__uint_as_float(s_max[1]), SOLVER == SOLVER_DL ? 8 : 13);
+  const float unscale = 1.f / (tau * sigma);   // exact: powers of two
 
   if (warp < 4) {
-    // warpgroup 0 writes A = Qs^T (hi | lo) into tensor memory: lane m = row of variable v = 4 (m % 32) + m / 32,
-    // column = K position P of input variable k = 4 (P % QW) + P / QW, column PB = h_v
+    // warpgroup 0 writes A = tau Qs^T (hi | lo) into tensor memory: lane m = row of variable v = 4 (m % 32) + m / 32,
+    // 32-bit column c = K positions 2 c (low half), 2 c + 1; K position P <-> input variable k (mma_koff)
     const int v = 4 * lane + warp;
     const bool valid = v < N;
-    float h = 0.f, aj = 0.f;
+    float aj = 0.f;
     if (valid) {
       float cs = 0.f;
       for (int i = 0; i < N; ++i) cs += p.q[i * N + v];
       aj = av[v];
-      h = -aj * (p.b_half * cs + p.v[v]);
+      hv[v] = -aj * (p.b_half * cs + p.v[v]);
     }
     const int o1 = mma_koff(N, 1), o2 = mma_koff(N, 2), o3 = mma_koff(N, 3);
     const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16) + MMA_D_COLS;
-    for (int c4 = 0; c4 < KD / 4; ++c4) {
-      float hi[4], lo[4];
+    for (int c4 = 0; c4 < KD / 8; ++c4) {
+      uint32_t hi[4], lo[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int P = 4 * c4 + e;
-        float val = 0.f;
-        if (valid) {
-          if (P < PB) {
+        float val[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int P = 8 * c4 + 2 * e + u;
+          val[u] = 0.f;
+          if (valid && P < N) {
             const int q = P >= o3 ? 3 : P >= o2 ? 2 : P >= o1 ? 1 : 0;
             const int k = 4 * (P - (q == 3 ? o3 : q == 2 ? o2 : q == 1 ? o1 : 0)) + q;
-            val = -av[k] * aj * p.q[k * N + v];
-          } else if (P == PB) {
-            val = h;
+            val[u] = (-av[k] * aj * p.q[k * N + v]) * tau;
           }
         }
-        hi[e] = tf32_rna(val);
-        lo[e] = val - hi[e];
+        hi[e] = f16x2_sat(val[0], val[1]);
+        lo[e] = f16x2_sat(val[0] - f16_lo_to_f32(hi[e]), val[1] - f16_hi_to_f32(hi[e]));
       }
-      tmem_st4(tl + 4 * c4, hi[0], hi[1], hi[2], hi[3]);
-      tmem_st4(tl + KD + 4 * c4, lo[0], lo[1], lo[2], lo[3]);
+      tmem_st4(tl + 4 * c4, __uint_as_float(hi[0]), __uint_as_float(hi[1]), __uint_as_float(hi[2]), __uint_as_float(hi[3]));
+      tmem_st4(tl + KD / 2 + 4 * c4, __uint_as_float(lo[0]), __uint_as_float(lo[1]), __uint_as_float(lo[2]),
+               __uint_as_float(lo[3]));
     }
     tmem_wait_st();
-  } else if (warp < 8) {
-    // warpgroup 1: the constant 1 that meets the affine column (hi tiles of both warpgroups, every row)
-    const int r = tid - 128;
-    if (r < 2 * NR) {
-      const int g = r / NR, row = r % NR;
-      *reinterpret_cast<float*>(tiles_g + (size_t)g * 2 * MMA_TILE_BYTES + (row >> 3) * MMA_SBO + (row & 7) * 16 +
-                                (PB >> 2) * MMA_LBO + (PB & 3) * 4) = 1.f;
-    }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -273,11 +323,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     // ================================================================ MMA issuer
     // The whole warp stays converged and ONE elected lane issues (elect.sync): in a divergent `if (lane == 0)`
     // ptxas wraps every tcgen05.mma into an ELECT / BRA.U.ANY waterfall (~7 instructions and a branch per MMA:
-    // measured ~35 cycles each, 2 x 30 MMAs per iteration through one thread = half of the iteration).
-    // instruction descriptor: D = F32, A = B = TF32, K-major, M = 128, N = NR
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int KS = KD / 8;
-    const uint32_t a_hi = tbase + MMA_D_COLS, a_lo = a_hi + KD;
+    // measured ~35 cycles each).  Per k-step of 16:  D += Alo . Bhi^T + Ahi . Blo^T + Ahi . Bhi^T  (small terms first).
+    // (Contracting [Bhi | Blo] against Ahi in ONE instruction of twice the N was measured: same tensor time -- it is
+    // proportional to the columns contracted, ~28 cycles per 16 columns and k-step -- and more work for the threads.)
+    // instruction descriptor: D = F32, A = B = F16, K-major, M = 128, N = NR
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const int KS = KD / 16;
+    const uint32_t a_hi = tbase + MMA_D_COLS, a_lo = a_hi + KD / 2;
     // whichever warpgroup has its tile ready is served first (non-blocking tests: the two run out of phase)
     int it[2] = {0, 0};
     uint32_t spins = 0;
@@ -295,15 +347,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         tc_fence_after();
         MMA_STAMP(g == 0 && lane == 0, it[g], 6)
         if (elect_one()) {
-          const uint32_t d_tmem = tbase + g * (3 * 32);
-          const uint64_t b_hi = umma_desc_k_none(tiles + g * 2 * MMA_TILE_BYTES);
-          const uint64_t b_lo = umma_desc_k_none(tiles + g * 2 * MMA_TILE_BYTES + MMA_TILE_BYTES);
+          const uint32_t d_tmem = tbase + g * 32;
+          const uint64_t b_hi = umma_desc_k_none(tiles + g * MMA_TILE_BYTES);
+          const uint64_t b_lo = umma_desc_k_none(tiles + g * MMA_TILE_BYTES + (NR / 8) * MMA_SBO);
           for (int ks = 0; ks < KS; ++ks) {
             const uint64_t adv = (uint64_t)(ks * (2 * MMA_LBO >> 4));   // two 16-byte K chunks per MMA
-            // MMA number 3 ks + i goes to accumulator (3 ks + i) % NACC; the first one into each overwrites
-            umma_tf32_ts(d_tmem + 32 * ((3 * ks + 0) % MMA_NACC), a_lo + 8 * ks, b_hi + adv, idesc, 3 * ks + 0 >= MMA_NACC);
-            umma_tf32_ts(d_tmem + 32 * ((3 * ks + 1) % MMA_NACC), a_hi + 8 * ks, b_lo + adv, idesc, 3 * ks + 1 >= MMA_NACC);
-            umma_tf32_ts(d_tmem + 32 * ((3 * ks + 2) % MMA_NACC), a_hi + 8 * ks, b_hi + adv, idesc, 3 * ks + 2 >= MMA_NACC);
+            umma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + adv, idesc, ks != 0);
+            umma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + adv, idesc, 1u);
+            umma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + adv, idesc, 1u);
           }
           umma_commit(done_bar(g));
         }
@@ -322,48 +373,69 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   } else {
     // ================================================================ update warpgroups
     const int g = warp >> 2, w4 = warp & 3;
-    const int v = 4 * lane + w4;                       // this thread's variable
-    const bool valid = v < N;
-    const int P = mma_koff(N, w4) + lane;              // its K position in the B tiles
+    const int cnt = mma_qcount(N, w4), koff = mma_koff(N, w4);   // this quadrant's variables v = 4 i + w4, i < cnt
+    const int n_items = cnt * NBP;                                // (variable, pair) items: e = i * NBP + pair
     const long long b0 = (long long)cta * per_cta + (long long)g * 2 * NBP;   // first trajectory of the warpgroup
-    const uint32_t tl = tbase + ((uint32_t)(w4 * 32) << 16) + g * (3 * 32);
-    uint8_t* xb = tiles_g + (size_t)g * 2 * MMA_TILE_BYTES + (P >> 2) * MMA_LBO + (P & 3) * 4;
-    const float sc = valid ? (p.clamp_s_vec ? p.clamp_s_vec[v] : p.clamp_s) : 0.f;
+    const uint32_t tl = tbase + ((uint32_t)(w4 * 32) << 16) + g * 32;
+    uint8_t* tile = tiles_g + (size_t)g * MMA_TILE_BYTES;
+    float2* sw = scratch + (size_t)warp * 2 * MMA_SCRATCH_ITEMS;
+    const pf2 usc = dup(unscale), sg2 = dup(sigma);
 
-    pf2 st0[NBP], st1[NBP];                  // c | mu, s | sigma   (x: trajectory 2 ip, y: 2 ip + 1)
-    pf2 m0[NBP], v0[NBP], m1[NBP], v1[NBP];  // Adam moments
-    pf2 W[NBP];                              // MF: noise of the current measurement
-    pf2 meas[NBP];
-    NoiseStream rs[NBP];
+    // lane L owns items e = 32 j + L (consecutive lanes read consecutive slots of the redistribution buffer)
+    int vj[IPL], prj[IPL];
+    bool okj[IPL];
+    uint8_t* xbj[IPL];
+    float hj[IPL], scj[IPL];
+    pf2 st0[IPL], st1[IPL];                  // c | mu, s | sigma   (x: trajectory 2 pair, y: 2 pair + 1)
+    pf2 m0[IPL], v0[IPL], m1[IPL], v1[IPL];  // Adam moments
+    pf2 W[IPL];                              // MF: noise of the current measurement
+    pf2 meas[IPL];
+    NoiseStream rs[IPL];
     const uint2 key = make_uint2(p.seed_lo, p.seed_hi ^ p.off_hi);
 #pragma unroll
-    for (int ip = 0; ip < NBP; ++ip) {
-      st0[ip] = dup(0.f);
-      st1[ip] = dup(SOLVER == SOLVER_MF ? 0.5f : 0.f);
-      m0[ip] = v0[ip] = m1[ip] = v1[ip] = dup(0.f);
-      W[ip] = meas[ip] = dup(0.f);
-      rs[ip] = stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + b0 + 2 * ip) >> 1,
-                           (uint32_t)(valid ? v : 0) | MMA_STREAM_TAG);
+    for (int j = 0; j < IPL; ++j) {
+      const int e = 32 * j + lane;
+      okj[j] = e < n_items;
+      const int i = okj[j] ? e / NBP : 0;
+      prj[j] = okj[j] ? e - i * NBP : 0;
+      vj[j] = 4 * i + w4;
+      // K position in the B tile; idle slots run the same code on zeros and store where it cannot matter: just past
+      // the K extent (the row groups are laid out for KD = 128, no MMA reads there), or for KD = 128 at a K position
+      // whose A column is zero (n <= P < KD; the value is finite: saturating conversion, clamped or cubic-saturated
+      // dynamics) -- no predicate, no branch around the stores
+      const int P = okj[j] ? koff + i : (KD < MMA_KD_MAX ? KD : N);
+      const int row = 2 * prj[j];
+      xbj[j] = tile + (P >> 3) * MMA_LBO + (P & 7) * 2 + (row >> 3) * MMA_SBO + (row & 7) * 16;
+      hj[j] = okj[j] ? hv[vj[j]] : 0.f;
+      scj[j] = okj[j] ? (p.clamp_s_vec ? p.clamp_s_vec[vj[j]] : p.clamp_s) : 0.f;
+      st0[j] = dup(0.f);
+      st1[j] = dup(SOLVER == SOLVER_MF ? 0.5f : 0.f);
+      m0[j] = v0[j] = m1[j] = v1[j] = dup(0.f);
+      W[j] = meas[j] = dup(0.f);
+      rs[j] = stream_init(key.x, key.y, p.off_lo, (unsigned long long)(p.traj_base + b0 + 2 * prj[j]) >> 1,
+                          (uint32_t)(okj[j] ? vj[j] : 0) | MMA_STREAM_TAG);
     }
-    // contraction input of row `row` (trajectory index inside the warpgroup, + 16 for the s quadrature)
-    auto stage = [&](int row, float x) {
-      const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);   // exact TF32 head, lo = the rest
-      uint8_t* dst = xb + (row >> 3) * MMA_SBO + (row & 7) * 16;
-      *reinterpret_cast<float*>(dst) = hi;
-      *reinterpret_cast<float*>(dst + MMA_TILE_BYTES) = x - hi;
+    // contraction input of an item's trajectory pair (rows 2 pair, 2 pair + 1 of the hi half; `quad` = 1: the s rows):
+    // scaled, split into FP16 (hi, lo) and stored; the lo half of the tile starts NR rows further down
+    auto stage2 = [&](uint8_t* base, int quad, const pf2 x) {
+      const pf2 xs = mul2(x, sg2);
+      const uint32_t hi = f16x2_sat(xs.x, xs.y);
+      const uint32_t lo = f16x2_sat(xs.x - f16_lo_to_f32(hi), xs.y - f16_hi_to_f32(hi));
+      uint8_t* dst = base + quad * 2 * MMA_SBO;
+      *reinterpret_cast<unsigned short*>(dst) = (unsigned short)hi;
+      *reinterpret_cast<unsigned short*>(dst + 16) = (unsigned short)(hi >> 16);
+      *reinterpret_cast<unsigned short*>(dst + (NR / 8) * MMA_SBO) = (unsigned short)lo;
+      *reinterpret_cast<unsigned short*>(dst + (NR / 8) * MMA_SBO + 16) = (unsigned short)(lo >> 16);
     };
     const float4* sched4 = reinterpret_cast<const float4*>(sched);
     float4 sa = sched4[0], sb = sched4[1];
     if constexpr (SOLVER == SOLVER_MF) {
       // measurement of iteration 0 (mf_solver.py:551-554): mu = 0
 #pragma unroll
-      for (int ip = 0; ip < NBP; ++ip) {
-        W[ip] = stream_normal_pair(rs[ip]);
-        meas[ip] = clamp2(fma2(dup(sa.x), W[ip], st0[ip]), -sc, sc);
-        if (valid) {
-          stage(2 * ip, meas[ip].x);
-          stage(2 * ip + 1, meas[ip].y);
-        }
+      for (int j = 0; j < IPL; ++j) {
+        W[j] = stream_normal_pair(rs[j]);
+        meas[j] = clamp2(fma2(dup(sa.x), W[j], st0[j]), -scj[j], scj[j]);
+        stage2(xbj[j], 0, meas[j]);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -382,14 +454,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         const pf2 d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
         const pf2 mdt = dup(-p.dt), half = dup(0.5f);
 #pragma unroll
-        for (int ip = 0; ip < NBP; ++ip) {
-          const pf2 wc = stream_normal_pair(rs[ip]), ws = stream_normal_pair(rs[ip]);
-          const pf2 c = st0[ip], s = st1[ip];
+        for (int j = 0; j < IPL; ++j) {
+          const pf2 wc = stream_normal_pair(rs[j]), ws = stream_normal_pair(rs[j]);
+          const pf2 c = st0[j], s = st1[j];
           const pf2 r2 = fma2(c, c, mul2(s, s));
           const pf2 rt = sqrt2(add2(r2, half));
           const pf2 uc = fma2(r2, mdt, d1), us = fma2(r2, mdt, d2);
-          st0[ip] = add2(c, fma2(c, uc, mul2(mul2(rt, n1), wc)));
-          st1[ip] = add2(s, fma2(s, us, mul2(mul2(rt, n2), ws)));
+          st0[j] = add2(c, fma2(c, uc, mul2(mul2(rt, n1), wc)));
+          st1[j] = add2(s, fma2(s, us, mul2(mul2(rt, n2), ws)));
         }
       } else if constexpr (SOLVER == SOLVER_MF) {
         // mf_solver.py:158-233 with the constants folded (as in sde_kernel_tmem.cuh); sigma does not see the drift
@@ -397,110 +469,102 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         const pf2 dtp = dup(p.dt), mhalf = dup(-0.5f);
         const pf2 ng2 = dup(-p.g2), n3g2 = dup(-3.f * p.g2), p2g2 = dup(2.f * p.g2), two = dup(2.f);
 #pragma unroll
-        for (int ip = 0; ip < NBP; ++ip) {
-          const pf2 mu = st0[ip], sg = st1[ip];
+        for (int j = 0; j < IPL; ++j) {
+          const pf2 mu = st0[j], sg = st1[j];
           const pf2 mm = mul2(mu, mu);
           const pf2 a1 = fma2(mm, ng2, pr);
           const pf2 sh = add2(sg, mhalf);
-          st0[ip] = fma2(dtp, fma2(mul2(sh, W[ip]), sj, mul2(a1, mu)), mu);
+          st0[j] = fma2(dtp, fma2(mul2(sh, W[j]), sj, mul2(a1, mu)), mu);
           const pf2 a3 = fma2(mm, n3g2, pr);
           const pf2 t3 = fma2(mm, p2g2, opj);
           const pf2 inner = fma2(mul2(sh, sh), m2j, t3);
-          st1[ip] = fma2(dtp, fma2(mul2(a3, sg), two, inner), sg);
-          W[ip] = stream_normal_pair(rs[ip]);   // the measurement noise of iteration t + 1
+          st1[j] = fma2(dtp, fma2(mul2(a3, sg), two, inner), sg);
+          W[j] = stream_normal_pair(rs[j]);   // the measurement noise of iteration t + 1
         }
       } else {
         const pf2 sig = dup(p.sig), mdt = dup(-p.dt), d1 = dup(ca.y);
 #pragma unroll
-        for (int ip = 0; ip < NBP; ++ip) {
-          const pf2 w = stream_normal_pair(rs[ip]);
-          const pf2 c = st0[ip];
+        for (int j = 0; j < IPL; ++j) {
+          const pf2 w = stream_normal_pair(rs[j]);
+          const pf2 c = st0[j];
           pf2 pre = fma2(sig, w, c);
           if constexpr (SOLVER == SOLVER_PLV) pre = fma2(c, fma2(mul2(c, c), mdt, d1), pre);
-          st0[ip] = pre;
+          st0[j] = pre;
         }
       }
       AdamConsts ac;
       if constexpr (ADAM) ac = adam_consts(p, cb.y, cb.z);
 
-      // ---- the drift of this iteration
+      // ---- the drift of this iteration: this lane's ROW of D, dealt out to the lanes' items through the warp's
+      //      redistribution buffer
       MMA_STAMP(tid == 0, t, 1)
       mbar_wait(done_bar(g), (uint32_t)(t & 1));
       tc_fence_after();
       MMA_STAMP(tid == 0, t, 2)
-      float d[NR];
-      if constexpr (K == 2) tmem_ld_row32(tl, d);
-      else tmem_ld_row16(tl, d);
-      if constexpr (MMA_NACC > 1) {
-        float e[NR], e2[NR];
-        if constexpr (K == 2) tmem_ld_row32(tl + 32, e);
-        else tmem_ld_row16(tl + 32, e);
-        if constexpr (MMA_NACC > 2) {
-          if constexpr (K == 2) tmem_ld_row32(tl + 64, e2);
-          else tmem_ld_row16(tl + 64, e2);
-        }
+      {
+        float d[NR];
+        if constexpr (K == 2) tmem_ld_row32(tl, d);
+        else tmem_ld_row16(tl, d);
         tmem_wait_ld();
+        tc_fence_before();
+        if (lane < cnt) {
 #pragma unroll
-        for (int i = 0; i < 2 * NBP; i += 2) {
+          for (int pr = 0; pr < 8; ++pr) {
+            if (pr < NBP) {
 #pragma unroll
-          for (int h = 0; h < K; ++h) {
-            pf2 sum = add2(pk(d[16 * h + i], d[16 * h + i + 1]), pk(e[16 * h + i], e[16 * h + i + 1]));
-            if constexpr (MMA_NACC > 2) sum = add2(sum, pk(e2[16 * h + i], e2[16 * h + i + 1]));
-            d[16 * h + i] = sum.x;
-            d[16 * h + i + 1] = sum.y;
+              for (int h = 0; h < K; ++h)
+                sw[h * MMA_SCRATCH_ITEMS + lane * NBP + pr] = make_float2(d[16 * h + 2 * pr], d[16 * h + 2 * pr + 1]);
+            }
           }
         }
-      } else {
-        tmem_wait_ld();
       }
-      tc_fence_before();
+      __syncwarp();
+      pf2 gq[K][IPL];
+#pragma unroll
+      for (int j = 0; j < IPL; ++j)
+#pragma unroll
+        for (int h = 0; h < K; ++h) {
+          const float2 t2 = sw[h * MMA_SCRATCH_ITEMS + 32 * j + lane];
+          gq[h][j] = fma2(pk(t2.x, t2.y), usc, dup(hj[j]));
+        }
+      __syncwarp();
       MMA_STAMP(tid == 0, t, 3)
 
       // ---- finish the step and publish the next contraction input
       if constexpr (SOLVER == SOLVER_DL) {
         const pf2 gain = dup(ca.x);
 #pragma unroll
-        for (int ip = 0; ip < NBP; ++ip) {
-          pf2 gc = pk(d[2 * ip], d[2 * ip + 1]), gs = pk(d[16 + 2 * ip], d[16 + 2 * ip + 1]);
+        for (int j = 0; j < IPL; ++j) {
+          pf2 gc = gq[0][j], gs = gq[K - 1][j];
           if constexpr (ADAM) {
-            gc = adam_pair(gc, m0[ip], v0[ip], ac);
-            gs = adam_pair(gs, m1[ip], v1[ip], ac);
+            gc = adam_pair(gc, m0[j], v0[j], ac);
+            gs = adam_pair(gs, m1[j], v1[j], ac);
           }
-          st0[ip] = fma2(gain, gc, st0[ip]);
-          st1[ip] = fma2(gain, gs, st1[ip]);
-          if (valid) {
-            stage(2 * ip, st0[ip].x);
-            stage(2 * ip + 1, st0[ip].y);
-            stage(16 + 2 * ip, st1[ip].x);
-            stage(16 + 2 * ip + 1, st1[ip].y);
-          }
+          st0[j] = fma2(gain, gc, st0[j]);
+          st1[j] = fma2(gain, gs, st1[j]);
+          stage2(xbj[j], 0, st0[j]);
+          stage2(xbj[j], 1, st1[j]);
         }
       } else if constexpr (SOLVER == SOLVER_MF) {
         const pf2 fs = dup(p.fs), dtp = dup(p.dt);
 #pragma unroll
-        for (int ip = 0; ip < NBP; ++ip) {
-          pf2 gr = mul2(fs, pk(d[2 * ip], d[2 * ip + 1]));
-          if constexpr (ADAM) gr = adam_pair(gr, m0[ip], v0[ip], ac);
-          st0[ip] = fma2(dtp, gr, st0[ip]);
+        for (int j = 0; j < IPL; ++j) {
+          pf2 gr = mul2(fs, gq[0][j]);
+          if constexpr (ADAM) gr = adam_pair(gr, m0[j], v0[j], ac);
+          st0[j] = fma2(dtp, gr, st0[j]);
           if (t + 1 < T) {
-            meas[ip] = clamp2(fma2(dup(sa.x), W[ip], st0[ip]), -sc, sc);
-            if (valid) {
-              stage(2 * ip, meas[ip].x);
-              stage(2 * ip + 1, meas[ip].y);
-            }
+            meas[j] = clamp2(fma2(dup(sa.x), W[j], st0[j]), -scj[j], scj[j]);
+            stage2(xbj[j], 0, meas[j]);
           }
         }
       } else {
         const pf2 dtfs = dup(p.dtfs);
 #pragma unroll
-        for (int ip = 0; ip < NBP; ++ip) {
-          pf2 gr = pk(d[2 * ip], d[2 * ip + 1]);
-          if constexpr (ADAM) gr = adam_pair(gr, m0[ip], v0[ip], ac);
-          st0[ip] = clamp2(fma2(dtfs, gr, st0[ip]), -sc, sc);
-          if (valid) {
-            stage(2 * ip, st0[ip].x);
-            stage(2 * ip + 1, st0[ip].y);
-          }
+        for (int j = 0; j < IPL; ++j) {
+          pf2 gr = gq[0][j];
+          if constexpr (ADAM) gr = adam_pair(gr, m0[j], v0[j], ac);
+          st0[j] = clamp2(fma2(dtfs, gr, st0[j]), -scj[j], scj[j]);
+          stage2(xbj[j], 0, st0[j]);
         }
       }
       MMA_STAMP(tid == 0, t, 4)
@@ -512,26 +576,26 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     }
 
     // ---------------------------------------------------------------- results
-    if (valid) {
 #pragma unroll
-      for (int ip = 0; ip < NBP; ++ip)
+    for (int j = 0; j < IPL; ++j) {
+      if (!okj[j]) continue;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const long long b = b0 + 2 * ip + i;
-          if (b >= p.batch) continue;
-          const size_t o = (size_t)b * N + v;
-          const float x0 = i ? st0[ip].y : st0[ip].x, x1 = i ? st1[ip].y : st1[ip].x;
-          if constexpr (SOLVER == SOLVER_DL) {
-            p.out0[o] = clampf(x0, -sc, sc);
-            p.out1[o] = x1;
-          } else if constexpr (SOLVER == SOLVER_MF) {
-            p.out0[o] = x0;
-            p.out1[o] = i ? meas[ip].y : meas[ip].x;
-            p.out2[o] = x1;
-          } else {
-            p.out0[o] = x0;
-          }
+      for (int i = 0; i < 2; ++i) {
+        const long long b = b0 + 2 * prj[j] + i;
+        if (b >= p.batch) continue;
+        const size_t o = (size_t)b * N + vj[j];
+        const float x0 = i ? st0[j].y : st0[j].x, x1 = i ? st1[j].y : st1[j].x;
+        if constexpr (SOLVER == SOLVER_DL) {
+          p.out0[o] = clampf(x0, -scj[j], scj[j]);
+          p.out1[o] = x1;
+        } else if constexpr (SOLVER == SOLVER_MF) {
+          p.out0[o] = x0;
+          p.out1[o] = i ? meas[j].y : meas[j].x;
+          p.out2[o] = x1;
+        } else {
+          p.out0[o] = x0;
         }
+      }
     }
   }
 

@@ -113,7 +113,8 @@ int regs_tc(int version);
 
 // ---- small-n tensor-core kernel (sde_kernel_mma.cuh): contraction on tcgen05 with Qs^T resident in TMEM
 struct MmaPlan {
-  int nbp;     // trajectory pairs per warpgroup (7 or 8): a CTA advances 4 nbp trajectories
+  int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
+  int ipl;     // (variable, pair) items per lane compiled into the kernel variant: ceil(ceil(n / 4) nbp / 32), >= 2
   int kd, tcols;       // MmaLaunch
   int ctas, threads;
   size_t smem;
@@ -121,7 +122,7 @@ struct MmaPlan {
 template <int SOLVER, bool ADAM>
 int launch_mma(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStream_t st);
 template <int SOLVER, bool ADAM>
-int regs_mma(int nbp);
+int regs_mma(int ipl);
 
 // dispatch on run-time (solver, algorithm): `CALL` is a macro taking (SOLVER, ADAM)
 #define CCVM_DISPATCH_TILE(solver, adam, CALL)                 \

@@ -128,14 +128,17 @@ def solve(solver, algorithm, q, v, batch, iterations, **kwargs):
     return plan.outputs, plan.samples
 
 
-def dump_noise(solver, n, batch, iterations, seed, offset, traj_base=0, device=None):
+def dump_noise(solver, n, batch, iterations, seed, offset, traj_base=0, device=None, launch_batch=None):
     """The standard normals a Philox-mode solve with these (seed, offset, traj_base) draws, as a replay
-    tensor [iterations][K][n][batch] (``ccvm_dump_noise``): validation only."""
+    tensor [iterations][K][n][batch] (``ccvm_dump_noise``): validation only.  ``launch_batch``: batch of the launch
+    this is a slice of (the kernel family, and with it the generator, is chosen from the launch's batch)."""
     nat.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     d = nat.SolveDesc()
     d.solver, d.n, d.batch, d.iterations = solver, int(n), int(batch), int(iterations)
     d.seed, d.offset, d.traj_base = int(seed), int(offset), int(traj_base)
+    if launch_batch is not None:
+        d.noise_batch = int(launch_batch)
     k = 2 if solver == nat.SOLVER_DL else 1
     out = torch.empty((iterations, k, n, batch), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):

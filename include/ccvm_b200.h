@@ -123,6 +123,11 @@ int ccvm_solve(const ccvm_solve_desc* desc, void* stream);
  * Normal(0,1).sample((N,)).T, one [n][batch] slab per draw).  Replaying this tensor through the
  * reference arithmetic reproduces a production run, which pins the production kernel variants
  * (in-loop noise generation, compile-time column-group counts) to the oracle.
+ * Which generator a launch uses depends on the kernel family the library picks for it (noise streams per
+ * (trajectory pair, 4 variables) in the tiled kernels, per (trajectory pair, variable) in the small-n tensor-core
+ * kernel, counter mode on the n > 256 tensor-core path), and that choice depends on the batch of the LAUNCH: to
+ * dump a slice of a larger launch (batch trajectories from traj_base), put the launch's batch into
+ * desc->noise_batch (0: the launch is desc->batch trajectories).
  */
 int ccvm_dump_noise(const ccvm_solve_desc* desc, float* noise, void* stream);
 

@@ -27,6 +27,7 @@ KW = {
 
 @pytest.mark.parametrize("n,b", SHAPES)
 def test_pipe_kernels_match_plain_variant(monkeypatch, n, b):
+    monkeypatch.setenv("CCVM_MMA", "0")   # the tiled kernels (the tensor-core kernel has its own tests: test_gpu_mma.py)
     t = 24
     for k, (name, (sid, kw)) in enumerate(KW.items()):
         adam = (n + b + k) % 2 == 1

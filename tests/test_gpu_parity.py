@@ -163,8 +163,10 @@ def test_philox_reproducible_and_shard_invariant():
     assert torch.equal(torch.cat([a[0], bb[0]]), full[0])
 
 
-def test_philox_noise_is_standard_normal():
-    """With Q = V = 0 and a huge S, Langevin's c_T is sigma*sqrt(dt) * sum of T normals."""
+def test_philox_noise_is_standard_normal(monkeypatch):
+    """With Q = V = 0 and a huge S, Langevin's c_T is sigma*sqrt(dt) * sum of T normals (the column-group streams of the
+    tiled kernels; the tensor-core kernel's streams: test_gpu_mma.py)."""
+    monkeypatch.setenv("CCVM_MMA", "0")
     n, b, t = 64, 2048, 64
     q, v = torch.zeros(n, n), torch.zeros(n)
     outs, _ = E.solve(nat.SOLVER_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, s=1e6, dt=1.0 / t, sigma=1.0,

@@ -49,10 +49,12 @@ def test_run_time_pipe_and_hybrid_variants(solver, adam, n, b, t):
     parity_case(solver, adam, n, b, t, tol_of(solver, adam), philox=(99, n + b))
 
 
-# the launch geometry of the benchmark: N = 70, B = 4096 -> 147 CTAs of two 7-pair groups
+# the launch geometry of the benchmark on the TILED kernels (CCVM_MMA=0; the tensor-core kernel that serves this shape
+# by default is covered by test_gpu_mma.py): N = 70, B = 4096 -> 147 CTAs of two 7-pair groups
 @pytest.mark.parametrize("solver,adam", TILES)
 @pytest.mark.parametrize("mode", ["replay", "philox"])
-def test_benchmark_geometry(solver, adam, mode):
+def test_benchmark_geometry(monkeypatch, solver, adam, mode):
+    monkeypatch.setenv("CCVM_MMA", "0")
     info = launch_info(solver, adam, 70, 4096, 100)
     assert info["ctas"] == 147 and info["threads"] == 256 and info["traj_per_cta"] == 28
     parity_case(solver, adam, 70, 4096, 100, tol_of(solver, adam), philox=(7, 3) if mode == "philox" else None)

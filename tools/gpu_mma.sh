@@ -8,7 +8,7 @@ cat $out/check_first.jsonl; tail -5 $out/check_first.err
 timeout 600 python tools/mma_check.py --n ${CHECK_N:-70} > $out/check.jsonl 2>$out/check.err; echo "check rc=$?" | tee -a $out/rc.txt
 cat $out/check.jsonl; tail -5 $out/check.err
 for n in ${SIZES:-70}; do
-  timeout 300 python tools/quick_bench.py --n $n --reps 5 > $out/quick_n${n}_mma.jsonl 2>$out/quick_mma.err; echo "quick mma rc=$?" | tee -a $out/rc.txt
+  CCVM_MMA=1 timeout 300 python tools/quick_bench.py --n $n --reps 5 > $out/quick_n${n}_mma.jsonl 2>$out/quick_mma.err; echo "quick mma rc=$?" | tee -a $out/rc.txt
   CCVM_MMA=0 timeout 300 python tools/quick_bench.py --n $n --reps 5 > $out/quick_n${n}_tiled.jsonl 2>&1
   python - <<PY
 import json

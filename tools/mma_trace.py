@@ -5,6 +5,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["CCVM_MMA"] = "1"
 import torch  # noqa: E402
 from ccvm_b200 import engine as E, _native as nat  # noqa: E402
 from tools.quick_bench import synth  # noqa: E402
