@@ -362,7 +362,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         MMA_STAMP(g == 0 && lane == 0, it[g], 7)
         ++it[g];
       }
-      if ((++spins & 0xfffff) == 0) {   // a protocol bug must trap, not hang the device
+      if (spins != 0) __nanosleep(40);   // nothing was ready: leave the issue slots of this scheduler to the update warps
+      if ((++spins & 0xffff) == 0) {     // a protocol bug must trap, not hang the device
         const long long now = clock64();
         if (spin_start == 0) spin_start = now;
         else if (now - spin_start > 8000000000ll) __trap();

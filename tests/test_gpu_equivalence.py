@@ -19,9 +19,9 @@ SOLVERS = [s for s in G.ALL_LOOPS if f"{s}/seed0/70" in REF]
 ENGINE_SEEDS = (0, 1, 2)
 
 
-@pytest.mark.parametrize("route", ["many", "single"])
+@pytest.mark.parametrize("route", ["many", "single", "single-mma"])
 @pytest.mark.parametrize("name", SOLVERS)
-def test_statistically_equivalent_on_bundled_instances(name, route):
+def test_statistically_equivalent_on_bundled_instances(monkeypatch, name, route):
     """All eight loops (the _solve_adam ones on the first 10 instances of every size, with the
     AdamParameters of the reference's examples), through batched launches (solve_many) AND through
     one Solver.__call__ per instance (the single-launch kernel instantiations).
@@ -30,6 +30,12 @@ def test_statistically_equivalent_on_bundled_instances(name, route):
     loop about 4 % of the time (measured: tools/equivalence_null.py, engine vs engine).  The test runs three
     independent engine seeds and applies the criteria by majority (tools/equivalence_gpu.py::majority_gate)."""
     meta = REF["_meta"]
+    if route == "single-mma":
+        # the small-n tensor-core kernel (csrc/sde_kernel_mma.cuh) forced for every size of the bundled set (it serves
+        # n >= 40 at batch >= 2048 by default): the four _solve_adam loops here, all eight in
+        # profiles/r2y_equivalence_mma_kernel_single_3seeds.log
+        monkeypatch.setenv("CCVM_MMA", "1")
+        route = "single"
     if route == "single" and not name.endswith("_adam"):
         pytest.skip("300 single calls per solver and seed: run with tools/equivalence_gpu.py --route single")
     runs = []
