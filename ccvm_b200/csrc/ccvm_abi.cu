@@ -142,17 +142,24 @@ static bool tc_eligible(const ccvm_solve_desc& d) {
 
 // Small-n tensor-core kernel (sde_kernel_mma.cuh): single-instance launches in production (Philox) mode whose batch
 // gives every SM a few dozen trajectories.  There the register-tile kernels are issue-bound on the contraction's
-// FFMA2 stream; the tensor core takes it off the SIMT pipes: measured at B = 4096 (profiles/r2y_*): 1.2-1.5x at
-// n = 40, 1.5-1.7x at n = 70, 3.0-3.7x at n = 100 ... 128; below ~40 variables the ~0.6 us handshake per iteration
-// (mbarrier -> MMA -> commit -> tcgen05.ld) is longer than the whole tiled iteration and the tiled kernel wins.
-// Noise replay, evolution sampling and batched (many-instance) launches stay on the tiled kernels.
-// CCVM_MMA=0 / 1 overrides the size rule ("1": whenever the kernel can run).
+// FFMA2 stream; the tensor core takes it off the SIMT pipes.  Its iteration is latency-bound (~0.6-0.7 us: mbarrier ->
+// MMA -> commit -> tcgen05.ld per warpgroup) and hardly depends on the batch up to one wave of CTAs, while the tiled
+// kernel's time grows with the trajectories per SM and with n^2: measured crossovers (profiles/r2y_*, r2z_batch_crossover.txt;
+// tensor-core / tiled ms at T = 1500):
+//   n = 40:  B = 3000  Langevin 0.98 / 0.66, DL-adam 1.41 / 1.53;   B = 4096  0.97 / 1.11, 1.53 / 2.36
+//   n = 70:  B = 2048  Langevin 1.03 / 0.90, DL-adam 1.67 / 2.14;   B = 3000  1.06 / 1.58, 2.01 / 3.19;  B = 4096  1.07 / 1.59, 2.00 / 3.22
+//   n = 128: B = 2048  Langevin 1.25 / 2.59, DL-adam 2.23 / 4.94;   B = 4096  1.42 / 5.10, 3.61 / 9.88
+// Below ~40 variables the handshake is longer than the whole tiled iteration.  Noise replay, evolution sampling and
+// batched (many-instance) launches stay on the tiled kernels.  CCVM_MMA=0 / 1 overrides the rule ("1": whenever the
+// kernel can run).
 static bool mma_eligible(const ccvm_solve_desc& d) {
   if (d.n > 128 || d.rng_mode != CCVM_RNG_PHILOX || d.evolution_step > 0) return false;
   if (const char* e = getenv("CCVM_MMA")) {
     if (e[0] != 'a') return atoi(e) != 0;
   }
-  return d.n >= 40 && d.batch >= 2048;
+  if (d.n < 40) return false;
+  const int min_batch = (d.solver == CCVM_SOLVER_DL || d.n >= 96) ? 2048 : d.n >= 56 ? 2560 : 3584;
+  return d.batch >= min_batch;
 }
 
 static int choose_path(const ccvm_solve_desc& d, bool single_launch = false) {

@@ -1,7 +1,7 @@
 """The small-n tensor-core kernel (csrc/sde_kernel_mma.cuh: drift contraction on tcgen05 with FP16-split operands,
 Qs^T resident in tensor memory) against the oracle and against the tiled kernels.
 
-It serves single-instance Philox-mode launches with 40 <= n <= 128 and batch >= 2048 (CCVM_MMA=1 forces it for any
+It serves single-instance Philox-mode launches with 40 <= n <= 128 and batch >= 2048 ... 3584 (by n and solver; CCVM_MMA=1 forces it for any
 shape it can run, CCVM_MMA=0 disables it).  Same bar as every production kernel: the oracle replays the normals
 ``ccvm_dump_noise`` writes for the launch, per-trajectory objective within 1e-3 relative (2e-3 DL-adam; reference loops
 dl_solver.py:468-769, mf_solver.py:493-764, langevin_solver.py:368-561, pumped_langevin_solver.py:232-449)."""
@@ -31,7 +31,11 @@ def test_size_rule(monkeypatch):
     info = launch_info("dl", True, 70, 4096, 10)
     assert info["ctas"] == 147 and info["traj_per_cta"] == 28       # 148 SMs: 7 pairs per warpgroup
     assert launch_info("lv", False, 128, 2048, 10)["threads"] == 288
-    assert launch_info("lv", False, 40, 2048, 10)["threads"] == 288
+    assert launch_info("lv", False, 40, 4096, 10)["threads"] == 288
+    assert launch_info("lv", False, 40, 3000, 10)["threads"] != 288   # measured crossover of the K = 1 loops at n = 40: ~3600
+    assert launch_info("dl", False, 40, 2048, 10)["threads"] == 288
+    assert launch_info("mf", True, 70, 2560, 10)["threads"] == 288
+    assert launch_info("mf", True, 70, 2048, 10)["threads"] != 288
     assert launch_info("lv", False, 36, 4096, 10)["threads"] != 288   # too few variables: tiled kernel
     assert launch_info("lv", False, 70, 1000, 10)["threads"] != 288   # too few trajectories per SM
     assert launch_info("lv", False, 129, 4096, 10)["threads"] != 288  # hybrid kernel
@@ -41,7 +45,7 @@ def test_size_rule(monkeypatch):
 
 # the shapes the size rule selects: every tile, K extents 48 ... 128, 4 ... 8 pairs per warpgroup, 3 ... 7 items per lane
 @pytest.mark.parametrize("solver,adam", TILES)
-@pytest.mark.parametrize("n,b,t", [(40, 2048, 60), (64, 2300, 60), (70, 4096, 60), (100, 2048, 40), (128, 2240, 40)])
+@pytest.mark.parametrize("n,b,t", [(40, 3600, 60), (64, 2600, 60), (70, 4096, 60), (100, 2048, 40), (128, 2240, 40)])
 def test_production_parity_selected_shapes(solver, adam, n, b, t):
     assert launch_info(solver, adam, n, b, t)["threads"] == 288
     parity_case(solver, adam, n, b, t, tol_of(solver, adam), philox=(31, 7 * n + b))
@@ -77,21 +81,22 @@ def test_reproducible_and_shard_invariant():
     q, v, _ = instance(n, 2, 0.05)
     qg, vg = q.cuda(), v.cuda()
     kw = dict(s=0.5, pump=2.0, dt=0.002, sigma=0.5, feedback_scale=1.0, seed=11, offset=4)
-    full, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 4500, t, **kw)
+    full, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 5400, t, **kw)   # two waves of CTAs
     full = full[0].clone()
-    again, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 4500, t, **kw)
+    again, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 5400, t, **kw)
     assert torch.equal(full, again[0])
-    a, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 2050, t, traj_base=0, **kw)
-    bb, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 2450, t, traj_base=2050, **kw)
+    assert launch_info("plv", False, n, 2600, t)["threads"] == 288
+    a, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 2600, t, traj_base=0, **kw)
+    bb, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 2800, t, traj_base=2600, **kw)
     assert torch.equal(torch.cat([a[0], bb[0]]), full)
-    other, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 4500, t, **dict(kw, seed=12))
+    other, _ = E.solve(nat.SOLVER_PUMPED_LANGEVIN, nat.ALG_ORIGINAL, qg, vg, 5400, t, **dict(kw, seed=12))
     assert not torch.equal(full, other[0])
 
 
 def test_noise_is_standard_normal():
     """Q = V = 0 and a huge S: Langevin's c_T is sigma sqrt(dt) times a sum of T normals (the per-(pair, variable)
     streams of the tensor-core kernel)."""
-    n, b, t = 64, 2048, 64
+    n, b, t = 64, 2560, 64
     q, v = torch.zeros(n, n), torch.zeros(n)
     assert launch_info("lv", False, n, b, t)["threads"] == 288
     outs, _ = E.solve(nat.SOLVER_LANGEVIN, nat.ALG_ORIGINAL, q.cuda(), v.cuda(), b, t, s=1e6, dt=1.0 / t, sigma=1.0,
