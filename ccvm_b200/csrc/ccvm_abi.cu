@@ -291,6 +291,10 @@ static void plan_mma(const ccvm_solve_desc& d, const DeviceInfo& di, MmaPlan& P)
   P.ipl = (((d.n + 3) / 4) * P.nbp + 31) / 32;
   if (P.ipl < 2) P.ipl = 2;
   P.threads = MMA_THREADS;
+  // the two update warpgroups start half an iteration apart (sde_kernel_mma.cuh; profiles/r2z_issuer_protocol.txt);
+  // CCVM_MMA_STAGGER=0 releases them together
+  P.stagger = 1;
+  if (const char* e = getenv("CCVM_MMA_STAGGER")) P.stagger = atoi(e) != 0;
   P.ctas = (int)(((long long)d.batch + 4 * P.nbp - 1) / (4 * P.nbp));
   P.smem = mma_loop_smem_bytes();
 }

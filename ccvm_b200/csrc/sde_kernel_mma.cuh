@@ -44,8 +44,9 @@ namespace ccvm {
 #ifndef CCVM_MMA_ISSUERS
 #define CCVM_MMA_ISSUERS 1
 #endif
-constexpr int MMA_ISSUERS = CCVM_MMA_ISSUERS;   // 1: warp 8 serves both warpgroups; 2: warp 8 + g serves warpgroup g
-constexpr int MMA_THREADS = 256 + 32 * MMA_ISSUERS;   // warps 0-3, 4-7: two update warpgroups; then the MMA issuer(s)
+constexpr int MMA_ISSUERS = CCVM_MMA_ISSUERS;   // 1: one warp serves both warpgroups; 2: issuer warp g serves warpgroup g
+constexpr int MMA_UW = 8;                                  // update warps: two warpgroups of four
+constexpr int MMA_THREADS = 32 * (MMA_UW + MMA_ISSUERS);   // the update warps, then the MMA issuer(s)
 constexpr int MMA_KD_MAX = 128;           // K extent: n rounded up to 16 (one FP16 MMA contracts 16)
 constexpr int MMA_LBO = 144;              // bytes between the two 16-byte K chunks of a core matrix pair (128 + 16:
                                           // 32 consecutive K positions land in different banks)
@@ -56,7 +57,7 @@ constexpr int MMA_SCRATCH_ITEMS = 256;    // per warp and quadrature: float2 slo
 constexpr uint32_t MMA_STREAM_TAG = 0x40000000u;      // keeps these noise streams apart from the column-group streams
 
 __host__ __device__ inline size_t mma_loop_smem_bytes() {
-  return 256 * sizeof(float) + 128 + 2 * (size_t)MMA_TILE_BYTES + (size_t)8 * 2 * MMA_SCRATCH_ITEMS * 8;
+  return 256 * sizeof(float) + 128 + 2 * (size_t)MMA_TILE_BYTES + (size_t)MMA_UW * 2 * MMA_SCRATCH_ITEMS * 8;
 }
 
 // D[tmem] (+)= A[tmem] . B[smem]^T, A = 128 x 16 FP16 in tensor memory (lane = row, 32-bit column = two k)
@@ -151,19 +152,6 @@ __device__ __forceinline__ pf2 stream_normal_pair(NoiseStream& s) {
   return w;
 }
 
-// non-blocking: has the phase with this parity completed?
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, q;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-
 // one lane of a converged warp (elect.sync)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -176,10 +164,11 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 #ifdef CCVM_MMA_TRACE
-// development aid: clock64 stamps of CTA 0 (warpgroup 0 thread 0: slots 0-5, issuer: 6-7) for iterations 64 .. 95
-__device__ long long g_mma_trace[32 * 8];
+// development aid: clock64 stamps of CTA 0 (first thread of warpgroup g: slots 8 g + 0..5, issuer serving g: 8 g + 6, 7)
+// for iterations 64 .. 95
+__device__ long long g_mma_trace[32 * 16];
 #define MMA_STAMP(cond, t, slot)                                                          \
-  if ((cond) && blockIdx.x == 0 && (t) >= 64 && (t) < 96) g_mma_trace[((t) - 64) * 8 + (slot)] = clock64();
+  if ((cond) && blockIdx.x == 0 && (t) >= 64 && (t) < 96) g_mma_trace[((t) - 64) * 16 + (slot)] = clock64();
 #else
 #define MMA_STAMP(cond, t, slot)
 #endif
@@ -188,6 +177,7 @@ struct MmaLaunch {
   int kd;      // K extent of the contraction: n rounded up to a multiple of 16
   int tcols;   // TMEM columns to allocate (power of two >= MMA_D_COLS + kd)
   int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
+  int stagger; // warpgroup 1 starts half an iteration after warpgroup 0
 };
 
 // Variables are dealt to the four TMEM lane quadrants round-robin: v = 4 i + q sits in lane i of quadrant q and at
@@ -209,7 +199,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   constexpr int K = SolverTraits<SOLVER>::K;
   constexpr int NR = 16 * K;   // B rows per half (hi | lo) and warpgroup (DL: c rows 0-15, s rows 16-31)
   extern __shared__ __align__(16) float smem[];
-  __shared__ __align__(8) unsigned long long bars[4];
+  __shared__ __align__(8) unsigned long long bars[5];
   __shared__ uint32_t tmem_slot;
   __shared__ unsigned int s_max[2];
 
@@ -224,6 +214,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   const uint32_t bar0 = smem_u32(bars);
   auto ready_bar = [&](int g) { return bar0 + 8u * g; };       // B tile of warpgroup g written (128 arrivals)
   auto done_bar = [&](int g) { return bar0 + 8u * (2 + g); };  // accumulator of warpgroup g complete (tcgen05.commit)
+  const uint32_t phase_bar = bar0 + 8u * 4;                    // L.stagger: warpgroup 0 has read its first accumulator
 
   // ------------------------------------------------------------------ prologue
   const unsigned long long t_start = f.stats ? global_timer_ns() : 0ull;
@@ -232,10 +223,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     mbar_init(ready_bar(1), 128);
     mbar_init(done_bar(0), 1);
     mbar_init(done_bar(1), 1);
+    mbar_init(phase_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_max[0] = s_max[1] = 0u;
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, L.tcols);
+  if (warp == MMA_UW) tmem_alloc(&tmem_slot, L.tcols);
   const float* sched = p.sched;
   if (f.sched_inline) {
     float* mine = f.sched_scratch + (size_t)cta * p.iterations * SCHED_W;
@@ -319,7 +311,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   tc_fence_after();
 
   const long long per_cta = 4 * NBP;
-  if (warp >= 8) {
+  if (warp >= MMA_UW) {
     // ================================================================ MMA issuer
     // The whole warp stays converged and ONE elected lane issues (elect.sync): in a divergent `if (lane == 0)`
     // ptxas wraps every tcgen05.mma into an ELECT / BRA.U.ANY waterfall (~7 instructions and a branch per MMA:
@@ -330,45 +322,35 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int KS = KD / 16;
     const uint32_t a_hi = tbase + MMA_D_COLS, a_lo = a_hi + KD / 2;
-    // whichever warpgroup has its tile ready is served first (non-blocking tests: the two run out of phase)
-    int it[2] = {0, 0};
-    uint32_t spins = 0;
-    long long spin_start = 0;
-    while (it[0] < T || it[1] < T) {
+    auto issue = [&](int g) {
+      if (elect_one()) {
+        const uint32_t d_tmem = tbase + g * 32;
+        const uint64_t b_hi = umma_desc_k_none(tiles + g * MMA_TILE_BYTES);
+        const uint64_t b_lo = umma_desc_k_none(tiles + g * MMA_TILE_BYTES + (NR / 8) * MMA_SBO);
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * (2 * MMA_LBO >> 4));   // two 16-byte K chunks per MMA
+          umma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + adv, idesc, ks != 0);
+          umma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + adv, idesc, 1u);
+          umma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + adv, idesc, 1u);
+        }
+        umma_commit(done_bar(g));
+      }
+      __syncwarp();
+    };
+    // The warpgroups are served in STRICT ALTERNATION with blocking waits: mbarrier.try_wait suspends the warp (no issue
+    // slots taken from the update warps of its scheduler) and wakes within tens of cycles of the last arrival.  Polling
+    // both barriers with mbarrier.test_wait + __nanosleep ("whoever is ready first") left a ready tile waiting ~300
+    // cycles for the issuer: 3-8 % of every loop (profiles/r2z_issuer_protocol.txt).
+    for (int t = 0; t < T; ++t) {
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        if (it[g] >= T) continue;
-        if (MMA_ISSUERS == 2 && g != warp - 8) {
-          it[g] = T;
-          continue;
-        }
-        if (!__all_sync(0xffffffffu, mbar_test(ready_bar(g), (uint32_t)(it[g] & 1)))) continue;
-        spins = 0;
-        tc_fence_after();
-        MMA_STAMP(g == 0 && lane == 0, it[g], 6)
-        if (elect_one()) {
-          const uint32_t d_tmem = tbase + g * 32;
-          const uint64_t b_hi = umma_desc_k_none(tiles + g * MMA_TILE_BYTES);
-          const uint64_t b_lo = umma_desc_k_none(tiles + g * MMA_TILE_BYTES + (NR / 8) * MMA_SBO);
-          for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * (2 * MMA_LBO >> 4));   // two 16-byte K chunks per MMA
-            umma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + adv, idesc, ks != 0);
-            umma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + adv, idesc, 1u);
-            umma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + adv, idesc, 1u);
-          }
-          umma_commit(done_bar(g));
-        }
+        if (MMA_ISSUERS == 2 && g != warp - MMA_UW) continue;
+        mbar_wait(ready_bar(g), (uint32_t)(t & 1));
         __syncwarp();
-        MMA_STAMP(g == 0 && lane == 0, it[g], 7)
-        ++it[g];
-      }
-      if (spins != 0) __nanosleep(40);   // nothing was ready: leave the issue slots of this scheduler to the update warps
-      if ((++spins & 0xffff) == 0) {     // a protocol bug must trap, not hang the device
-        const long long now = clock64();
-        if (spin_start == 0) spin_start = now;
-        else if (now - spin_start > 8000000000ll) __trap();
-      } else if (spins == 1) {
-        spin_start = 0;
+        tc_fence_after();
+        MMA_STAMP(lane == 0, t, 8 * g + 6)
+        issue(g);
+        MMA_STAMP(lane == 0, t, 8 * g + 7)
       }
     }
   } else {
@@ -440,6 +422,14 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // L.stagger: the two warpgroups start HALF AN ITERATION apart (warpgroup 1 waits until warpgroup 0 has read its first
+    // accumulator).  The phase between them is not pinned by anything once the loop runs: where the MMA chain has slack
+    // (DL, the Adam tiles, MF at n > 96) it keeps whatever offset the start left, and with both warpgroups released
+    // together one runs right behind the other -- both in their MUFU-heavy noise phase at once, 6-10 % slower, and
+    // WHICH tiles fall into that state changes with unrelated code changes (profiles/r2z_issuer_protocol.txt).
+    // Starting half an iteration apart puts every tile in the good state; the loops bound by the MMA chain settle out of
+    // phase by themselves and do not care.
+    if (L.stagger && g == 1) mbar_wait(phase_bar, 0u);
     mbar_arrive(ready_bar(g));
 
     // ---------------------------------------------------------------- main loop
@@ -449,7 +439,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         sa = sched4[2 * (t + 1)];
         sb = sched4[2 * (t + 1) + 1];
       }
-      MMA_STAMP(tid == 0, t, 0)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 0)
       // ---- everything that does not depend on the drift, while the tensor core contracts
       if constexpr (SOLVER == SOLVER_DL) {
         const pf2 d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
@@ -498,16 +488,17 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
 
       // ---- the drift of this iteration: this lane's ROW of D, dealt out to the lanes' items through the warp's
       //      redistribution buffer
-      MMA_STAMP(tid == 0, t, 1)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 1)
       mbar_wait(done_bar(g), (uint32_t)(t & 1));
       tc_fence_after();
-      MMA_STAMP(tid == 0, t, 2)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 2)
       {
         float d[NR];
         if constexpr (K == 2) tmem_ld_row32(tl, d);
         else tmem_ld_row16(tl, d);
         tmem_wait_ld();
         tc_fence_before();
+        if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
         if (lane < cnt) {
 #pragma unroll
           for (int pr = 0; pr < 8; ++pr) {
@@ -529,7 +520,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
           gq[h][j] = fma2(pk(t2.x, t2.y), usc, dup(hj[j]));
         }
       __syncwarp();
-      MMA_STAMP(tid == 0, t, 3)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 3)
 
       // ---- finish the step and publish the next contraction input
       if constexpr (SOLVER == SOLVER_DL) {
@@ -568,12 +559,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
           stage2(xbj[j], 0, st0[j]);
         }
       }
-      MMA_STAMP(tid == 0, t, 4)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 4)
       if (t + 1 < T) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(ready_bar(g));
       }
-      MMA_STAMP(tid == 0, t, 5)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 5)
     }
 
     // ---------------------------------------------------------------- results
@@ -617,7 +608,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_free(tbase, L.tcols);
+  if (warp == MMA_UW) tmem_free(tbase, L.tcols);
 }
 
 }  // namespace ccvm

@@ -116,6 +116,7 @@ struct MmaPlan {
   int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
   int ipl;     // (variable, pair) items per lane compiled into the kernel variant: ceil(ceil(n / 4) nbp / 32), >= 2
   int kd, tcols;       // MmaLaunch
+  int stagger;         // MmaLaunch: warpgroup 1 starts half an iteration after warpgroup 0
   int ctas, threads;
   size_t smem;
 };

@@ -16,6 +16,7 @@ static int launch_mma_variant(const SdeParams& p, const MmaPlan& P, const FusedT
   L.kd = P.kd;
   L.tcols = P.tcols;
   L.nbp = P.nbp;
+  L.stagger = P.stagger;
   kern<<<P.ctas, MMA_THREADS, P.smem, st>>>(p, L, f);
   CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
@@ -54,7 +55,7 @@ int regs_mma(int ipl) {
 #ifdef CCVM_MMA_TRACE
 }  // namespace ccvm
 extern "C" int ccvm_debug_mma_trace(long long* host) {
-  return (int)cudaMemcpyFromSymbol(host, ccvm::g_mma_trace, sizeof(long long) * 32 * 8);
+  return (int)cudaMemcpyFromSymbol(host, ccvm::g_mma_trace, sizeof(long long) * 32 * 16);
 }
 namespace ccvm {
 #endif

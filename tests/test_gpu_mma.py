@@ -172,12 +172,21 @@ def test_solver_call_through_tensor_core_path(monkeypatch):
             inst.scale_coefs(solver.get_scaling_factor(inst.q_matrix))
         res[mode] = solver(instance=inst, post_processor="adam", algorithm_parameters=hp)
     a, b = res["1"], res["0"]
-    # two independent samples of 4096 trajectories: means within 5 standard errors, best objective within 1 %
-    # (it is a maximum over a few rare trajectories), success fractions within 4 binomial standard errors
+    # two independent samples of 4096 trajectories (calibration: tools/mma_call_stats.py, four seeds per kernel --
+    # objective mean 72, standard deviation 38, best_objective_value = max(-E) between 40 and 58 for EITHER kernel):
+    # means within 5 standard errors; the 1 % / 99 % quantiles within 5 standard errors of a sample quantile
+    # (sqrt(p (1 - p) / n) / density, Gaussian density at 2.33 sigma: 0.058 sigma each, 0.082 sigma for the difference);
+    # the best value within 4 Gumbel scales sigma / sqrt(2 ln n) of a sample maximum
     oa, ob = a.objective_values.double().cpu(), b.objective_values.double().cpu()
     se = float(np.sqrt(oa.var().item() / oa.numel() + ob.var().item() / ob.numel()))
     assert abs(oa.mean().item() - ob.mean().item()) <= 5 * se, (oa.mean().item(), ob.mean().item(), se)
-    assert abs(a.best_objective_value - b.best_objective_value) <= 1e-2 * abs(b.best_objective_value)
+    sd = float(np.sqrt(0.5 * (oa.var().item() + ob.var().item())))
+    assert abs(oa.std().item() - ob.std().item()) <= 5 * sd / np.sqrt(oa.numel()), (oa.std().item(), ob.std().item())
+    for p in (0.01, 0.99):
+        qa, qb = torch.quantile(oa, p).item(), torch.quantile(ob, p).item()
+        assert abs(qa - qb) <= 5 * 0.082 * sd, (p, qa, qb, sd)
+    assert abs(a.best_objective_value - b.best_objective_value) <= 4 * sd / np.sqrt(2 * np.log(oa.numel())), \
+        (a.best_objective_value, b.best_objective_value, sd)
     for key in ("one_percent", "five_percent", "ten_percent"):
         pa, pb = a.solution_performance[key], b.solution_performance[key]
         assert abs(pa - pb) <= 4 * np.sqrt(max(pb * (1 - pb), 1e-3) * 2 / 4096) + 1e-3, (key, pa, pb)

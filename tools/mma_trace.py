@@ -24,14 +24,19 @@ q, v, f = synth(n, 0, mult, dev)
 for w in range(3):
     E.solve(sid, alg, q, v, 4096, 300, seed=1, offset=w, **kw)
 torch.cuda.synchronize()
-buf = (C.c_longlong * 256)()
+buf = (C.c_longlong * 512)()
 lib = nat.load()
 lib.ccvm_debug_mma_trace.argtypes = [C.POINTER(C.c_longlong)]
 rc = lib.ccvm_debug_mma_trace(buf)
-rows = [[buf[i * 8 + s] for s in range(8)] for i in range(32)]
-print("rc", rc, "slots: 0 iter start | 1 noise done | 2 D ready | 3 D loaded | 4 staged | 5 arrived | 6 issuer woke | 7 issued")
+rows = [[buf[i * 16 + s] for s in range(16)] for i in range(32)]
+print("rc", rc, "per warpgroup g: iter start | noise done | D ready | D loaded | staged | arrived (relative to the iteration start of"
+      " warpgroup 0); issuer: woke / issued relative to that warpgroup's arrival")
 for i in range(1, 31):
     r = rows[i]
     base = r[0]
-    print(i + 64, "period", r[0] - rows[i - 1][0], " rel:", [x - base for x in r[1:6]], "issuer woke/issued (next iter) rel to arrive:",
-          rows[i + 1][6] - r[5], rows[i + 1][7] - r[5])
+    line = [f"{i + 64} period {r[0] - rows[i - 1][0]:5d}"]
+    for g in (0, 1):
+        o = 8 * g
+        line.append(f"wg{g} " + " ".join(f"{r[o + k] - base:5d}" for k in range(6)))
+        line.append(f"issuer(next) +{rows[i + 1][o + 6] - r[o + 5]:4d} +{rows[i + 1][o + 7] - r[o + 5]:4d}")
+    print(" | ".join(line))
