@@ -322,9 +322,16 @@ def sweep_record(rank, world, dev):
         n, k = specs[i]
         return sweep.synthetic_instance(n, k, solver._scaling_multiplier, on_device=True)
 
-    # untimed warm-up: one instance of every size through the same path (module loading, allocator)
-    warm = [sweep.synthetic_instance(n, 10_000 + n, solver._scaling_multiplier, on_device=True) for n in SWEEP_SIZES]
-    solver.solve_many(warm, post_processor="grad-descent")
+    # untimed warm-up: a small sweep of the same shape (every size, the same ramp of chunk sizes up to full
+    # chunks, two chunks in flight).  One instance per size is not enough: the FIRST sweep of a process then still
+    # grows the library's stream-ordered pool to the working set of two full chunks, which costs 0.5-1 s of
+    # blocking driver calls inside the enqueue path (profiles/r2z_sweep_first_vs_repeat.jsonl: wall 2.1-2.5 s for
+    # the first sweep, 1.81 s for every later one)
+    warm_specs = [(SWEEP_SIZES[k % len(SWEEP_SIZES)], 10_000 + k) for k in range(3 * SWEEP_CHUNK)]
+    sweep.solve_sweep(solver, (len(warm_specs), lambda i: sweep.synthetic_instance(
+        warm_specs[i][0], warm_specs[i][1], solver._scaling_multiplier, on_device=True)),
+        post_processor="grad-descent", chunk=SWEEP_CHUNK, costs=[n * n + 1000 for n, _ in warm_specs],
+        rank=0, world_size=1, gather=False)
     torch.cuda.synchronize(dev)
     solver.host_seconds = {"launch": 0.0, "collect": 0.0}
     if world > 1:
