@@ -288,7 +288,7 @@ static void plan_mma(const ccvm_solve_desc& d, const DeviceInfo& di, MmaPlan& P)
   }
   P.kd = ((d.n + 15) / 16) * 16;
   P.tcols = 256;
-  P.ipl = (((d.n + 3) / 4) * P.nbp + 32 * MMA_WPQ - 1) / (32 * MMA_WPQ);
+  P.ipl = (((d.n + 3) / 4) * P.nbp + 31) / 32;
   if (P.ipl < 2) P.ipl = 2;
   P.threads = MMA_THREADS;
   // the two update warpgroups start half an iteration apart (sde_kernel_mma.cuh; profiles/r2z_issuer_protocol.txt);

@@ -45,11 +45,7 @@ namespace ccvm {
 #define CCVM_MMA_ISSUERS 1
 #endif
 constexpr int MMA_ISSUERS = CCVM_MMA_ISSUERS;   // 1: one warp serves both warpgroups; 2: issuer warp g serves warpgroup g
-#ifndef CCVM_MMA_WPQ
-#define CCVM_MMA_WPQ 1
-#endif
-constexpr int MMA_WPQ = CCVM_MMA_WPQ;     // update warps per (warpgroup, TMEM lane quadrant): they share the quadrant's items
-constexpr int MMA_UW = 8 * MMA_WPQ;       // update warps: two warpgroups of 4 MMA_WPQ
+constexpr int MMA_UW = 8;                                  // update warps: two warpgroups of four
 constexpr int MMA_THREADS = 32 * (MMA_UW + MMA_ISSUERS);   // the update warps, then the MMA issuer(s)
 constexpr int MMA_KD_MAX = 128;           // K extent: n rounded up to 16 (one FP16 MMA contracts 16)
 constexpr int MMA_LBO = 144;              // bytes between the two 16-byte K chunks of a core matrix pair (128 + 16:
@@ -201,11 +197,7 @@ __device__ __forceinline__ int mma_koff(int n, int q) {
 // IPL items for the whole run (n = 70, 7 pairs: 126 items on 32 x 4 slots) -- the elementwise work, two thirds of it
 // the noise, is the bound of this kernel and would otherwise run at 56 % lane occupancy.
 template <int SOLVER, bool ADAM, int IPL>
-#if CCVM_MMA_WPQ == 2
-__global__ void __maxnreg__(120)
-#else
 __global__ void __launch_bounds__(MMA_THREADS, 1)
-#endif
     sde_mma_kernel(const SdeParams p, const MmaLaunch L, const FusedTail f) {
   constexpr int K = SolverTraits<SOLVER>::K;
   constexpr int NR = 16 * K;   // B rows per half (hi | lo) and warpgroup (DL: c rows 0-15, s rows 16-31)
@@ -230,11 +222,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   // ------------------------------------------------------------------ prologue
   const unsigned long long t_start = f.stats ? global_timer_ns() : 0ull;
   if (tid == 0) {
-    mbar_init(ready_bar(0), 128 * MMA_WPQ);
-    mbar_init(ready_bar(1), 128 * MMA_WPQ);
+    mbar_init(ready_bar(0), 128);
+    mbar_init(ready_bar(1), 128);
     mbar_init(done_bar(0), 1);
     mbar_init(done_bar(1), 1);
-    mbar_init(phase_bar, 128 * MMA_WPQ);
+    mbar_init(phase_bar, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_max[0] = s_max[1] = 0u;
   }
@@ -366,7 +358,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     }
   } else {
     // ================================================================ update warpgroups
-    const int g = warp / (4 * MMA_WPQ), w4 = warp & 3, wh = (warp >> 2) % MMA_WPQ;   // wh: which share of the quadrant's items
+    const int g = warp >> 2, w4 = warp & 3;
     const int cnt = mma_qcount(N, w4), koff = mma_koff(N, w4);   // this quadrant's variables v = 4 i + w4, i < cnt
     const int n_items = cnt * NBP;                                // (variable, pair) items: e = i * NBP + pair
     const long long b0 = (long long)cta * per_cta + (long long)g * 2 * NBP;   // first trajectory of the warpgroup
@@ -388,7 +380,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     const uint2 key = make_uint2(p.seed_lo, p.seed_hi ^ p.off_hi);
 #pragma unroll
     for (int j = 0; j < IPL; ++j) {
-      const int e = 32 * (j * MMA_WPQ + wh) + lane;
+      const int e = 32 * j + lane;
       okj[j] = e < n_items;
       const int i = okj[j] ? e / NBP : 0;
       prj[j] = okj[j] ? e - i * NBP : 0;
@@ -450,7 +442,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         sa = sched4[2 * (t + 1)];
         sb = sched4[2 * (t + 1) + 1];
       }
-      MMA_STAMP((tid & (128 * MMA_WPQ - 1)) == 0, t, 8 * g + 0)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 0)
       // ---- everything that does not depend on the drift, while the tensor core contracts
       if constexpr (SOLVER == SOLVER_DL) {
         const pf2 d1 = dup(ca.y), d2 = dup(ca.z), n1 = dup(ca.w), n2 = dup(cb.x);
@@ -499,10 +491,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
 
       // ---- the drift of this iteration: this lane's ROW of D, dealt out to the lanes' items through the warp's
       //      redistribution buffer
-      MMA_STAMP((tid & (128 * MMA_WPQ - 1)) == 0, t, 8 * g + 1)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 1)
       mbar_wait(done_bar(g), (uint32_t)(t & 1));
       tc_fence_after();
-      MMA_STAMP((tid & (128 * MMA_WPQ - 1)) == 0, t, 8 * g + 2)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 2)
       {
         float d[NR];
         if constexpr (K == 2) tmem_ld_row32(tl, d);
@@ -527,11 +519,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
       for (int j = 0; j < IPL; ++j)
 #pragma unroll
         for (int h = 0; h < K; ++h) {
-          const float2 t2 = sw[h * MMA_SCRATCH_ITEMS + 32 * (j * MMA_WPQ + wh) + lane];
+          const float2 t2 = sw[h * MMA_SCRATCH_ITEMS + 32 * j + lane];
           gq[h][j] = fma2(pk(t2.x, t2.y), usc, dup(hj[j]));
         }
       __syncwarp();
-      MMA_STAMP((tid & (128 * MMA_WPQ - 1)) == 0, t, 8 * g + 3)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 3)
 
       // ---- finish the step and publish the next contraction input
       if constexpr (SOLVER == SOLVER_DL) {
@@ -570,12 +562,12 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
           stage2(xbj[j], 0, st0[j]);
         }
       }
-      MMA_STAMP((tid & (128 * MMA_WPQ - 1)) == 0, t, 8 * g + 4)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 4)
       if (t + 1 < T) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(ready_bar(g));
       }
-      MMA_STAMP((tid & (128 * MMA_WPQ - 1)) == 0, t, 8 * g + 5)
+      MMA_STAMP((tid & 127) == 0, t, 8 * g + 5)
     }
 
     // ---------------------------------------------------------------- results
