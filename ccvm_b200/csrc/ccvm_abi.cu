@@ -153,11 +153,15 @@ static bool tc_eligible(const ccvm_solve_desc& d) {
 // batched (many-instance) launches stay on the tiled kernels.  CCVM_MMA=0 / 1 overrides the rule ("1": whenever the
 // kernel can run).
 static bool mma_eligible(const ccvm_solve_desc& d) {
-  if (d.n > 128 || d.rng_mode != CCVM_RNG_PHILOX || d.evolution_step > 0) return false;
+  if (d.n > MMA_N_MAX || d.rng_mode != CCVM_RNG_PHILOX || d.evolution_step > 0) return false;
   if (const char* e = getenv("CCVM_MMA")) {
     if (e[0] != 'a') return atoi(e) != 0;
   }
   if (d.n < 40) return false;
+  // two M tiles (128 < n <= 192): twice the MMAs per iteration, but the hybrid FP32 kernel they replace needs a wave of
+  // CTAs per ~590 trajectories (3-6 ms each at T = 1500) -- measured (profiles/r2z_two_m_tiles.txt): DL wins from the smallest
+  // batches on, the K = 1 loops from the hybrid kernel's second wave
+  if (d.n > 128) return d.batch >= (d.solver == CCVM_SOLVER_DL ? 256 : 640);
   const int min_batch = (d.solver == CCVM_SOLVER_DL || d.n >= 96) ? 2048 : d.n >= 56 ? 2560 : 3584;
   return d.batch >= min_batch;
 }
@@ -279,16 +283,29 @@ static void plan_mma(const ccvm_solve_desc& d, const DeviceInfo& di, MmaPlan& P)
     const long long ctas = ((long long)d.batch + 4 * nbp - 1) / (4 * nbp);
     return (ctas + di.sms - 1) / di.sms;
   };
-  P.nbp = 8;
-  for (int nbp = 7; nbp >= 1; --nbp)
+  // a lane owns at most `ipl_max` (variable, pair) items: the per-item state has to stay in registers (compiled variants:
+  // 2 ... 8 for every tile, 9 ... 11 for the tiles with the smallest state)
+  const bool light = d.algorithm != CCVM_ALG_ADAM || d.solver == CCVM_SOLVER_LANGEVIN || d.solver == CCVM_SOLVER_PUMPED_LANGEVIN;
+  int ipl_max = light ? MMA_IPL_MAX_LIGHT : MMA_IPL_MAX;
+  if (const char* e = getenv("CCVM_MMA_IPL_MAX")) {   // tuning aid; never above what the tile has compiled in
+    const int v = atoi(e);
+    if (v >= 2 && v < ipl_max) ipl_max = v;
+  }
+  const int per_quadrant = d.n <= 128 ? (d.n + 3) / 4 : 32 + (d.n - 128 + 3) / 4;
+  int nbp_max = 32 * ipl_max / per_quadrant;
+  if (nbp_max > 8) nbp_max = 8;
+  if (nbp_max < 1) nbp_max = 1;
+  P.nbp = nbp_max;
+  for (int nbp = nbp_max - 1; nbp >= 1; --nbp)
     if (waves(nbp) <= waves(P.nbp)) P.nbp = nbp;
   if (const char* e = getenv("CCVM_MMA_NBP")) {
     const int v = atoi(e);
-    if (v >= 1 && v <= 8) P.nbp = v;
+    if (v >= 1 && v <= nbp_max) P.nbp = v;
   }
   P.kd = ((d.n + 15) / 16) * 16;
-  P.tcols = 256;
-  P.ipl = (((d.n + 3) / 4) * P.nbp + 31) / 32;
+  P.mt = d.n > 128 ? 2 : 1;
+  P.tcols = P.mt == 1 ? 256 : 512;   // mt (64 accumulator columns + kd columns of A)
+  P.ipl = (per_quadrant * P.nbp + 31) / 32;
   if (P.ipl < 2) P.ipl = 2;
   P.threads = MMA_THREADS;
   // the two update warpgroups start half an iteration apart (sde_kernel_mma.cuh; profiles/r2z_issuer_protocol.txt);

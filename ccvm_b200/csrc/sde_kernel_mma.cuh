@@ -47,7 +47,8 @@ namespace ccvm {
 constexpr int MMA_ISSUERS = CCVM_MMA_ISSUERS;   // 1: one warp serves both warpgroups; 2: issuer warp g serves warpgroup g
 constexpr int MMA_UW = 8;                                  // update warps: two warpgroups of four
 constexpr int MMA_THREADS = 32 * (MMA_UW + MMA_ISSUERS);   // the update warps, then the MMA issuer(s)
-constexpr int MMA_KD_MAX = 128;           // K extent: n rounded up to 16 (one FP16 MMA contracts 16)
+constexpr int MMA_N_MAX = 192;            // two M tiles of 128 rows; 64 D + 192 A columns of tensor memory per M tile
+constexpr int MMA_KD_MAX = 192;           // K extent: n rounded up to 16 (one FP16 MMA contracts 16)
 constexpr int MMA_LBO = 144;              // bytes between the two 16-byte K chunks of a core matrix pair (128 + 16:
                                           // 32 consecutive K positions land in different banks)
 constexpr int MMA_SBO = (MMA_KD_MAX / 8) * MMA_LBO + 16;   // bytes between 8-row groups (compile-time: immediates); the 16
@@ -55,12 +56,13 @@ constexpr int MMA_SBO = (MMA_KD_MAX / 8) * MMA_LBO + 16;   // bytes between 8-ro
                                           // rows 0 ... 12 of ~5 K positions, and with a stride of 0 mod 128 bytes rows 8-12
                                           // fell on the banks of rows 0-4 (2.0 wavefronts per store; now 1.0-1.1)
 constexpr int MMA_TILE_BYTES = 8 * MMA_SBO;           // one warpgroup's B tile: rows [hi | lo], up to 2 x 32 (DL: 16 c + 16 s)
-constexpr int MMA_D_COLS = 64;            // TMEM columns [0, 64): the two warpgroups' accumulators (32 each)
-constexpr int MMA_SCRATCH_ITEMS = 256;    // per warp and quadrature: float2 slots of the row -> item redistribution
+constexpr int MMA_D_COLS = 64;            // TMEM columns per M tile for the two warpgroups' accumulators (32 each)
+constexpr int MMA_SCRATCH_ITEMS = 384;    // per warp and quadrature: float2 slots of the row -> item redistribution
+                                          // (48 variables per quadrant x 8 pairs)
 constexpr uint32_t MMA_STREAM_TAG = 0x40000000u;      // keeps these noise streams apart from the column-group streams
 
 __host__ __device__ inline size_t mma_loop_smem_bytes() {
-  return 256 * sizeof(float) + 128 + 2 * (size_t)MMA_TILE_BYTES + (size_t)MMA_UW * 2 * MMA_SCRATCH_ITEMS * 8;
+  return 2 * 256 * sizeof(float) + 128 + 2 * (size_t)MMA_TILE_BYTES + (size_t)MMA_UW * 2 * MMA_SCRATCH_ITEMS * 8;
 }
 
 // D[tmem] (+)= A[tmem] . B[smem]^T, A = 128 x 16 FP16 in tensor memory (lane = row, 32-bit column = two k)
@@ -178,19 +180,27 @@ __device__ long long g_mma_trace[32 * 16];
 
 struct MmaLaunch {
   int kd;      // K extent of the contraction: n rounded up to a multiple of 16
-  int tcols;   // TMEM columns to allocate (power of two >= MMA_D_COLS + kd)
+  int tcols;   // TMEM columns to allocate (power of two >= mt (MMA_D_COLS + kd))
+  int mt;      // M tiles of 128 variables (rows of D): 1 for n <= 128, else 2
   int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
   int stagger; // warpgroup 1 starts half an iteration after warpgroup 0
 };
 
-// Variables are dealt to the four TMEM lane quadrants round-robin: v = 4 i + q sits in lane i of quadrant q and at
-// K position koff(q) + i (quadrant by quadrant, no holes: a warp's stores hit consecutive K positions)
-__device__ __forceinline__ int mma_qcount(int n, int q) { return (n - q + 3) >> 2; }
+// Variables are dealt to the four TMEM lane quadrants round-robin, M tile by M tile: v = 128 m + 4 i + q is row 32 q + i of
+// M tile m (lane i of quadrant q), has the LOCAL index li = 32 m + i in its quadrant and sits at K position koff(q) + li
+// (quadrant by quadrant, no holes: a warp's stores hit consecutive K positions).  n <= 128: one M tile, li = i.
+__device__ __forceinline__ int mma_qcount_tile(int n, int q, int m) {   // rows of quadrant q in M tile m
+  const int r = n - 128 * m;
+  return r <= 0 ? 0 : r >= 128 ? 32 : (r - q + 3) >> 2;
+}
+__device__ __forceinline__ int mma_qcount(int n, int q) { return mma_qcount_tile(n, q, 0) + mma_qcount_tile(n, q, 1); }
 __device__ __forceinline__ int mma_koff(int n, int q) {
   int o = 0;
   for (int i = 0; i < q; ++i) o += mma_qcount(n, i);
   return o;
 }
+// (a second M tile exists only when the first is full: its local indices start at 32)
+__device__ __forceinline__ int mma_var(int li, int q) { return li < 32 ? 4 * li + q : 128 + 4 * (li - 32) + q; }
 
 // IPL: (variable, trajectory pair) items per lane.  A warp reads the rows of its TMEM lane quadrant (one variable per
 // lane, 18 of 32 lanes at n = 70) and deals the values out again through shared memory, so that EVERY lane owns
@@ -209,9 +219,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.n, T = p.iterations, KD = L.kd, NBP = L.nbp;
   const int cta = blockIdx.x;
-  float* av = smem;                                                    // [128] alpha_v
-  float* hv = smem + 128;                                              // [128] affine term h_v
-  const uint32_t tiles = (smem_u32(smem) + 256 * 4 + 127u) & ~127u;    // [warpgroup] B tiles, rows [hi | lo]
+  const int MT = L.mt;
+  float* av = smem;                                                    // [256] alpha_v
+  float* hv = smem + 256;                                              // [256] affine term h_v
+  const uint32_t tiles = (smem_u32(smem) + 512 * 4 + 127u) & ~127u;    // [warpgroup] B tiles, rows [hi | lo]
   uint8_t* tiles_g = reinterpret_cast<uint8_t*>(smem) + (tiles - smem_u32(smem));
   float2* scratch = reinterpret_cast<float2*>(tiles_g + 2 * MMA_TILE_BYTES);   // [warp][K][MMA_SCRATCH_ITEMS]
   const uint32_t bar0 = smem_u32(bars);
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     build_schedule_cta(f.sa, mine);
     sched = mine;
   }
-  for (int j = tid; j < 128; j += MMA_THREADS)
+  for (int j = tid; j < 256; j += MMA_THREADS)
     av[j] = j < N ? p.a_half / (p.drift_s_vec ? p.drift_s_vec[j] : p.drift_s) : 0.f;
   for (int i = tid; i < 2 * MMA_TILE_BYTES / 16; i += MMA_THREADS)
     reinterpret_cast<float4*>(tiles_g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -270,41 +281,45 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   const float sigma = pow2_scale(__uint_as_float(s_max[1]), SOLVER == SOLVER_DL ? 8 : 13);
   const float unscale = 1.f / (tau * sigma);   // exact: powers of two
 
+  // tensor memory: [accumulators: (warpgroup g, M tile m) at 32 (g MT + m)] [A of M tile m: hi | lo, KD / 2 columns each]
+  const uint32_t a_base = tbase + (uint32_t)(MMA_D_COLS * MT);
   if (warp < 4) {
-    // warpgroup 0 writes A = tau Qs^T (hi | lo) into tensor memory: lane m = row of variable v = 4 (m % 32) + m / 32,
-    // 32-bit column c = K positions 2 c (low half), 2 c + 1; K position P <-> input variable k (mma_koff)
-    const int v = 4 * lane + warp;
-    const bool valid = v < N;
-    float aj = 0.f;
-    if (valid) {
-      float cs = 0.f;
-      for (int i = 0; i < N; ++i) cs += p.q[i * N + v];
-      aj = av[v];
-      hv[v] = -aj * (p.b_half * cs + p.v[v]);
-    }
+    // warpgroup 0 writes A = tau Qs^T (hi | lo) into tensor memory: lane 32 q + i of M tile m = row of variable
+    // v = 128 m + 4 i + q, 32-bit column c = K positions 2 c (low half), 2 c + 1; K position P <-> input variable k
     const int o1 = mma_koff(N, 1), o2 = mma_koff(N, 2), o3 = mma_koff(N, 3);
-    const uint32_t tl = tbase + ((uint32_t)(warp * 32) << 16) + MMA_D_COLS;
-    for (int c4 = 0; c4 < KD / 8; ++c4) {
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float val[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int P = 8 * c4 + 2 * e + u;
-          val[u] = 0.f;
-          if (valid && P < N) {
-            const int q = P >= o3 ? 3 : P >= o2 ? 2 : P >= o1 ? 1 : 0;
-            const int k = 4 * (P - (q == 3 ? o3 : q == 2 ? o2 : q == 1 ? o1 : 0)) + q;
-            val[u] = (-av[k] * aj * p.q[k * N + v]) * tau;
-          }
-        }
-        hi[e] = f16x2_sat(val[0], val[1]);
-        lo[e] = f16x2_sat(val[0] - f16_lo_to_f32(hi[e]), val[1] - f16_hi_to_f32(hi[e]));
+    for (int m = 0; m < MT; ++m) {
+      const int v = 128 * m + 4 * lane + warp;
+      const bool valid = v < N;
+      float aj = 0.f;
+      if (valid) {
+        float cs = 0.f;
+        for (int i = 0; i < N; ++i) cs += p.q[i * N + v];
+        aj = av[v];
+        hv[v] = -aj * (p.b_half * cs + p.v[v]);
       }
-      tmem_st4(tl + 4 * c4, __uint_as_float(hi[0]), __uint_as_float(hi[1]), __uint_as_float(hi[2]), __uint_as_float(hi[3]));
-      tmem_st4(tl + KD / 2 + 4 * c4, __uint_as_float(lo[0]), __uint_as_float(lo[1]), __uint_as_float(lo[2]),
-               __uint_as_float(lo[3]));
+      const uint32_t tl = a_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * KD);
+      for (int c4 = 0; c4 < KD / 8; ++c4) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float val[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int P = 8 * c4 + 2 * e + u;
+            val[u] = 0.f;
+            if (valid && P < N) {
+              const int q = P >= o3 ? 3 : P >= o2 ? 2 : P >= o1 ? 1 : 0;
+              const int k = mma_var(P - (q == 3 ? o3 : q == 2 ? o2 : q == 1 ? o1 : 0), q);
+              val[u] = (-av[k] * aj * p.q[k * N + v]) * tau;
+            }
+          }
+          hi[e] = f16x2_sat(val[0], val[1]);
+          lo[e] = f16x2_sat(val[0] - f16_lo_to_f32(hi[e]), val[1] - f16_hi_to_f32(hi[e]));
+        }
+        tmem_st4(tl + 4 * c4, __uint_as_float(hi[0]), __uint_as_float(hi[1]), __uint_as_float(hi[2]), __uint_as_float(hi[3]));
+        tmem_st4(tl + KD / 2 + 4 * c4, __uint_as_float(lo[0]), __uint_as_float(lo[1]), __uint_as_float(lo[2]),
+                 __uint_as_float(lo[3]));
+      }
     }
     tmem_wait_st();
   }
@@ -324,17 +339,19 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     // instruction descriptor: D = F32, A = B = F16, K-major, M = 128, N = NR
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const int KS = KD / 16;
-    const uint32_t a_hi = tbase + MMA_D_COLS, a_lo = a_hi + KD / 2;
     auto issue = [&](int g) {
       if (elect_one()) {
-        const uint32_t d_tmem = tbase + g * 32;
         const uint64_t b_hi = umma_desc_k_none(tiles + g * MMA_TILE_BYTES);
         const uint64_t b_lo = umma_desc_k_none(tiles + g * MMA_TILE_BYTES + (NR / 8) * MMA_SBO);
-        for (int ks = 0; ks < KS; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * (2 * MMA_LBO >> 4));   // two 16-byte K chunks per MMA
-          umma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + adv, idesc, ks != 0);
-          umma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + adv, idesc, 1u);
-          umma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + adv, idesc, 1u);
+        for (int m = 0; m < MT; ++m) {
+          const uint32_t d_tmem = tbase + (uint32_t)(32 * (g * MT + m));
+          const uint32_t a_hi = a_base + (uint32_t)(m * KD), a_lo = a_hi + KD / 2;
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * (2 * MMA_LBO >> 4));   // two 16-byte K chunks per MMA
+            umma_f16_ts(d_tmem, a_lo + 8 * ks, b_hi + adv, idesc, ks != 0);
+            umma_f16_ts(d_tmem, a_hi + 8 * ks, b_lo + adv, idesc, 1u);
+            umma_f16_ts(d_tmem, a_hi + 8 * ks, b_hi + adv, idesc, 1u);
+          }
         }
         umma_commit(done_bar(g));
       }
@@ -359,10 +376,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   } else {
     // ================================================================ update warpgroups
     const int g = warp >> 2, w4 = warp & 3;
-    const int cnt = mma_qcount(N, w4), koff = mma_koff(N, w4);   // this quadrant's variables v = 4 i + w4, i < cnt
-    const int n_items = cnt * NBP;                                // (variable, pair) items: e = i * NBP + pair
+    const int cnt = mma_qcount(N, w4), koff = mma_koff(N, w4);   // this quadrant's variables mma_var(li, w4), li < cnt
+    const int n_items = cnt * NBP;                                // (variable, pair) items: e = li * NBP + pair
     const long long b0 = (long long)cta * per_cta + (long long)g * 2 * NBP;   // first trajectory of the warpgroup
-    const uint32_t tl = tbase + ((uint32_t)(w4 * 32) << 16) + g * 32;
+    const uint32_t tl = tbase + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(32 * g * MT);
     uint8_t* tile = tiles_g + (size_t)g * MMA_TILE_BYTES;
     float2* sw = scratch + (size_t)warp * 2 * MMA_SCRATCH_ITEMS;
     const pf2 usc = dup(unscale), sg2 = dup(sigma);
@@ -384,9 +401,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
       okj[j] = e < n_items;
       const int i = okj[j] ? e / NBP : 0;
       prj[j] = okj[j] ? e - i * NBP : 0;
-      vj[j] = 4 * i + w4;
+      vj[j] = mma_var(i, w4);
       // K position in the B tile; idle slots run the same code on zeros and store where it cannot matter: just past
-      // the K extent (the row groups are laid out for KD = 128, no MMA reads there), or for KD = 128 at a K position
+      // the K extent (the row groups are laid out for KD = MMA_KD_MAX, no MMA reads there), or for KD = MMA_KD_MAX at a K position
       // whose A column is zero (n <= P < KD; the value is finite: saturating conversion, clamped or cubic-saturated
       // dynamics) -- no predicate, no branch around the stores
       const int P = okj[j] ? koff + i : (KD < MMA_KD_MAX ? KD : N);
@@ -495,24 +512,25 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
       mbar_wait(done_bar(g), (uint32_t)(t & 1));
       tc_fence_after();
       MMA_STAMP((tid & 127) == 0, t, 8 * g + 2)
-      {
+      for (int m = 0; m < MT; ++m) {
         float d[NR];
-        if constexpr (K == 2) tmem_ld_row32(tl, d);
-        else tmem_ld_row16(tl, d);
+        if constexpr (K == 2) tmem_ld_row32(tl + 32 * m, d);
+        else tmem_ld_row16(tl + 32 * m, d);
         tmem_wait_ld();
-        tc_fence_before();
-        if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
-        if (lane < cnt) {
+        if (lane < mma_qcount_tile(N, w4, m)) {
 #pragma unroll
           for (int pr = 0; pr < 8; ++pr) {
             if (pr < NBP) {
 #pragma unroll
               for (int h = 0; h < K; ++h)
-                sw[h * MMA_SCRATCH_ITEMS + lane * NBP + pr] = make_float2(d[16 * h + 2 * pr], d[16 * h + 2 * pr + 1]);
+                sw[h * MMA_SCRATCH_ITEMS + (32 * m + lane) * NBP + pr] =
+                    make_float2(d[16 * h + 2 * pr], d[16 * h + 2 * pr + 1]);
             }
           }
         }
       }
+      tc_fence_before();
+      if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
       __syncwarp();
       pf2 gq[K][IPL];
 #pragma unroll

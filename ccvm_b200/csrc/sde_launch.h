@@ -112,10 +112,12 @@ template <int SOLVER, bool ADAM>
 int regs_tc(int version);
 
 // ---- small-n tensor-core kernel (sde_kernel_mma.cuh): contraction on tcgen05 with Qs^T resident in TMEM
+constexpr int MMA_IPL_MAX = 8;          // items per lane compiled in for every tile
+constexpr int MMA_IPL_MAX_LIGHT = 11;   // ... for every tile but DL-adam and MF-adam
 struct MmaPlan {
   int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
   int ipl;     // (variable, pair) items per lane compiled into the kernel variant: ceil(ceil(n / 4) nbp / 32), >= 2
-  int kd, tcols;       // MmaLaunch
+  int kd, tcols, mt;   // MmaLaunch
   int stagger;         // MmaLaunch: warpgroup 1 starts half an iteration after warpgroup 0
   int ctas, threads;
   size_t smem;

@@ -16,15 +16,29 @@ static int launch_mma_variant(const SdeParams& p, const MmaPlan& P, const FusedT
   L.kd = P.kd;
   L.tcols = P.tcols;
   L.nbp = P.nbp;
+  L.mt = P.mt;
   L.stagger = P.stagger;
   kern<<<P.ctas, MMA_THREADS, P.smem, st>>>(p, L, f);
   CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
 }
 
-// items per lane compiled in: 2 ... 8 (n = 70 with 7 pairs per warpgroup: 4)
+// items per lane compiled in: 2 ... 8 (n = 70 with 7 pairs per warpgroup: 4), 9 ... 11 for every tile but DL-adam and MF-adam
+// (n = 129 ... 192 with 7 pairs per warpgroup: one wave of CTAs at B = 4096; with the Adam moments of two quadratures, or of
+// MF's mean next to its variance, the spills cost more than the second wave: profiles/r2z_two_m_tiles.txt)
+template <int SOLVER, bool ADAM>
+constexpr bool mma_light_tile() { return !ADAM || SOLVER == SOLVER_LV || SOLVER == SOLVER_PLV; }
+
 template <int SOLVER, bool ADAM>
 int launch_mma(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStream_t st) {
+  if constexpr (mma_light_tile<SOLVER, ADAM>()) {
+    switch (P.ipl) {
+      case 9: return launch_mma_variant<SOLVER, ADAM, 9>(p, P, f, st);
+      case 10: return launch_mma_variant<SOLVER, ADAM, 10>(p, P, f, st);
+      case 11: return launch_mma_variant<SOLVER, ADAM, 11>(p, P, f, st);
+      default: break;
+    }
+  }
   switch (P.ipl) {
     case 2: return launch_mma_variant<SOLVER, ADAM, 2>(p, P, f, st);
     case 3: return launch_mma_variant<SOLVER, ADAM, 3>(p, P, f, st);
@@ -39,7 +53,16 @@ int launch_mma(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStr
 template <int SOLVER, bool ADAM>
 int regs_mma(int ipl) {
   cudaFuncAttributes fa;
-  cudaError_t e;
+  cudaError_t e = cudaErrorInvalidValue;
+  if constexpr (mma_light_tile<SOLVER, ADAM>()) {
+    switch (ipl) {
+      case 9: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 9>); break;
+      case 10: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 10>); break;
+      case 11: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 11>); break;
+      default: break;
+    }
+    if (ipl >= 9 && ipl <= 11) return e == cudaSuccess ? fa.numRegs : -1;
+  }
   switch (ipl) {
     case 2: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 2>); break;
     case 3: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 3>); break;

@@ -1,7 +1,8 @@
 """The small-n tensor-core kernel (csrc/sde_kernel_mma.cuh: drift contraction on tcgen05 with FP16-split operands,
 Qs^T resident in tensor memory) against the oracle and against the tiled kernels.
 
-It serves single-instance Philox-mode launches with 40 <= n <= 128 and batch >= 2048 ... 3584 (by n and solver; CCVM_MMA=1 forces it for any
+It serves single-instance Philox-mode launches with 40 <= n <= 128 and batch >= 2048 ... 3584 (by n and solver), and with
+128 < n <= 192 (two M tiles) from batch 256 (DL) / 640 (CCVM_MMA=1 forces it for any
 shape it can run, CCVM_MMA=0 disables it).  Same bar as every production kernel: the oracle replays the normals
 ``ccvm_dump_noise`` writes for the launch, per-trajectory objective within 1e-3 relative (2e-3 DL-adam; reference loops
 dl_solver.py:468-769, mf_solver.py:493-764, langevin_solver.py:368-561, pumped_langevin_solver.py:232-449)."""
@@ -38,14 +39,24 @@ def test_size_rule(monkeypatch):
     assert launch_info("mf", True, 70, 2048, 10)["threads"] != 288
     assert launch_info("lv", False, 36, 4096, 10)["threads"] != 288   # too few variables: tiled kernel
     assert launch_info("lv", False, 70, 1000, 10)["threads"] != 288   # too few trajectories per SM
-    assert launch_info("lv", False, 129, 4096, 10)["threads"] != 288  # hybrid kernel
+    # two M tiles: 128 < n <= 192, DL from batch 256, the K = 1 loops from 640; above 192 the hybrid kernel
+    assert launch_info("lv", False, 129, 4096, 10)["threads"] == 288
+    assert launch_info("lv", False, 160, 4096, 10)["ctas"] == 147          # 9 items per lane: one wave of CTAs
+    assert launch_info("dl", True, 160, 4096, 10)["ctas"] == 171           # 8 items per lane at most: 6 pairs per warpgroup
+    assert launch_info("mf", False, 192, 640, 10)["threads"] == 288
+    assert launch_info("mf", False, 192, 600, 10)["threads"] != 288
+    assert launch_info("dl", False, 150, 256, 10)["threads"] == 288
+    assert launch_info("dl", False, 150, 200, 10)["threads"] != 288
+    assert launch_info("lv", False, 193, 4096, 10)["threads"] != 288  # hybrid kernel
     monkeypatch.setenv("CCVM_MMA", "0")
     assert launch_info("dl", True, 70, 4096, 10)["threads"] == 256
 
 
-# the shapes the size rule selects: every tile, K extents 48 ... 128, 4 ... 8 pairs per warpgroup, 3 ... 7 items per lane
+# the shapes the size rule selects: every tile, K extents 48 ... 192, one and two M tiles, 4 ... 8 pairs per warpgroup,
+# 3 ... 11 items per lane
 @pytest.mark.parametrize("solver,adam", TILES)
-@pytest.mark.parametrize("n,b,t", [(40, 3600, 60), (64, 2600, 60), (70, 4096, 60), (100, 2048, 40), (128, 2240, 40)])
+@pytest.mark.parametrize("n,b,t", [(40, 3600, 60), (64, 2600, 60), (70, 4096, 60), (100, 2048, 40), (128, 2240, 40),
+                                   (129, 1000, 40), (150, 4096, 30), (177, 700, 40), (192, 4096, 30)])
 def test_production_parity_selected_shapes(solver, adam, n, b, t):
     assert launch_info(solver, adam, n, b, t)["threads"] == 288
     parity_case(solver, adam, n, b, t, tol_of(solver, adam), philox=(31, 7 * n + b))
@@ -54,7 +65,8 @@ def test_production_parity_selected_shapes(solver, adam, n, b, t):
 # forced: ragged sizes (n % 4 != 0, n % 16 != 0), odd batches (a half-filled pair, a partly filled CTA), one pair per
 # warpgroup, tiny n
 @pytest.mark.parametrize("solver,adam", TILES)
-@pytest.mark.parametrize("n,b,t", [(33, 129, 100), (47, 301, 100), (70, 1001, 80), (113, 75, 60), (20, 64, 100), (5, 37, 60)])
+@pytest.mark.parametrize("n,b,t", [(33, 129, 100), (47, 301, 100), (70, 1001, 80), (113, 75, 60), (20, 64, 100), (5, 37, 60),
+                                   (131, 75, 50), (161, 301, 40), (190, 37, 40)])
 def test_production_parity_forced_shapes(force_mma, solver, adam, n, b, t):
     assert launch_info(solver, adam, n, b, t)["threads"] == 288
     parity_case(solver, adam, n, b, t, tol_of(solver, adam), philox=(77, 5 * n + b))

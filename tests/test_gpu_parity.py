@@ -261,6 +261,7 @@ def test_hybrid_philox_matches_streamed_q(monkeypatch, solver, adam, n, b):
     the streamed-Q kernel under the same Philox stream: same noise, same arithmetic up to the
     order of the prefetch, so the states must agree closely after a short run; the hybrid path must
     also be bit-reproducible and independent of how the batch is split."""
+    monkeypatch.setenv("CCVM_MMA", "0")   # (n <= 192 at these batches is served by the tensor-core kernel: test_gpu_mma.py)
     t = 40
     q, v, _ = instance(n, 11, 0.2 if solver == "dl" else 0.05)
     sid = {"dl": nat.SOLVER_DL, "mf": nat.SOLVER_MF, "lv": nat.SOLVER_LANGEVIN, "plv": nat.SOLVER_PUMPED_LANGEVIN}[solver]
