@@ -575,7 +575,7 @@ extern "C" int ccvm_query_launch(const ccvm_solve_desc* d, int32_t* info5) {
     info5[1] = P.ctas;
     info5[2] = 4 * P.nbp;
     info5[3] = (int)P.smem;
-#define REGS_MMA(S, A) regs = regs_mma<S, A>(P.ipl)
+#define REGS_MMA(S, A) regs = regs_mma<S, A>(P.ipl, P.mt)
     CCVM_DISPATCH_TILE(d->solver, adam, REGS_MMA)
 #undef REGS_MMA
     info5[4] = regs;

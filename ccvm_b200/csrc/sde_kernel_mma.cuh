@@ -1,5 +1,5 @@
-// Persistent Euler-Maruyama kernel, tensor-core variant for SMALL n (n <= 128) and large single batches:
-// the drift contraction of every iteration runs on the 5th-generation tensor cores (tcgen05, 3xTF32),
+// Persistent Euler-Maruyama kernel, tensor-core variant for SMALL n (n <= 192) and large single batches:
+// the drift contraction of every iteration runs on the 5th-generation tensor cores (tcgen05, FP16-split operands),
 // the SIMT pipes only draw the noise and apply the solver's elementwise step.
 // Reference loops: dl_solver.py:468-769, mf_solver.py:493-764, langevin_solver.py:368-561,
 // pumped_langevin_solver.py:232-449 (the einsum "bi,ij->bj" + the elementwise SDE step).
@@ -30,7 +30,8 @@
 //     Two warpgroups per CTA run out of phase on the same four schedulers.
 //
 // Variables are dealt to the four TMEM lane quadrants round-robin (v = 4 lane + quadrant), so that the four
-// warps of a warpgroup carry the same load; 70 variables occupy 18 lanes of every warp.
+// warps of a warpgroup carry the same load; 70 variables occupy 18 lanes of every warp.  Variables 128 ... 191 are the
+// rows of a SECOND M tile (its own A in tensor memory, its own accumulators; twice the MMAs per iteration).
 // Noise: one xoshiro128+ stream per (global trajectory pair, variable), seeded by Philox4x32-10 (ccvm_common.cuh);
 // a Box-Muller pair serves the two trajectories of the pair.  ccvm_dump_noise reproduces it.
 #pragma once
@@ -181,7 +182,7 @@ __device__ long long g_mma_trace[32 * 16];
 struct MmaLaunch {
   int kd;      // K extent of the contraction: n rounded up to a multiple of 16
   int tcols;   // TMEM columns to allocate (power of two >= mt (MMA_D_COLS + kd))
-  int mt;      // M tiles of 128 variables (rows of D): 1 for n <= 128, else 2
+  int mt;      // M tiles of 128 variables (rows of D): 1 for n <= 128, else 2 (= the kernel's template argument MT)
   int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
   int stagger; // warpgroup 1 starts half an iteration after warpgroup 0
 };
@@ -206,7 +207,7 @@ __device__ __forceinline__ int mma_var(int li, int q) { return li < 32 ? 4 * li 
 // lane, 18 of 32 lanes at n = 70) and deals the values out again through shared memory, so that EVERY lane owns
 // IPL items for the whole run (n = 70, 7 pairs: 126 items on 32 x 4 slots) -- the elementwise work, two thirds of it
 // the noise, is the bound of this kernel and would otherwise run at 56 % lane occupancy.
-template <int SOLVER, bool ADAM, int IPL>
+template <int SOLVER, bool ADAM, int IPL, int MT>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
     sde_mma_kernel(const SdeParams p, const MmaLaunch L, const FusedTail f) {
   constexpr int K = SolverTraits<SOLVER>::K;
@@ -219,7 +220,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.n, T = p.iterations, KD = L.kd, NBP = L.nbp;
   const int cta = blockIdx.x;
-  const int MT = L.mt;
   float* av = smem;                                                    // [256] alpha_v
   float* hv = smem + 256;                                              // [256] affine term h_v
   const uint32_t tiles = (smem_u32(smem) + 512 * 4 + 127u) & ~127u;    // [warpgroup] B tiles, rows [hi | lo]
@@ -343,6 +343,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
       if (elect_one()) {
         const uint64_t b_hi = umma_desc_k_none(tiles + g * MMA_TILE_BYTES);
         const uint64_t b_lo = umma_desc_k_none(tiles + g * MMA_TILE_BYTES + (NR / 8) * MMA_SBO);
+#pragma unroll
         for (int m = 0; m < MT; ++m) {
           const uint32_t d_tmem = tbase + (uint32_t)(32 * (g * MT + m));
           const uint32_t a_hi = a_base + (uint32_t)(m * KD), a_lo = a_hi + KD / 2;
@@ -378,6 +379,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     const int g = warp >> 2, w4 = warp & 3;
     const int cnt = mma_qcount(N, w4), koff = mma_koff(N, w4);   // this quadrant's variables mma_var(li, w4), li < cnt
     const int n_items = cnt * NBP;                                // (variable, pair) items: e = li * NBP + pair
+    int cnt_tile[MT];                                             // ... of which in M tile m (lanes of this quadrant)
+#pragma unroll
+    for (int m = 0; m < MT; ++m) cnt_tile[m] = mma_qcount_tile(N, w4, m);
     const long long b0 = (long long)cta * per_cta + (long long)g * 2 * NBP;   // first trajectory of the warpgroup
     const uint32_t tl = tbase + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(32 * g * MT);
     uint8_t* tile = tiles_g + (size_t)g * MMA_TILE_BYTES;
@@ -512,12 +516,13 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
       mbar_wait(done_bar(g), (uint32_t)(t & 1));
       tc_fence_after();
       MMA_STAMP((tid & 127) == 0, t, 8 * g + 2)
+#pragma unroll
       for (int m = 0; m < MT; ++m) {
         float d[NR];
         if constexpr (K == 2) tmem_ld_row32(tl + 32 * m, d);
         else tmem_ld_row16(tl + 32 * m, d);
         tmem_wait_ld();
-        if (lane < mma_qcount_tile(N, w4, m)) {
+        if (lane < cnt_tile[m]) {
 #pragma unroll
           for (int pr = 0; pr < 8; ++pr) {
             if (pr < NBP) {

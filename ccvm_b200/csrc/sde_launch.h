@@ -125,7 +125,7 @@ struct MmaPlan {
 template <int SOLVER, bool ADAM>
 int launch_mma(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStream_t st);
 template <int SOLVER, bool ADAM>
-int regs_mma(int ipl);
+int regs_mma(int ipl, int mt);
 
 // dispatch on run-time (solver, algorithm): `CALL` is a macro taking (SOLVER, ADAM)
 #define CCVM_DISPATCH_TILE(solver, adam, CALL)                 \

@@ -8,9 +8,9 @@
 
 namespace ccvm {
 
-template <int SOLVER, bool ADAM, int IPL>
-static int launch_mma_variant(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStream_t st) {
-  auto kern = sde_mma_kernel<SOLVER, ADAM, IPL>;
+template <int SOLVER, bool ADAM, int IPL, int MT>
+static int launch_mma_tiles(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStream_t st) {
+  auto kern = sde_mma_kernel<SOLVER, ADAM, IPL, MT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
   MmaLaunch L;
   L.kd = P.kd;
@@ -21,6 +21,17 @@ static int launch_mma_variant(const SdeParams& p, const MmaPlan& P, const FusedT
   kern<<<P.ctas, MMA_THREADS, P.smem, st>>>(p, L, f);
   CUDA_TRY(cudaGetLastError());
   return CCVM_OK;
+}
+
+// one or two M tiles of 128 variables
+template <int SOLVER, bool ADAM, int IPL>
+static int launch_mma_variant(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStream_t st) {
+  return P.mt == 2 ? launch_mma_tiles<SOLVER, ADAM, IPL, 2>(p, P, f, st) : launch_mma_tiles<SOLVER, ADAM, IPL, 1>(p, P, f, st);
+}
+template <int SOLVER, bool ADAM, int IPL>
+static cudaError_t attrs_mma_variant(cudaFuncAttributes* fa, int mt) {
+  return mt == 2 ? cudaFuncGetAttributes(fa, sde_mma_kernel<SOLVER, ADAM, IPL, 2>)
+                 : cudaFuncGetAttributes(fa, sde_mma_kernel<SOLVER, ADAM, IPL, 1>);
 }
 
 // items per lane compiled in: 2 ... 8 (n = 70 with 7 pairs per warpgroup: 4), 9 ... 11 for every tile but DL-adam and MF-adam
@@ -51,26 +62,26 @@ int launch_mma(const SdeParams& p, const MmaPlan& P, const FusedTail& f, cudaStr
 }
 
 template <int SOLVER, bool ADAM>
-int regs_mma(int ipl) {
+int regs_mma(int ipl, int mt) {
   cudaFuncAttributes fa;
   cudaError_t e = cudaErrorInvalidValue;
   if constexpr (mma_light_tile<SOLVER, ADAM>()) {
     switch (ipl) {
-      case 9: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 9>); break;
-      case 10: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 10>); break;
-      case 11: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 11>); break;
+      case 9: e = attrs_mma_variant<SOLVER, ADAM, 9>(&fa, mt); break;
+      case 10: e = attrs_mma_variant<SOLVER, ADAM, 10>(&fa, mt); break;
+      case 11: e = attrs_mma_variant<SOLVER, ADAM, 11>(&fa, mt); break;
       default: break;
     }
     if (ipl >= 9 && ipl <= 11) return e == cudaSuccess ? fa.numRegs : -1;
   }
   switch (ipl) {
-    case 2: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 2>); break;
-    case 3: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 3>); break;
-    case 4: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 4>); break;
-    case 5: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 5>); break;
-    case 6: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 6>); break;
-    case 7: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 7>); break;
-    default: e = cudaFuncGetAttributes(&fa, sde_mma_kernel<SOLVER, ADAM, 8>); break;
+    case 2: e = attrs_mma_variant<SOLVER, ADAM, 2>(&fa, mt); break;
+    case 3: e = attrs_mma_variant<SOLVER, ADAM, 3>(&fa, mt); break;
+    case 4: e = attrs_mma_variant<SOLVER, ADAM, 4>(&fa, mt); break;
+    case 5: e = attrs_mma_variant<SOLVER, ADAM, 5>(&fa, mt); break;
+    case 6: e = attrs_mma_variant<SOLVER, ADAM, 6>(&fa, mt); break;
+    case 7: e = attrs_mma_variant<SOLVER, ADAM, 7>(&fa, mt); break;
+    default: e = attrs_mma_variant<SOLVER, ADAM, 8>(&fa, mt); break;
   }
   return e == cudaSuccess ? fa.numRegs : -1;
 }
@@ -85,6 +96,6 @@ namespace ccvm {
 
 template int launch_mma<CCVM_INST_SOLVER, (CCVM_INST_ADAM != 0)>(const SdeParams&, const MmaPlan&, const FusedTail&,
                                                                   cudaStream_t);
-template int regs_mma<CCVM_INST_SOLVER, (CCVM_INST_ADAM != 0)>(int);
+template int regs_mma<CCVM_INST_SOLVER, (CCVM_INST_ADAM != 0)>(int, int);
 
 }  // namespace ccvm

@@ -42,7 +42,7 @@ def test_size_rule(monkeypatch):
     # two M tiles: 128 < n <= 192, DL from batch 256, the K = 1 loops from 640; above 192 the hybrid kernel
     assert launch_info("lv", False, 129, 4096, 10)["threads"] == 288
     assert launch_info("lv", False, 160, 4096, 10)["ctas"] == 147          # 9 items per lane: one wave of CTAs
-    assert launch_info("dl", True, 160, 4096, 10)["ctas"] == 171           # 8 items per lane at most: 6 pairs per warpgroup
+    assert launch_info("dl", True, 160, 4096, 10)["ctas"] == 256           # 8 items per lane at most: two waves, 4 pairs per warpgroup
     assert launch_info("mf", False, 192, 640, 10)["threads"] == 288
     assert launch_info("mf", False, 192, 600, 10)["threads"] != 288
     assert launch_info("dl", False, 150, 256, 10)["threads"] == 288
@@ -56,7 +56,7 @@ def test_size_rule(monkeypatch):
 # 3 ... 11 items per lane
 @pytest.mark.parametrize("solver,adam", TILES)
 @pytest.mark.parametrize("n,b,t", [(40, 3600, 60), (64, 2600, 60), (70, 4096, 60), (100, 2048, 40), (128, 2240, 40),
-                                   (129, 1000, 40), (150, 4096, 30), (177, 700, 40), (192, 4096, 30)])
+                                   (129, 1000, 30), (150, 4096, 30), (177, 700, 40), (192, 4096, 20)])
 def test_production_parity_selected_shapes(solver, adam, n, b, t):
     assert launch_info(solver, adam, n, b, t)["threads"] == 288
     parity_case(solver, adam, n, b, t, tol_of(solver, adam), philox=(31, 7 * n + b))
