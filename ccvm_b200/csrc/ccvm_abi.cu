@@ -313,7 +313,7 @@ static void plan_mma(const ccvm_solve_desc& d, const DeviceInfo& di, MmaPlan& P)
   P.stagger = 1;
   if (const char* e = getenv("CCVM_MMA_STAGGER")) P.stagger = atoi(e) != 0;
   P.ctas = (int)(((long long)d.batch + 4 * P.nbp - 1) / (4 * P.nbp));
-  P.smem = mma_loop_smem_bytes();
+  P.smem = mma_loop_smem_bytes(P.mt);
 }
 
 // Qs[k][j] = -alpha_k alpha_j Q_kj, zero padded to NP x NP (QSRC_GMEM operand)

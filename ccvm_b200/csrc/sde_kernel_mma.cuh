@@ -49,22 +49,40 @@ constexpr int MMA_ISSUERS = CCVM_MMA_ISSUERS;   // 1: one warp serves both warpg
 constexpr int MMA_UW = 8;                                  // update warps: two warpgroups of four
 constexpr int MMA_THREADS = 32 * (MMA_UW + MMA_ISSUERS);   // the update warps, then the MMA issuer(s)
 constexpr int MMA_N_MAX = 192;            // two M tiles of 128 rows; 64 D + 192 A columns of tensor memory per M tile
-constexpr int MMA_KD_MAX = 192;           // K extent: n rounded up to 16 (one FP16 MMA contracts 16)
 constexpr int MMA_LBO = 144;              // bytes between the two 16-byte K chunks of a core matrix pair (128 + 16:
                                           // 32 consecutive K positions land in different banks)
-constexpr int MMA_SBO = (MMA_KD_MAX / 8) * MMA_LBO + 16;   // bytes between 8-row groups (compile-time: immediates); the 16
-                                          // extra bytes shift every row group by four banks: a warp's staging store covers
-                                          // rows 0 ... 12 of ~5 K positions, and with a stride of 0 mod 128 bytes rows 8-12
-                                          // fell on the banks of rows 0-4 (2.0 wavefronts per store; now 1.0-1.1)
-constexpr int MMA_TILE_BYTES = 8 * MMA_SBO;           // one warpgroup's B tile: rows [hi | lo], up to 2 x 32 (DL: 16 c + 16 s)
 constexpr int MMA_D_COLS = 64;            // TMEM columns per M tile for the two warpgroups' accumulators (32 each)
-constexpr int MMA_SCRATCH_ITEMS = 384;    // per warp and quadrature: float2 slots of the row -> item redistribution
-                                          // (48 variables per quadrant x 8 pairs)
 constexpr uint32_t MMA_STREAM_TAG = 0x40000000u;      // keeps these noise streams apart from the column-group streams
 
-__host__ __device__ inline size_t mma_loop_smem_bytes() {
-  return 2 * 256 * sizeof(float) + 128 + 2 * (size_t)MMA_TILE_BYTES + (size_t)MMA_UW * 2 * MMA_SCRATCH_ITEMS * 8;
-}
+// Shared-memory layout by the number of M tiles.  The one-tile kernels (n <= 128) keep the layout they were tuned with:
+// sized for two tiles, the same loop ran 14 % slower at n = 70 (DL-adam, B = 4096: 1.94 -> 2.21 ms,
+// profiles/r2zz_bench_n1_two_tile_layout.json) -- the strides are immediates of the staging stores and the register-bound
+// tiles (168 registers, 300 bytes of stack) pay for every change of the address arithmetic around them.
+// (tuning switches of that measurement: -DCCVM_MMA_WIDE_LAYOUT=1 sizes the one-tile kernels like the two-tile ones,
+//  -DCCVM_MMA_LATE_FENCE=1 moves their tcgen05 fence + phase arrival behind the redistribution stores)
+#ifndef CCVM_MMA_WIDE_LAYOUT
+#define CCVM_MMA_WIDE_LAYOUT 0
+#endif
+#ifndef CCVM_MMA_LATE_FENCE
+#define CCVM_MMA_LATE_FENCE 0
+#endif
+template <int MT_>
+struct MmaLayout {
+  static constexpr int MT = CCVM_MMA_WIDE_LAYOUT ? 2 : MT_;
+  static constexpr int KD_MAX = MT == 1 ? 128 : 192;   // K extent: n rounded up to 16 (one FP16 MMA contracts 16)
+  static constexpr int NV = 128 * MT;                  // entries of the per-variable tables alpha_v, h_v
+  // bytes between 8-row groups (compile-time: immediates); the 16 extra bytes shift every row group by four banks: a
+  // warp's staging store covers rows 0 ... 12 of ~5 K positions, and with a stride of 0 mod 128 bytes rows 8-12 fell on
+  // the banks of rows 0-4 (2.0 wavefronts per store; now 1.0-1.1)
+  static constexpr int SBO = (KD_MAX / 8) * MMA_LBO + 16;
+  static constexpr int TILE_BYTES = 8 * SBO;   // one warpgroup's B tile: rows [hi | lo], up to 2 x 32 (DL: 16 c + 16 s)
+  // per warp and quadrature: float2 slots of the row -> item redistribution (32 MT variables per quadrant x 8 pairs,
+  // capped by 32 lanes x 11 items)
+  static constexpr int SCRATCH_ITEMS = MT == 1 ? 256 : 384;
+  static constexpr size_t SMEM = 2 * NV * sizeof(float) + 128 + 2 * (size_t)TILE_BYTES + (size_t)MMA_UW * 2 * SCRATCH_ITEMS * 8;
+};
+
+inline size_t mma_loop_smem_bytes(int mt) { return mt == 2 ? MmaLayout<2>::SMEM : MmaLayout<1>::SMEM; }
 
 // D[tmem] (+)= A[tmem] . B[smem]^T, A = 128 x 16 FP16 in tensor memory (lane = row, 32-bit column = two k)
 __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -77,11 +95,12 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 // shared-memory matrix descriptor: K-major, no swizzle; core matrices of 8 rows x 16 bytes
+template <int SBO>
 __device__ __forceinline__ uint64_t umma_desc_k_none(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);   // start address  [0,14)
   d |= (uint64_t)(MMA_LBO >> 4) << 16;           // leading byte offset: next 16-byte K chunk
-  d |= (uint64_t)(MMA_SBO >> 4) << 32;           // stride byte offset: next group of 8 rows
+  d |= (uint64_t)(SBO >> 4) << 32;               // stride byte offset: next group of 8 rows
   d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
   return d;                                      // layout type 0: SWIZZLE_NONE
 }
@@ -181,8 +200,7 @@ __device__ long long g_mma_trace[32 * 16];
 
 struct MmaLaunch {
   int kd;      // K extent of the contraction: n rounded up to a multiple of 16
-  int tcols;   // TMEM columns to allocate (power of two >= mt (MMA_D_COLS + kd))
-  int mt;      // M tiles of 128 variables (rows of D): 1 for n <= 128, else 2 (= the kernel's template argument MT)
+  int tcols;   // TMEM columns to allocate (power of two >= MT (MMA_D_COLS + kd)); MT = 1 for n <= 128, else 2: template argument
   int nbp;     // trajectory pairs per warpgroup (<= 8): a CTA advances 4 nbp trajectories
   int stagger; // warpgroup 1 starts half an iteration after warpgroup 0
 };
@@ -190,18 +208,28 @@ struct MmaLaunch {
 // Variables are dealt to the four TMEM lane quadrants round-robin, M tile by M tile: v = 128 m + 4 i + q is row 32 q + i of
 // M tile m (lane i of quadrant q), has the LOCAL index li = 32 m + i in its quadrant and sits at K position koff(q) + li
 // (quadrant by quadrant, no holes: a warp's stores hit consecutive K positions).  n <= 128: one M tile, li = i.
+// One M tile (MT = 1): v = 4 i + q, the plain expressions the n <= 128 kernels were tuned with.
 __device__ __forceinline__ int mma_qcount_tile(int n, int q, int m) {   // rows of quadrant q in M tile m
   const int r = n - 128 * m;
   return r <= 0 ? 0 : r >= 128 ? 32 : (r - q + 3) >> 2;
 }
-__device__ __forceinline__ int mma_qcount(int n, int q) { return mma_qcount_tile(n, q, 0) + mma_qcount_tile(n, q, 1); }
+template <int MT>
+__device__ __forceinline__ int mma_qcount(int n, int q) {
+  if constexpr (MT == 1) return (n - q + 3) >> 2;
+  else return mma_qcount_tile(n, q, 0) + mma_qcount_tile(n, q, 1);
+}
+template <int MT>
 __device__ __forceinline__ int mma_koff(int n, int q) {
   int o = 0;
-  for (int i = 0; i < q; ++i) o += mma_qcount(n, i);
+  for (int i = 0; i < q; ++i) o += mma_qcount<MT>(n, i);
   return o;
 }
 // (a second M tile exists only when the first is full: its local indices start at 32)
-__device__ __forceinline__ int mma_var(int li, int q) { return li < 32 ? 4 * li + q : 128 + 4 * (li - 32) + q; }
+template <int MT>
+__device__ __forceinline__ int mma_var(int li, int q) {
+  if constexpr (MT == 1) return 4 * li + q;
+  else return li < 32 ? 4 * li + q : 128 + 4 * (li - 32) + q;
+}
 
 // IPL: (variable, trajectory pair) items per lane.  A warp reads the rows of its TMEM lane quadrant (one variable per
 // lane, 18 of 32 lanes at n = 70) and deals the values out again through shared memory, so that EVERY lane owns
@@ -211,6 +239,9 @@ template <int SOLVER, bool ADAM, int IPL, int MT>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
     sde_mma_kernel(const SdeParams p, const MmaLaunch L, const FusedTail f) {
   constexpr int K = SolverTraits<SOLVER>::K;
+  using LY = MmaLayout<MT>;
+  constexpr int MMA_KD_MAX = LY::KD_MAX, MMA_SBO = LY::SBO, MMA_TILE_BYTES = LY::TILE_BYTES;
+  constexpr int MMA_SCRATCH_ITEMS = LY::SCRATCH_ITEMS, NV = LY::NV;
   constexpr int NR = 16 * K;   // B rows per half (hi | lo) and warpgroup (DL: c rows 0-15, s rows 16-31)
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) unsigned long long bars[5];
@@ -220,9 +251,9 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N = p.n, T = p.iterations, KD = L.kd, NBP = L.nbp;
   const int cta = blockIdx.x;
-  float* av = smem;                                                    // [256] alpha_v
-  float* hv = smem + 256;                                              // [256] affine term h_v
-  const uint32_t tiles = (smem_u32(smem) + 512 * 4 + 127u) & ~127u;    // [warpgroup] B tiles, rows [hi | lo]
+  float* av = smem;                                                    // [NV] alpha_v
+  float* hv = smem + NV;                                               // [NV] affine term h_v
+  const uint32_t tiles = (smem_u32(smem) + 2 * NV * 4 + 127u) & ~127u; // [warpgroup] B tiles, rows [hi | lo]
   uint8_t* tiles_g = reinterpret_cast<uint8_t*>(smem) + (tiles - smem_u32(smem));
   float2* scratch = reinterpret_cast<float2*>(tiles_g + 2 * MMA_TILE_BYTES);   // [warp][K][MMA_SCRATCH_ITEMS]
   const uint32_t bar0 = smem_u32(bars);
@@ -248,7 +279,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     build_schedule_cta(f.sa, mine);
     sched = mine;
   }
-  for (int j = tid; j < 256; j += MMA_THREADS)
+  for (int j = tid; j < NV; j += MMA_THREADS)
     av[j] = j < N ? p.a_half / (p.drift_s_vec ? p.drift_s_vec[j] : p.drift_s) : 0.f;
   for (int i = tid; i < 2 * MMA_TILE_BYTES / 16; i += MMA_THREADS)
     reinterpret_cast<float4*>(tiles_g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -286,7 +317,6 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   if (warp < 4) {
     // warpgroup 0 writes A = tau Qs^T (hi | lo) into tensor memory: lane 32 q + i of M tile m = row of variable
     // v = 128 m + 4 i + q, 32-bit column c = K positions 2 c (low half), 2 c + 1; K position P <-> input variable k
-    const int o1 = mma_koff(N, 1), o2 = mma_koff(N, 2), o3 = mma_koff(N, 3);
     for (int m = 0; m < MT; ++m) {
       const int v = 128 * m + 4 * lane + warp;
       const bool valid = v < N;
@@ -297,6 +327,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         aj = av[v];
         hv[v] = -aj * (p.b_half * cs + p.v[v]);
       }
+      const int o1 = mma_koff<MT>(N, 1), o2 = mma_koff<MT>(N, 2), o3 = mma_koff<MT>(N, 3);
       const uint32_t tl = a_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(m * KD);
       for (int c4 = 0; c4 < KD / 8; ++c4) {
         uint32_t hi[4], lo[4];
@@ -309,7 +340,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
             val[u] = 0.f;
             if (valid && P < N) {
               const int q = P >= o3 ? 3 : P >= o2 ? 2 : P >= o1 ? 1 : 0;
-              const int k = mma_var(P - (q == 3 ? o3 : q == 2 ? o2 : q == 1 ? o1 : 0), q);
+              const int k = mma_var<MT>(P - (q == 3 ? o3 : q == 2 ? o2 : q == 1 ? o1 : 0), q);
               val[u] = (-av[k] * aj * p.q[k * N + v]) * tau;
             }
           }
@@ -341,8 +372,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
     const int KS = KD / 16;
     auto issue = [&](int g) {
       if (elect_one()) {
-        const uint64_t b_hi = umma_desc_k_none(tiles + g * MMA_TILE_BYTES);
-        const uint64_t b_lo = umma_desc_k_none(tiles + g * MMA_TILE_BYTES + (NR / 8) * MMA_SBO);
+        const uint64_t b_hi = umma_desc_k_none<MMA_SBO>(tiles + g * MMA_TILE_BYTES);
+        const uint64_t b_lo = umma_desc_k_none<MMA_SBO>(tiles + g * MMA_TILE_BYTES + (NR / 8) * MMA_SBO);
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
           const uint32_t d_tmem = tbase + (uint32_t)(32 * (g * MT + m));
@@ -377,11 +408,11 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   } else {
     // ================================================================ update warpgroups
     const int g = warp >> 2, w4 = warp & 3;
-    const int cnt = mma_qcount(N, w4), koff = mma_koff(N, w4);   // this quadrant's variables mma_var(li, w4), li < cnt
+    const int cnt = mma_qcount<MT>(N, w4), koff = mma_koff<MT>(N, w4);   // this quadrant's variables mma_var(li, w4), li < cnt
     const int n_items = cnt * NBP;                                // (variable, pair) items: e = li * NBP + pair
     int cnt_tile[MT];                                             // ... of which in M tile m (lanes of this quadrant)
 #pragma unroll
-    for (int m = 0; m < MT; ++m) cnt_tile[m] = mma_qcount_tile(N, w4, m);
+    for (int m = 0; m < MT; ++m) cnt_tile[m] = MT == 1 ? cnt : mma_qcount_tile(N, w4, m);
     const long long b0 = (long long)cta * per_cta + (long long)g * 2 * NBP;   // first trajectory of the warpgroup
     const uint32_t tl = tbase + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(32 * g * MT);
     uint8_t* tile = tiles_g + (size_t)g * MMA_TILE_BYTES;
@@ -405,7 +436,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
       okj[j] = e < n_items;
       const int i = okj[j] ? e / NBP : 0;
       prj[j] = okj[j] ? e - i * NBP : 0;
-      vj[j] = mma_var(i, w4);
+      vj[j] = mma_var<MT>(i, w4);
       // K position in the B tile; idle slots run the same code on zeros and store where it cannot matter: just past
       // the K extent (the row groups are laid out for KD = MMA_KD_MAX, no MMA reads there), or for KD = MMA_KD_MAX at a K position
       // whose A column is zero (n <= P < KD; the value is finite: saturating conversion, clamped or cubic-saturated
@@ -522,6 +553,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         if constexpr (K == 2) tmem_ld_row32(tl + 32 * m, d);
         else tmem_ld_row16(tl + 32 * m, d);
         tmem_wait_ld();
+        if constexpr (MT == 1 && !CCVM_MMA_LATE_FENCE) {   // (one tile: before the redistribution stores, the order this loop was tuned in)
+          tc_fence_before();
+          if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
+        }
         if (lane < cnt_tile[m]) {
 #pragma unroll
           for (int pr = 0; pr < 8; ++pr) {
@@ -534,8 +569,10 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
           }
         }
       }
-      tc_fence_before();
-      if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
+      if constexpr (MT > 1 || CCVM_MMA_LATE_FENCE) {
+        tc_fence_before();
+        if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
+      }
       __syncwarp();
       pf2 gq[K][IPL];
 #pragma unroll

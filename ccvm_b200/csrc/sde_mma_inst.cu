@@ -16,7 +16,6 @@ static int launch_mma_tiles(const SdeParams& p, const MmaPlan& P, const FusedTai
   L.kd = P.kd;
   L.tcols = P.tcols;
   L.nbp = P.nbp;
-  L.mt = P.mt;
   L.stagger = P.stagger;
   kern<<<P.ctas, MMA_THREADS, P.smem, st>>>(p, L, f);
   CUDA_TRY(cudaGetLastError());
