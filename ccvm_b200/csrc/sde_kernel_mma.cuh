@@ -66,6 +66,10 @@ constexpr uint32_t MMA_STREAM_TAG = 0x40000000u;      // keeps these noise strea
 #ifndef CCVM_MMA_LATE_FENCE
 #define CCVM_MMA_LATE_FENCE 0
 #endif
+// one-tile kernels that take the late arrival anyway (bit = 2 solver + adam): DL settles 4 % faster with it at n = 70
+#ifndef CCVM_MMA_LATE_MASK
+#define CCVM_MMA_LATE_MASK 0x01
+#endif
 template <int MT_>
 struct MmaLayout {
   static constexpr int MT = CCVM_MMA_WIDE_LAYOUT ? 2 : MT_;
@@ -243,6 +247,8 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
   constexpr int MMA_KD_MAX = LY::KD_MAX, MMA_SBO = LY::SBO, MMA_TILE_BYTES = LY::TILE_BYTES;
   constexpr int MMA_SCRATCH_ITEMS = LY::SCRATCH_ITEMS, NV = LY::NV;
   constexpr int NR = 16 * K;   // B rows per half (hi | lo) and warpgroup (DL: c rows 0-15, s rows 16-31)
+  // tcgen05 fence + phase arrival behind the redistribution stores (else right after the accumulator read)
+  constexpr bool LATE = MT > 1 || CCVM_MMA_LATE_FENCE || ((CCVM_MMA_LATE_MASK >> (2 * SOLVER + (ADAM ? 1 : 0))) & 1) != 0;
   extern __shared__ __align__(16) float smem[];
   __shared__ __align__(8) unsigned long long bars[5];
   __shared__ uint32_t tmem_slot;
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
         if constexpr (K == 2) tmem_ld_row32(tl + 32 * m, d);
         else tmem_ld_row16(tl + 32 * m, d);
         tmem_wait_ld();
-        if constexpr (MT == 1 && !CCVM_MMA_LATE_FENCE) {   // (one tile: before the redistribution stores, the order this loop was tuned in)
+        if constexpr (!LATE) {   // (before the redistribution stores: the order the one-tile loops were tuned in)
           tc_fence_before();
           if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
         }
@@ -569,7 +575,7 @@ __global__ void __launch_bounds__(MMA_THREADS, 1)
           }
         }
       }
-      if constexpr (MT > 1 || CCVM_MMA_LATE_FENCE) {
+      if constexpr (LATE) {
         tc_fence_before();
         if (L.stagger && g == 0 && t == 0) mbar_arrive(phase_bar);
       }
