@@ -54,19 +54,19 @@ constexpr int MMA_LBO = 144;              // bytes between the two 16-byte K chu
 constexpr int MMA_D_COLS = 64;            // TMEM columns per M tile for the two warpgroups' accumulators (32 each)
 constexpr uint32_t MMA_STREAM_TAG = 0x40000000u;      // keeps these noise streams apart from the column-group streams
 
-// Shared-memory layout by the number of M tiles.  The one-tile kernels (n <= 128) keep the layout they were tuned with:
-// sized for two tiles, the same loop ran 14 % slower at n = 70 (DL-adam, B = 4096: 1.94 -> 2.21 ms,
-// profiles/r2zz_bench_n1_two_tile_layout.json) -- the strides are immediates of the staging stores and the register-bound
-// tiles (168 registers, 300 bytes of stack) pay for every change of the address arithmetic around them.
-// (tuning switches of that measurement: -DCCVM_MMA_WIDE_LAYOUT=1 sizes the one-tile kernels like the two-tile ones,
-//  -DCCVM_MMA_LATE_FENCE=1 moves their tcgen05 fence + phase arrival behind the redistribution stores)
+// Shared-memory layout by the number of M tiles: the one-tile kernels (n <= 128) are sized for K <= 128 (71 KB per CTA instead
+// of 107 KB).  Measured neutral for the loop time (+-1 %, profiles/r2zz_one_tile_layout_and_fence.txt); what did cost the
+// one-tile kernels 7-14 % after the two-tile extension was the point where warpgroup 0 releases warpgroup 1 (LATE below).
+// Tuning switches of that measurement: -DCCVM_MMA_WIDE_LAYOUT=1 sizes the one-tile kernels like the two-tile ones,
+// -DCCVM_MMA_LATE_FENCE=1 moves the tcgen05 fence + phase arrival of every kernel behind the redistribution stores.
 #ifndef CCVM_MMA_WIDE_LAYOUT
 #define CCVM_MMA_WIDE_LAYOUT 0
 #endif
 #ifndef CCVM_MMA_LATE_FENCE
 #define CCVM_MMA_LATE_FENCE 0
 #endif
-// one-tile kernels that take the late arrival anyway (bit = 2 solver + adam): DL settles 4 % faster with it at n = 70
+// one-tile kernels that take the late arrival anyway (bit = 2 solver + adam): DL settles 3-8 % faster with it (n = 70 ... 128),
+// DL-adam 7 % slower, the others within 1-3 % either way
 #ifndef CCVM_MMA_LATE_MASK
 #define CCVM_MMA_LATE_MASK 0x01
 #endif
